@@ -1,0 +1,10 @@
+"""bauklank-audio-stretch_b200: the Signalsmith-Stretch hot path of hanskerkhof/BAUKLANK-audio-stretch as
+hand-written CUDA for B200 (sm_100a), behind the reference's own operator surface.
+
+Import name: ``bauklank_audio_stretch_b200`` (the repo-root shim maps it onto this directory, whose name carries a
+hyphen as the project layout asks).
+"""
+from ._capi import load_library, Segment, EXPORTS  # noqa: F401
+from .batch import BatchStretch, KioskDrive, StreamingDrive, segment  # noqa: F401
+
+__all__ = ["BatchStretch", "KioskDrive", "StreamingDrive", "segment", "load_library", "Segment", "EXPORTS"]

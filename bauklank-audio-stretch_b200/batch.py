@@ -1,0 +1,164 @@
+"""Batched stretch engine: many independent streams with device-resident audio (Part 2 of the C ABI).
+
+Host code is plumbing only -- it describes each stream's *drive* the way the reference's worklet would perform it
+(``WasmProcessor.process``, app/SignalsmithStretch.mjs:826-954) and hands device pointers to the C ABI; the block
+schedule is compiled in C++ (``csrc/control.hpp``) and executed by the CUDA kernels (``csrc/kernels.cuh``).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+
+
+def segment(output=0.0, input=0.0, rate=1.0, semitones=0.0, tonality_hz=8000.0, formant_semitones=0.0,
+            formant_compensation=False, formant_base_hz=0.0, loop_start=0.0, loop_end=0.0, active=True):
+    """One time-map entry; defaults are the worklet's initial segment (app/SignalsmithStretch.mjs:587-600),
+    except ``active`` (a playing stream)."""
+    return _capi.Segment(float(output), float(input), float(rate), float(semitones), float(tonality_hz),
+                         float(formant_semitones), float(formant_base_hz), float(loop_start), float(loop_end),
+                         1 if active else 0, 1 if formant_compensation else 0)
+
+
+@dataclass
+class KioskDrive:
+    """Buffer playback: per render quantum ``seek(bufferLength, rate); process(0, quantum)`` (:883-943)."""
+    n_out: int
+    segments: Sequence = field(default_factory=lambda: [segment()])
+    quantum: int = 128
+    seed: int = 1
+
+
+@dataclass
+class StreamingDrive:
+    """``process(n_in, n_out)`` ``n_calls`` times over a contiguous input (:870-882 generalised)."""
+    n_in: int
+    n_out: int
+    n_calls: int
+    segments: Sequence = field(default_factory=lambda: [segment()])
+    seed: int = 1
+
+    @property
+    def total_out(self):
+        return self.n_out * self.n_calls
+
+
+def _ptr(a):
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _alloc_like(clip, channels, n):
+    if hasattr(clip, "data_ptr"):
+        import torch
+        return torch.zeros((channels, n), dtype=torch.float32, device=clip.device)
+    return np.zeros((channels, n), np.float32)
+
+
+class BatchStretch:
+    """N independent streams sharing one engine configuration (presetDefault / presetCheaper / configure)."""
+
+    def __init__(self, channels, sample_rate=48000.0, preset="default", block_samples=None, interval_samples=None,
+                 split_computation=False, lib=None):
+        self.lib = lib or _capi.load_library()
+        self.channels = int(channels)
+        self.sample_rate = float(sample_rate)
+        if block_samples is not None:
+            if interval_samples is None:
+                interval_samples = int(round(block_samples * 0.25))
+            self.h = self.lib.bsb_create(channels, int(block_samples), int(interval_samples),
+                                         1 if split_computation else 0, self.sample_rate)
+        else:
+            self.h = self.lib.bsb_create_preset(channels, self.sample_rate, 1 if preset == "cheaper" else 0)
+        if not self.h:
+            raise RuntimeError("bsb_create failed (no CUDA device, or unsupported configuration)")
+        self._keep = []
+        self.outputs = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bsb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # the reference's getters
+    def blockSamples(self): return self.lib.bsb_block_samples(self.h)
+    def intervalSamples(self): return self.lib.bsb_interval_samples(self.h)
+    def inputLatency(self): return self.lib.bsb_input_latency(self.h)
+    def outputLatency(self): return self.lib.bsb_output_latency(self.h)
+    def fftSamples(self): return self.lib.bsb_fft_samples(self.h)
+    def bands(self): return self.lib.bsb_bands(self.h)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("bauklank_stretch: " + self.lib.bsb_last_error(self.h).decode())
+
+    def plan(self, clips, drives, chunk_blocks=0, outputs=None):
+        """clips[i]: float32 [channels, len] in device memory (torch CUDA tensor); drives[i]: Kiosk/StreamingDrive.
+        Returns the list of output tensors [channels, n_out] (allocated here unless given)."""
+        assert len(clips) == len(drives) and len(clips) > 0
+        self._check(self.lib.bsb_begin(self.h, len(clips)))
+        self._keep = []
+        outs = []
+        for i, (clip, d) in enumerate(zip(clips, drives)):
+            assert tuple(clip.shape)[0] == self.channels and len(clip.shape) == 2
+            if hasattr(clip, "is_contiguous"):
+                assert clip.is_contiguous() and str(clip.dtype) == "torch.float32"
+            else:
+                assert clip.flags["C_CONTIGUOUS"] and clip.dtype == np.float32
+            clip_len = int(clip.shape[1])
+            segs = (_capi.Segment * len(d.segments))(*d.segments)
+            if isinstance(d, KioskDrive):
+                n_out = int(d.n_out)
+                out = outputs[i] if outputs is not None else _alloc_like(clip, self.channels, n_out)
+                self._check(self.lib.bsb_add_kiosk(self.h, i, _ptr(clip), clip_len, _ptr(out), n_out, int(d.quantum),
+                                                   segs, len(d.segments), int(d.seed) & 0xFFFFFFFF))
+            else:
+                n_out = int(d.total_out)
+                out = outputs[i] if outputs is not None else _alloc_like(clip, self.channels, n_out)
+                self._check(self.lib.bsb_add_streaming(self.h, i, _ptr(clip), clip_len, _ptr(out), int(d.n_in),
+                                                       int(d.n_out), int(d.n_calls), segs, len(d.segments),
+                                                       int(d.seed) & 0xFFFFFFFF))
+            self._keep.append((clip, out, segs))
+            outs.append(out)
+        self._check(self.lib.bsb_commit(self.h, int(chunk_blocks)))
+        self.outputs = outs
+        return outs
+
+    def rebind(self, i, clip, out):
+        self._check(self.lib.bsb_rebind(self.h, i, _ptr(clip), _ptr(out)))
+        self._keep[i] = (clip, out, self._keep[i][2])
+        self.outputs[i] = out
+
+    def run(self, cuda_stream=None):
+        """Execute every block of every stream.  ``cuda_stream``: a raw cudaStream_t (int); default = torch's
+        current stream when torch tensors are in use, else the null stream."""
+        if cuda_stream is None:
+            cuda_stream = 0
+            if self._keep and hasattr(self._keep[0][0], "data_ptr"):
+                import torch
+                cuda_stream = torch.cuda.current_stream().cuda_stream
+        self._check(self.lib.bsb_run(self.h, C.c_void_p(cuda_stream)))
+        return self.outputs
+
+    def total_blocks(self): return self.lib.bsb_total_blocks(self.h)
+    def stream_blocks(self, i): return self.lib.bsb_stream_blocks(self.h, i)
+    def chunk_blocks(self): return self.lib.bsb_chunk_blocks(self.h)
+    def launch_count(self): return self.lib.bsb_launch_count(self.h)
+
+    def kernel_ms(self):
+        a = (C.c_float * 3)()
+        self.lib.bsb_kernel_ms(self.h, a)
+        return dict(analysis=a[0], spectral=a[1], synthesis=a[2])
+
+    def block_info(self, stream, block):
+        a = (C.c_longlong * 8)()
+        if self.lib.bsb_block_info(self.h, stream, block, a) != 0:
+            raise IndexError("no such block")
+        tf = np.array([a[1]], np.uint32).view(np.float32)[0]
+        return dict(flags=int(a[0]), timeFactor=float(tf), cur=(int(a[2]), int(a[3]), int(a[4])),
+                    prev=(int(a[5]), int(a[6]), int(a[7])))

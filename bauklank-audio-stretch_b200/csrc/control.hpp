@@ -1,0 +1,233 @@
+// Host-side control plane of one stream: an exact, data-free emulation of the reference engine's block scheduling
+// (W#48 process control, W#49 seek, setters W#50-54) and of the worklet's time map arithmetic
+// (app/SignalsmithStretch.mjs:826-954).  It produces, for every analysis/synthesis block, a BlockRec (flags,
+// timeFactor, the parameter values each spectral step will see) and two Window descriptors saying where in the
+// stream's clip the "current" and "previous" analysis windows come from.  That table is what makes frame/hop
+// indexing bit-exact on the GPU: all integer and rounding rules live here, in f32/f64 exactly as the reference.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "tables.hpp"
+
+namespace bs {
+
+enum : uint32_t { kNew = 1u, kMapped = 2u, kFormants = 4u, kFormantComp = 8u, kValid = 16u };
+
+// One block of one stream, as consumed by the spectral kernel (32 bytes).
+struct BlockRec {
+  uint32_t flags;
+  float timeFactor;
+  float pkMult, pkLimit;    // freqMultiplier / freqTonalityLimit seen by findPeaks (mapped step 3)
+  float fmBaseFreq;         // formantBaseFreq seen by formant step 0
+  float fmMult, fmInv;      // formantMultiplier / invFormantMultiplier seen by formant step 2
+  float fmFreqMult;         // freqMultiplier seen by formant step 2 (fmLimit below)
+};
+struct BlockRec2 { float fmLimit; float pad[3]; };  // kept separate so BlockRec stays 32 B
+// sample i (0 <= i < L) of a window = (lo <= i < hi) ? clip[ch][start + i] : 0
+struct Window { long long start; int lo, hi; };
+
+struct Params {  // what the setters store (W#50-54)
+  float freqMult = 1.f, tonLimit = 0.5f, formantMult = 1.f, formantInv = 1.f, formantBase = 0.f;
+  int formantComp = 0;
+  void setTransposeFactor(float m, float tl) { freqMult = m; tonLimit = (tl <= 0.f) ? 1.f : (tl / sqrtf(m)); }
+  void setTransposeSemitones(float st, float tl) { setTransposeFactor((float)exp2((double)(st * 0x1.555556p-4f)), tl); }
+  void setFormantFactor(float m, int comp) { formantMult = m; formantComp = comp & 0xff; formantInv = 1.f / m; }
+  void setFormantSemitones(float st, int comp) { setFormantFactor((float)exp2((double)(st * 0x1.555556p-4f)), comp); }
+  void setFormantBase(float f) { formantBase = f; }
+};
+
+// Mirrors one timeMap entry of the worklet (app/SignalsmithStretch.mjs:587-600), all JS numbers = double.
+struct Segment {
+  double output, input, rate;
+  double semitones, tonalityHz, formantSemitones, formantBaseHz, loopStart, loopEnd;
+  int active, formantCompensation;
+};
+
+struct StreamPlan {
+  std::vector<BlockRec> blocks;
+  std::vector<BlockRec2> blocks2;
+  std::vector<Window> windows;  // 2 per block: cur, prev
+  long long nOut = 0;
+};
+
+class Control {
+ public:
+  explicit Control(const Geometry &g) : g_(g) {}
+  Params p;
+
+  // W#49 seek: only its control effects (the ring provenance is the caller's business)
+  void seek(double rate) {
+    didSeek_ = true;
+    double dH = (double)(uint32_t)g_.H;
+    seekTF_ = (float)(((rate * dH) > 1.0) ? (1.0 / rate) : dH);
+  }
+
+  // Emulates `count` output samples of one process(nIn, nOut) call starting at output index idx0, during which the
+  // parameters `p` do not change.  onStart(idx, inputOffset, inputInterval, rec index) is called when a block starts.
+  template <class StartFn>
+  void run(StreamPlan &plan, int idx0, int count, int nIn, int nOut, StartFn &&onStart) {
+    const int H = g_.H, C = g_.C;
+    float invOut = 1.0f / (float)(uint32_t)nOut, fIn = (float)nIn;
+    int idx = idx0, end = idx0 + count;
+    while (idx < end) {
+      if (since_ >= (uint32_t)H) {
+        step_ = 0; since_ = 0; steps_ = 0;
+        float r = roundf(((float)(uint32_t)idx * fIn) * invOut);
+        int inputOffset = std::fabs(r) < 2147483648.0f ? (int)r : INT32_MIN;
+        int interval = inputOffset - prevInputOffset_;
+        prevInputOffset_ = inputOffset;
+        bool isNew = didSeek_ || interval > 0;
+        bool mapped = p.freqMult != 1.0f;
+        bool rean = false;
+        if (isNew) {
+          rean = didSeek_ || std::abs(interval - H) > 1;
+          if (rean) steps_ += C + 1;
+          steps_ += C + 1;
+        }
+        bool formants = (p.formantMult == 1.0f) ? (p.formantComp && mapped) : true;
+        float tf;
+        if (didSeek_) tf = seekTF_;
+        else { float fi = (float)interval; tf = (float)(uint32_t)H / (fi > 1.0f ? fi : 1.0f); }
+        didSeek_ = false;
+        int specSteps = C + (isNew ? 10 : 9) + (isNew ? C : 0) + (mapped ? 4 : 0) + (formants ? 3 : 0);
+        int analysisSteps = steps_;
+        steps_ = C + (specSteps + steps_) + 1;
+        // absolute indices of the parameter-reading steps
+        int s0 = analysisSteps + (isNew ? C : 0);
+        stepPeaks_ = mapped ? s0 + 3 : -1;
+        int f0 = s0 + (mapped ? 5 : 1);
+        stepFm0_ = formants ? f0 : -1;
+        stepFm2_ = formants ? f0 + 2 : -1;
+        BlockRec rec{};
+        rec.flags = kValid | (isNew ? kNew : 0u) | (mapped ? kMapped : 0u) | (formants ? kFormants : 0u);
+        rec.timeFactor = tf;
+        plan.blocks.push_back(rec);
+        plan.blocks2.push_back(BlockRec2{});
+        plan.windows.push_back(Window{0, 0, 0});
+        plan.windows.push_back(Window{0, 0, 0});
+        cur_ = (long long)plan.blocks.size() - 1;
+        onStart(idx, inputOffset, interval, rean, isNew, cur_);
+      }
+      // samples until the next block start or the end of this span
+      int span = std::min<long long>(end - idx, (long long)H - (long long)since_);
+      int toStep;
+      if (g_.split) {
+        float pr = (((float)(uint32_t)steps_ + 0.999f) * (float)(uint32_t)(since_ + (uint32_t)span)) / (float)(uint32_t)H;
+        uint32_t lim = (pr < 4294967296.0f && pr >= 0.0f) ? (uint32_t)pr : 0u;
+        toStep = lim > (uint32_t)steps_ ? steps_ : (int)lim;
+      } else {
+        toStep = steps_;
+      }
+      if (cur_ >= 0 && toStep > step_) snapshot(plan, step_, toStep);
+      if (toStep > step_) step_ = toStep;
+      since_ += (uint32_t)span;
+      idx += span;
+    }
+  }
+  void endCall(int nIn) { prevInputOffset_ -= nIn; }
+
+ private:
+  void snapshot(StreamPlan &plan, int from, int to) {
+    BlockRec &r = plan.blocks[cur_];
+    if (stepPeaks_ >= from && stepPeaks_ < to) { r.pkMult = p.freqMult; r.pkLimit = p.tonLimit; }
+    if (stepFm0_ >= from && stepFm0_ < to) r.fmBaseFreq = p.formantBase;
+    if (stepFm2_ >= from && stepFm2_ < to) {
+      r.fmMult = p.formantMult; r.fmInv = p.formantInv; r.fmFreqMult = p.freqMult;
+      plan.blocks2[cur_].fmLimit = p.tonLimit;
+      if (p.formantComp == 1) r.flags |= kFormantComp;
+    }
+  }
+  Geometry g_;
+  uint32_t since_ = 0xffffffffu;
+  int steps_ = 0, step_ = 0;
+  int prevInputOffset_ = -1;
+  bool didSeek_ = false;
+  float seekTF_ = 0.f;
+  int stepPeaks_ = -1, stepFm0_ = -1, stepFm2_ = -1;
+  long long cur_ = -1;
+};
+
+inline void apply_segment_params(Params &p, const Segment &s, double sampleRate) {
+  // WasmProcessor.process, app/SignalsmithStretch.mjs:847-849 (JS doubles -> f32 at the wasm call boundary)
+  p.setTransposeSemitones((float)s.semitones, (float)(s.tonalityHz / sampleRate));
+  p.setFormantSemitones((float)s.formantSemitones, s.formantCompensation ? 1 : 0);
+  p.setFormantBase((float)(s.formantBaseHz / sampleRate));
+}
+
+inline Window clip_window(long long start, int L, int validFrom, long long clipLen) {
+  Window w; w.start = start;
+  long long lo = std::max<long long>(validFrom, -start), hi = std::min<long long>(L, clipLen - start);
+  if (lo < 0) lo = 0;
+  if (hi < lo) hi = lo;
+  w.lo = (int)lo; w.hi = (int)hi;
+  return w;
+}
+
+// Buffer-playback drive of the worklet (app/SignalsmithStretch.mjs:883-943): every quantum `_seek(bufferLength, rate)`
+// then `_process(0, q)`.  `segs` is the (already ordered) time map; currentTime = k*quantum/sampleRate.
+inline void plan_kiosk(const Geometry &g, double sampleRate, int quantum, long long nOut, long long clipLen,
+                       const Segment *segs, int nSegs, StreamPlan &plan) {
+  Control ctl(g);
+  const int L = g.L, H = g.H, cap = L + H;
+  const int bufLen = g.inLat + g.outLat;
+  const double inLatS = (double)g.inLat / sampleRate, outLatS = (double)g.outLat / sampleRate;
+  std::vector<Segment> tm(segs, segs + nSegs);
+  size_t si = 0;
+  plan.nOut = nOut;
+  long long pos = 0;
+  for (long long k = 0; pos < nOut; ++k) {
+    int q = (int)std::min<long long>(quantum, nOut - pos);
+    double currentTime = (double)(k * quantum) / sampleRate;
+    double outputTime = currentTime + outLatS;
+    while (si + 1 < tm.size() && tm[si + 1].output <= outputTime) ++si;
+    Segment &seg = tm[si];
+    apply_segment_params(ctl.p, seg, sampleRate);
+    double inputTime = seg.input + (outputTime - seg.output) * seg.rate;
+    double loopLength = seg.loopEnd - seg.loopStart;
+    if (loopLength > 0 && inputTime >= seg.loopEnd) { seg.input -= loopLength; inputTime -= loopLength; }
+    inputTime += inLatS;
+    long long end = (long long)std::floor(inputTime * sampleRate + 0.5);  // Math.round
+    ctl.seek(seg.rate);
+    int n = std::min(bufLen, cap);  // samples of pre-roll that seek() keeps
+    ctl.run(plan, 0, q, 0, q, [&](int, int, int, bool, bool isNew, long long bi) {
+      if (!isNew) return;  // spectra are carried over (flag kNew clear)
+      // ring after seek = [zeros(cap-n)][clip[end-n, end)]; cur = last L of it, prev = the L ending H earlier
+      plan.windows[2 * bi + 0] = clip_window(end - L, L, (cap - n) - H, clipLen);
+      plan.windows[2 * bi + 1] = clip_window(end - cap, L, cap - n, clipLen);
+    });
+    ctl.endCall(0);
+    pos += q;
+  }
+}
+
+// Streaming drive (live-input branch generalised): process(nIn, nOut) over a contiguous input, no seek.
+// Parameter segments are keyed by the output time of the first sample of a call.
+inline void plan_stream(const Geometry &g, double sampleRate, int nIn, int nOut, long long nCalls, long long clipLen,
+                        const Segment *segs, int nSegs, StreamPlan &plan) {
+  Control ctl(g);
+  const int L = g.L, H = g.H;
+  size_t si = 0;
+  plan.nOut = nCalls * nOut;
+  long long lastEnd = 0;   // stream position of the most recently analysed "current" window end
+  bool haveLast = false;
+  for (long long k = 0; k < nCalls; ++k) {
+    double t = (double)(k * nOut) / sampleRate;
+    while ((int)si + 1 < nSegs && segs[si + 1].output <= t) ++si;
+    apply_segment_params(ctl.p, segs[si], sampleRate);
+    long long base = k * nIn;
+    ctl.run(plan, 0, nOut, nIn, nOut, [&](int, int inputOffset, int, bool rean, bool isNew, long long bi) {
+      if (!isNew) return;
+      long long P = base + inputOffset;
+      long long prevEnd = (rean || !haveLast) ? P - H : lastEnd;
+      plan.windows[2 * bi + 0] = clip_window(P - L, L, 0, clipLen);
+      plan.windows[2 * bi + 1] = clip_window(prevEnd - L, L, 0, clipLen);
+      lastEnd = P; haveLast = true;
+    });
+    ctl.endCall(nIn);
+  }
+}
+
+}  // namespace bs

@@ -1,0 +1,398 @@
+// Host side of libbauklank_stretch.so: batched engine (Part 2 of include/bauklank_stretch.h) and kernel launchers.
+// Built by nvcc for sm_100a (product) or, with -DBS_HOSTEMU, by g++ as the serial test emulation of the same code.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/bauklank_stretch.h"
+#include "kernels.cuh"
+
+#ifndef BS_HOSTEMU
+#include <cuda_runtime.h>
+#endif
+
+namespace bs {
+
+// ---------------------------------------------------------------------------------- memory / launch abstraction
+#ifdef BS_HOSTEMU
+typedef void *stream_t;
+static bool dev_ok(std::string &) { return true; }
+static void *dmalloc(size_t n) { return std::calloc(1, n ? n : 1); }
+static void dfree(void *p) { std::free(p); }
+static void dzero(void *p, size_t n, stream_t) { std::memset(p, 0, n); }
+static void h2d(void *d, const void *h, size_t n, stream_t) { std::memcpy(d, h, n); }
+#else
+typedef cudaStream_t stream_t;
+static bool dev_ok(std::string &err) {
+  int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { err = std::string("no CUDA device: ") + cudaGetErrorString(e); return false; }
+  return true;
+}
+static void *dmalloc(size_t n) {
+  void *p = nullptr;
+  if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr;
+  return p;
+}
+static void dfree(void *p) { if (p) cudaFree(p); }
+static void dzero(void *p, size_t n, stream_t s) { cudaMemsetAsync(p, 0, n, s); }
+static void h2d(void *d, const void *h, size_t n, stream_t s) { cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s); }
+
+__global__ void __launch_bounds__(256) analysis_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                       const Window *windows, int slot0, int nSlots, cf *specIn) {
+  extern __shared__ float sm[];
+  int idx = blockIdx.x;
+  const int c = idx % g.C; idx /= g.C;
+  const int which = idx & 1; idx >>= 1;
+  const int slot = idx % nSlots; const int s = idx / nSlots;
+  const StreamDev sd = streams[s];
+  const long long m = (long long)slot0 + slot;
+  if (m >= sd.nBlocks) return;
+  if (!(blocks[sd.blockBase + m].flags & kNew)) return;
+  const Window w = windows[2 * (sd.blockBase + m) + which];
+  cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * g.B;
+  analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) spectral_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                       const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, cf *specOut,
+                                                       StateDev st) {
+  extern __shared__ float sm[];
+  const int s = blockIdx.x;
+  const StreamDev sd = streams[s];
+  const size_t CB = (size_t)g.C * g.B;
+  for (int t = 0; t < nSlots; ++t) {
+    const long long m = (long long)slot0 + t;
+    if (m >= sd.nBlocks) break;
+    const BlockRec rec = blocks[sd.blockBase + m];
+    const BlockRec2 rec2 = blocks2[sd.blockBase + m];
+    const bool keep = (m + 1 < sd.nBlocks) && !(blocks[sd.blockBase + m + 1].flags & kNew);
+    const cf *cur = specIn + (((size_t)s * nSlots + t) * 2 + 0) * CB;
+    const cf *prev = specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB;
+    spectral_block(g, T, rec, rec2, cur, prev, st.outSpec + s * CB, st.predE + s * CB, st.lastInput + s * CB, st.rng + s,
+                   st.freqEst + 2 * s, st.inEnergy + s * CB, st.map + (size_t)s * g.B * 2, st.predIn + s * CB,
+                   st.terms + (size_t)s * g.B * nterms(g.C), st.peaks + (size_t)s * g.B * 2,
+                   specOut + ((size_t)s * nSlots + t) * CB, keep, sm, threadIdx.x, blockDim.x);
+  }
+}
+
+__global__ void __launch_bounds__(256) synthesis_kernel(DevGeom g, DevTables T, const StreamDev *streams, int slot0, int nSlots,
+                                                        const cf *specOut, StateDev st) {
+  extern __shared__ float sm[];
+  const int s = blockIdx.x / g.C, c = blockIdx.x % g.C;
+  const StreamDev sd = streams[s];
+  float *ring = sm + 4 * (size_t)g.M;
+  synth_stream(g, T, sd, c, slot0, nSlots, specOut + (size_t)s * nSlots * g.C * g.B, st.ring + ((size_t)s * g.C + c) * g.L, sm, ring,
+               threadIdx.x, blockDim.x);
+}
+#endif
+
+struct Stream {
+  const float *clip = nullptr; float *out = nullptr; long long clipLen = 0; uint32_t seed = 1;
+  StreamPlan plan; bool planned = false;
+};
+
+}  // namespace bs
+
+using namespace bs;
+
+struct bsb_engine {
+  Geometry g; Tables T; double sampleRate = 48000.0;
+  DevGeom dg{}; DevTables dt{};
+  std::vector<void *> owned;      // device allocations of the tables
+  std::vector<void *> batchOwned; // device allocations of the current batch
+  std::vector<Stream> streams;
+  std::vector<StreamDev> hs;
+  StreamDev *dStreams = nullptr; BlockRec *dBlocks = nullptr; BlockRec2 *dBlocks2 = nullptr; Window *dWindows = nullptr;
+  uint32_t *dSeeds = nullptr;
+  StateDev st{}; cf *specIn = nullptr, *specOut = nullptr;
+  int chunk = 0; long long maxBlocks = 0, totalBlocks = 0, launches = 0;
+  std::vector<long long> blockBase;
+  bool committed = false;
+  float kms[3] = {0, 0, 0};
+#ifndef BS_HOSTEMU
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+#endif
+  std::string err;
+  int fail(const char *fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    err = buf; return -1;
+  }
+};
+
+template <class T>
+static T *upload(bsb_engine *e, const std::vector<T> &v, std::vector<void *> &owner) {
+  T *d = (T *)dmalloc(v.size() * sizeof(T));
+  if (!d) return nullptr;
+  owner.push_back(d);
+  h2d(d, v.data(), v.size() * sizeof(T), 0);
+  return d;
+}
+template <class T>
+static T *dalloc(size_t n, std::vector<void *> &owner) {
+  T *d = (T *)dmalloc(n * sizeof(T));
+  if (d) owner.push_back(d);
+  return d;
+}
+
+static void free_batch(bsb_engine *e) {
+  for (void *p : e->batchOwned) dfree(p);
+  e->batchOwned.clear(); e->committed = false;
+}
+
+extern "C" {
+
+bsb_engine *bsb_create(int channels, int block, int interval, int split, double sampleRate) {
+  std::string err;
+  if (channels < 1 || channels > 8 || block < 8 || interval < 1 || interval > block) return nullptr;
+  if (!dev_ok(err)) { std::fprintf(stderr, "bauklank_stretch: %s\n", err.c_str()); return nullptr; }
+  bsb_engine *e = new bsb_engine();
+  e->sampleRate = sampleRate;
+  e->g = make_geometry(channels, block, interval, split);
+  if (e->g.longStep < 1 || e->g.longStep > 32) { delete e; return nullptr; }
+  make_tables(e->g, e->T);
+  const Geometry &g = e->g;
+  e->dg = DevGeom{g.C, g.L, g.H, g.N, g.B, g.M, g.inner, g.outer, g.split, g.longStep, g.L >> 1, (int)e->T.wpStart.size()};
+  e->dt.win = upload(e, e->T.win, e->owned); e->dt.tw = upload(e, e->T.tw, e->owned);
+  e->dt.otr = upload(e, e->T.otr, e->owned); e->dt.oti = upload(e, e->T.oti, e->owned);
+  e->dt.untangle = upload(e, e->T.untangle, e->owned); e->dt.rot = upload(e, e->T.rot, e->owned);
+  e->dt.specRot = upload(e, e->T.specRot, e->owned);
+  e->dt.wpStart = upload(e, e->T.wpStart, e->owned); e->dt.wpSteady = upload(e, e->T.wpSteady, e->owned);
+#ifndef BS_HOSTEMU
+  for (auto &ev : e->ev) cudaEventCreate(&ev);
+  const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
+  const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float);
+  if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
+      cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY) != cudaSuccess ||
+      cudaFuncSetAttribute(spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smS) != cudaSuccess) {
+    std::fprintf(stderr, "bauklank_stretch: block size %d needs more shared memory than one SM has\n", block);
+    bsb_destroy(e); return nullptr;
+  }
+#endif
+  return e;
+}
+
+bsb_engine *bsb_create_preset(int channels, double sampleRate, int cheaper) {
+  // W#58 presetDefault / W#57 presetCheaper: f64 multiply then truncate; the wasm ABI passes sampleRate as f32
+  double d = (double)(float)sampleRate;
+  if (cheaper) return bsb_create(channels, (int)(d * 0.1), (int)(d * 0.04), 1, sampleRate);
+  return bsb_create(channels, (int)(d * 0.12), (int)(d * 0.03), 0, sampleRate);
+}
+
+void bsb_destroy(bsb_engine *e) {
+  if (!e) return;
+  free_batch(e);
+  for (void *p : e->owned) dfree(p);
+#ifndef BS_HOSTEMU
+  for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+#endif
+  delete e;
+}
+int bsb_block_samples(const bsb_engine *e) { return e->g.L; }
+int bsb_interval_samples(const bsb_engine *e) { return e->g.H; }
+int bsb_input_latency(const bsb_engine *e) { return e->g.inLat; }
+int bsb_output_latency(const bsb_engine *e) { return e->g.outLat; }
+int bsb_fft_samples(const bsb_engine *e) { return e->g.N; }
+int bsb_bands(const bsb_engine *e) { return e->g.B; }
+const char *bsb_last_error(const bsb_engine *e) { return e->err.c_str(); }
+long long bsb_total_blocks(const bsb_engine *e) { return e->totalBlocks; }
+long long bsb_stream_blocks(const bsb_engine *e, int s) { return (s >= 0 && s < (int)e->streams.size()) ? (long long)e->streams[s].plan.blocks.size() : -1; }
+int bsb_chunk_blocks(const bsb_engine *e) { return e->chunk; }
+long long bsb_launch_count(const bsb_engine *e) { return e->launches; }
+int bsb_kernel_ms(const bsb_engine *e, float out[3]) { for (int i = 0; i < 3; ++i) out[i] = e->kms[i]; return 0; }
+
+int bsb_begin(bsb_engine *e, int n) {
+  if (n < 1) return e->fail("n_streams must be >= 1");
+  free_batch(e);
+  e->streams.assign(n, Stream());
+  return 0;
+}
+
+static int check_segments(bsb_engine *e, const bsb_segment *segs, int n) {
+  if (!segs || n < 1) return e->fail("at least one time-map segment is required");
+  for (int i = 0; i < n; ++i) {
+    if (!segs[i].active) return e->fail("inactive time-map segments are not supported by the batched path");
+    if (i && segs[i].output < segs[i - 1].output) return e->fail("time-map segments must be ordered by output time");
+  }
+  return 0;
+}
+static std::vector<Segment> to_segments(const bsb_segment *s, int n) {
+  std::vector<Segment> v(n);
+  for (int i = 0; i < n; ++i)
+    v[i] = Segment{s[i].output, s[i].input, s[i].rate, s[i].semitones, s[i].tonality_hz, s[i].formant_semitones,
+                   s[i].formant_base_hz, s[i].loop_start, s[i].loop_end, s[i].active, s[i].formant_compensation};
+  return v;
+}
+
+int bsb_add_kiosk(bsb_engine *e, int si, const float *dClip, long long clipLen, float *dOut, long long nOut, int quantum,
+                  const bsb_segment *segs, int nSegs, uint32_t seed) {
+  if (si < 0 || si >= (int)e->streams.size()) return e->fail("stream index out of range");
+  if (quantum < 1 || nOut < 0 || clipLen < 0) return e->fail("bad sizes");
+  if (check_segments(e, segs, nSegs)) return -1;
+  Stream &s = e->streams[si];
+  s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
+  auto v = to_segments(segs, nSegs);
+  plan_kiosk(e->g, e->sampleRate, quantum, nOut, clipLen, v.data(), nSegs, s.plan);
+  s.planned = true; e->committed = false;
+  return 0;
+}
+
+int bsb_add_streaming(bsb_engine *e, int si, const float *dClip, long long clipLen, float *dOut, int nIn, int nOut, long long nCalls,
+                      const bsb_segment *segs, int nSegs, uint32_t seed) {
+  if (si < 0 || si >= (int)e->streams.size()) return e->fail("stream index out of range");
+  if (nIn < 1 || nOut < 1 || nCalls < 0 || nCalls * nIn > clipLen) return e->fail("bad sizes (n_calls*n_in must fit the clip)");
+  if (check_segments(e, segs, nSegs)) return -1;
+  Stream &s = e->streams[si];
+  s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
+  auto v = to_segments(segs, nSegs);
+  plan_stream(e->g, e->sampleRate, nIn, nOut, nCalls, clipLen, v.data(), nSegs, s.plan);
+  s.planned = true; e->committed = false;
+  return 0;
+}
+
+int bsb_rebind(bsb_engine *e, int si, const float *dClip, float *dOut) {
+  if (!e->committed || si < 0 || si >= (int)e->streams.size()) return e->fail("rebind needs a committed batch and a valid stream");
+  e->streams[si].clip = dClip; e->streams[si].out = dOut;
+  e->hs[si].clip = dClip; e->hs[si].out = dOut;
+  h2d(e->dStreams + si, &e->hs[si], sizeof(StreamDev), 0);
+  return 0;
+}
+
+int bsb_commit(bsb_engine *e, int chunkBlocks) {
+  const Geometry &g = e->g;
+  const int S = (int)e->streams.size();
+  if (S < 1) return e->fail("no batch: call bsb_begin first");
+  free_batch(e);
+  std::vector<BlockRec> blocks; std::vector<BlockRec2> blocks2; std::vector<Window> windows; std::vector<uint32_t> seeds(S);
+  e->hs.assign(S, StreamDev{}); e->blockBase.assign(S, 0); e->maxBlocks = 0;
+  for (int s = 0; s < S; ++s) {
+    Stream &st = e->streams[s];
+    if (!st.planned) return e->fail("stream %d was not added", s);
+    e->blockBase[s] = (long long)blocks.size();
+    blocks.insert(blocks.end(), st.plan.blocks.begin(), st.plan.blocks.end());
+    blocks2.insert(blocks2.end(), st.plan.blocks2.begin(), st.plan.blocks2.end());
+    windows.insert(windows.end(), st.plan.windows.begin(), st.plan.windows.end());
+    StreamDev &d = e->hs[s];
+    d.clip = st.clip; d.out = st.out; d.clipLen = st.clipLen; d.nOut = st.plan.nOut; d.blockBase = e->blockBase[s];
+    d.nBlocks = (int)st.plan.blocks.size();
+    e->maxBlocks = std::max<long long>(e->maxBlocks, d.nBlocks);
+    uint32_t sd = st.seed % 2147483647u; seeds[s] = sd <= 1u ? 1u : sd;   // W#26: minstd_rand seeding
+  }
+  e->totalBlocks = (long long)blocks.size();
+  if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
+  const size_t CB = (size_t)g.C * g.B;
+  const size_t perSlot = (size_t)S * CB * sizeof(cf) * 3;   // specIn (cur+prev) + specOut
+  if (chunkBlocks <= 0) {
+    const size_t budget = (size_t)6 << 30;
+    chunkBlocks = (int)std::min<size_t>(64, std::max<size_t>(1, budget / perSlot));
+  }
+  if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
+  e->chunk = chunkBlocks;
+  auto &own = e->batchOwned;
+  e->dStreams = upload(e, e->hs, own); e->dBlocks = upload(e, blocks, own); e->dBlocks2 = upload(e, blocks2, own);
+  e->dWindows = upload(e, windows, own); e->dSeeds = upload(e, seeds, own);
+  e->specIn = dalloc<cf>((size_t)S * chunkBlocks * 2 * CB, own);
+  e->specOut = dalloc<cf>((size_t)S * chunkBlocks * CB, own);
+  StateDev &st = e->st;
+  st.outSpec = dalloc<cf>(S * CB, own); st.predE = dalloc<float>(S * CB, own); st.lastInput = dalloc<cf>(S * CB, own);
+  st.rng = dalloc<uint32_t>(S, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
+  st.ring = dalloc<float>((size_t)S * g.C * g.L, own);
+  st.inEnergy = dalloc<float>(S * CB, own); st.map = dalloc<float>((size_t)S * g.B * 2, own);
+  st.predIn = dalloc<cf>(S * CB, own); st.terms = dalloc<float>((size_t)S * g.B * nterms(g.C), own);
+  st.peaks = dalloc<float>((size_t)S * g.B * 2, own);
+  if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
+      !st.predE || !st.lastInput || !st.rng || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.predIn || !st.terms ||
+      !st.peaks) {
+    free_batch(e);
+    return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);
+  }
+  e->committed = true;
+  return 0;
+}
+
+int bsb_run(bsb_engine *e, void *cudaStream) {
+  if (!e->committed) return e->fail("bsb_run needs a committed batch");
+  const Geometry &g = e->g;
+  const int S = (int)e->streams.size();
+  const size_t CB = (size_t)g.C * g.B;
+  stream_t q = (stream_t)cudaStream;
+  StateDev &st = e->st;
+  // reset(): zero phase state, rings, maps; seed the RNGs
+  dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE, S * CB * sizeof(float), q);
+  dzero(st.lastInput, S * CB * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
+  dzero(st.ring, (size_t)S * g.C * g.L * sizeof(float), q); dzero(st.map, (size_t)S * g.B * 2 * sizeof(float), q);
+#ifdef BS_HOSTEMU
+  std::memcpy(st.rng, e->dSeeds, S * sizeof(uint32_t));
+#else
+  cudaMemcpyAsync(st.rng, e->dSeeds, S * sizeof(uint32_t), cudaMemcpyDeviceToDevice, q);
+#endif
+  e->launches = 0;
+  e->kms[0] = e->kms[1] = e->kms[2] = 0.f;
+  const int nt = 256;
+  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk) {
+    const int nSlots = e->chunk;
+#ifdef BS_HOSTEMU
+    std::vector<float> sm(spectral_smem_floats(g.B, g.C) + 4 * (size_t)g.M + g.L + 64);
+    for (int s = 0; s < S; ++s) {
+      const StreamDev &sd = e->hs[s];
+      for (int t = 0; t < nSlots; ++t) {
+        long long m = slot0 + t;
+        if (m >= sd.nBlocks) break;
+        if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
+        for (int which = 0; which < 2; ++which)
+          for (int c = 0; c < g.C; ++c)
+            analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
+                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm.data(), 0, 1);
+      }
+      for (int t = 0; t < nSlots; ++t) {
+        long long m = slot0 + t;
+        if (m >= sd.nBlocks) break;
+        bool keep = (m + 1 < sd.nBlocks) && !(e->dBlocks[sd.blockBase + m + 1].flags & kNew);
+        spectral_block(e->dg, e->dt, e->dBlocks[sd.blockBase + m], e->dBlocks2[sd.blockBase + m],
+                       e->specIn + (((size_t)s * nSlots + t) * 2 + 0) * CB, e->specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB,
+                       st.outSpec + s * CB, st.predE + s * CB, st.lastInput + s * CB, st.rng + s, st.freqEst + 2 * s,
+                       st.inEnergy + s * CB, st.map + (size_t)s * g.B * 2, st.predIn + s * CB,
+                       st.terms + (size_t)s * g.B * nterms(g.C), st.peaks + (size_t)s * g.B * 2,
+                       e->specOut + ((size_t)s * nSlots + t) * CB, keep, sm.data(), 0, 1);
+      }
+      for (int c = 0; c < g.C; ++c)
+        synth_stream(e->dg, e->dt, sd, c, (int)slot0, nSlots, e->specOut + (size_t)s * nSlots * CB,
+                     st.ring + ((size_t)s * g.C + c) * g.L, sm.data(), sm.data() + 4 * (size_t)g.M, 0, 1);
+    }
+    e->launches += 3;
+#else
+    const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
+    const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float);
+    cudaEventRecord(e->ev[0], q);
+    analysis_kernel<<<(unsigned)((size_t)S * nSlots * 2 * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows,
+                                                                            (int)slot0, nSlots, e->specIn);
+    cudaEventRecord(e->ev[1], q);
+    spectral_kernel<<<S, nt, smS, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, (int)slot0, nSlots, e->specIn, e->specOut, st);
+    cudaEventRecord(e->ev[2], q);
+    synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, (int)slot0, nSlots, e->specOut, st);
+    cudaEventRecord(e->ev[3], q);
+    e->launches += 3;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
+    if (getenv("BS_KERNEL_TIMES")) {   // per-kernel split (serialises the chunks; not used for throughput numbers)
+      cudaEventSynchronize(e->ev[3]);
+      for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->kms[i] += ms; }
+    }
+#endif
+  }
+  return 0;
+}
+
+int bsb_block_info(const bsb_engine *e, int s, long long b, long long out[8]) {
+  if (s < 0 || s >= (int)e->streams.size()) return -1;
+  const StreamPlan &p = e->streams[s].plan;
+  if (b < 0 || b >= (long long)p.blocks.size()) return -1;
+  out[0] = p.blocks[b].flags; uint32_t u; std::memcpy(&u, &p.blocks[b].timeFactor, 4); out[1] = u;
+  for (int w = 0; w < 2; ++w) { const Window &x = p.windows[2 * b + w]; out[2 + 3 * w] = x.start; out[3 + 3 * w] = x.lo; out[4 + 3 * w] = x.hi; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+/*
+ * bauklank_stretch.h -- C ABI of libbauklank_stretch.so, the B200-native drop-in for the Signalsmith-Stretch hot path
+ * of hanskerkhof/BAUKLANK-audio-stretch.
+ *
+ * Part 1 mirrors, name for name, the 18 exports the reference's JS glue binds from its WASM engine
+ * (app/SignalsmithStretch.mjs:462-479: wasm exports "h".."y").  Same argument meaning, same conventions: planar
+ * f32, the ENGINE owns the I/O buffer returned by setBuffers (HOST memory here, as in the reference where it is wasm
+ * linear memory), no return codes -- an unrecoverable error aborts the process like the reference's wasm trap
+ * (abort() import, :454-459).  One "current" engine instance per process, like one wasm module instance per node.
+ *
+ * Part 2 is the batched, handle-based form of the same operator for many independent streams with DEVICE-resident
+ * audio: the worklet's per-quantum drive (app/SignalsmithStretch.mjs:826-954) is compiled on the host into a block
+ * table and executed by three CUDA kernels per time chunk.  No torch types cross this boundary: plain pointers, sizes
+ * and a cudaStream_t passed as void*.
+ *
+ * There is no CPU fallback: every entry point that computes requires a CUDA device.
+ */
+#ifndef BAUKLANK_STRETCH_H
+#define BAUKLANK_STRETCH_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- Part 1: the reference's own 18 entry points */
+/* wasm export "h"  (app/SignalsmithStretch.mjs:463, used at :806-815): allocates 2*channels*length floats and
+ * returns the base; in[c] = base + length*c, out[c] = base + length*(c+channels). */
+float *setBuffers(int channels, int length);
+int blockSamples(void);    /* "i" :464 */
+int intervalSamples(void); /* "j" :465 */
+int inputLatency(void);    /* "k" :466, used at :805, :800 */
+int outputLatency(void);   /* "l" :467 */
+void reset(void);          /* "m" :468, used at :792 */
+void presetDefault(int channels, float sampleRate); /* "n" :469, used at :796 */
+void presetCheaper(int channels, float sampleRate); /* "o" :470, used at :794 */
+void configure(int channels, int blockSamples, int intervalSamples, int splitComputation); /* "p" :471, used at :791 */
+void setTransposeFactor(float multiplier, float tonalityLimit);    /* "q" :472 */
+void setTransposeSemitones(float semitones, float tonalityLimit);  /* "r" :473, used at :847 */
+void setFormantFactor(float multiplier, int compensatePitch);      /* "s" :474 */
+void setFormantSemitones(float semitones, int compensatePitch);    /* "t" :475, used at :848 */
+void setFormantBase(float baseFreq);                               /* "u" :476, used at :849 */
+void seek(int inputSamples, double playbackRate);                  /* "v" :477, used at :935 */
+void process(int inputSamples, int outputSamples);                 /* "w" :478, used at :869, :882, :936 */
+void flush(int outputSamples); /* "x" :479 -- bound but never called by the reference JS; aborts with a message */
+int stretch_main(int argc, char **argv); /* "y" :480 `_main`, a no-op (a shared object cannot export `main`) */
+/* the reference seeds its RNG from crypto.getRandomValues (:382-394); a drop-in needs a way to pin it */
+void stretch_set_seed(uint32_t seed);
+
+/* ---------------------------------------------------------------- Part 2: batched streams on the device */
+typedef struct bsb_engine bsb_engine;
+
+/* one entry of the worklet's time map (app/SignalsmithStretch.mjs:587-600); JS numbers are doubles */
+typedef struct bsb_segment {
+  double output, input, rate;
+  double semitones, tonality_hz, formant_semitones, formant_base_hz, loop_start, loop_end;
+  int32_t active, formant_compensation;
+} bsb_segment;
+
+/* configure()/presetDefault()/presetCheaper() for a batch; all streams of one engine share the configuration */
+bsb_engine *bsb_create(int channels, int block_samples, int interval_samples, int split_computation, double sample_rate);
+bsb_engine *bsb_create_preset(int channels, double sample_rate, int cheaper);
+void bsb_destroy(bsb_engine *e);
+int bsb_block_samples(const bsb_engine *e);
+int bsb_interval_samples(const bsb_engine *e);
+int bsb_input_latency(const bsb_engine *e);
+int bsb_output_latency(const bsb_engine *e);
+int bsb_fft_samples(const bsb_engine *e);
+int bsb_bands(const bsb_engine *e);
+const char *bsb_last_error(const bsb_engine *e);
+
+/* Start describing a batch of n_streams independent streams.  d_clip / d_out are DEVICE pointers to planar f32
+ * [channels][len]. */
+int bsb_begin(bsb_engine *e, int n_streams);
+/* buffer-playback drive: per render quantum `seek(bufferLength, rate); process(0, quantum)` (:883-943) */
+int bsb_add_kiosk(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, long long n_out,
+                  int quantum, const bsb_segment *segments, int n_segments, uint32_t seed);
+/* streaming drive: `process(n_in, n_out)` n_calls times over a contiguous input (:870-882 generalised) */
+int bsb_add_streaming(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, int n_in,
+                      int n_out, long long n_calls, const bsb_segment *segments, int n_segments, uint32_t seed);
+/* upload the block tables, allocate per-stream state; chunk_blocks = blocks per kernel launch (0 = automatic) */
+int bsb_commit(bsb_engine *e, int chunk_blocks);
+/* run every block of every stream on `cuda_stream` (a cudaStream_t); state is reset first */
+int bsb_run(bsb_engine *e, void *cuda_stream);
+/* rebind the device I/O pointers of an already planned batch (same shapes) without re-planning */
+int bsb_rebind(bsb_engine *e, int stream, const float *d_clip, float *d_out);
+long long bsb_total_blocks(const bsb_engine *e);
+long long bsb_stream_blocks(const bsb_engine *e, int stream);
+int bsb_chunk_blocks(const bsb_engine *e);
+/* kernel launches issued by the last bsb_run, and a read-out of one block record (for the indexing tests):
+ * out[0]=flags out[1]=timeFactor bits, out[2..4]=cur window {start lo hi}, out[5..7]=prev window */
+long long bsb_launch_count(const bsb_engine *e);
+int bsb_block_info(const bsb_engine *e, int stream, long long block, long long out[8]);
+/* per-kernel device time of the last bsb_run in milliseconds (CUDA events): [analysis, spectral, synthesis] */
+int bsb_kernel_ms(const bsb_engine *e, float out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
