@@ -25,7 +25,8 @@ struct BlockRec {
   float fmMult, fmInv;      // formantMultiplier / invFormantMultiplier seen by formant step 2
   float fmFreqMult;         // freqMultiplier seen by formant step 2 (fmLimit below)
 };
-struct BlockRec2 { float fmLimit; float pad[3]; };  // kept separate so BlockRec stays 32 B
+struct BlockRec2 { float fmLimit; int lastNew; float pad[2]; };  // lastNew: stream-relative index of the block whose
+                                                                  // "current" spectrum is this block's input (-1: none yet)
 // sample i (0 <= i < L) of a window = (lo <= i < hi) ? clip[ch][start + i] : 0
 struct Window { long long start; int lo, hi; };
 
@@ -105,7 +106,9 @@ class Control {
         rec.flags = kValid | (isNew ? kNew : 0u) | (mapped ? kMapped : 0u) | (formants ? kFormants : 0u);
         rec.timeFactor = tf;
         plan.blocks.push_back(rec);
-        plan.blocks2.push_back(BlockRec2{});
+        if (isNew) lastNew_ = (int)plan.blocks.size() - 1;
+        BlockRec2 r2{}; r2.lastNew = lastNew_;
+        plan.blocks2.push_back(r2);
         plan.windows.push_back(Window{0, 0, 0});
         plan.windows.push_back(Window{0, 0, 0});
         cur_ = (long long)plan.blocks.size() - 1;
@@ -148,6 +151,7 @@ class Control {
   float seekTF_ = 0.f;
   int stepPeaks_ = -1, stepFm0_ = -1, stepFm2_ = -1;
   long long cur_ = -1;
+  int lastNew_ = -1;
 };
 
 inline void apply_segment_params(Params &p, const Segment &s, double sampleRate) {

@@ -57,26 +57,66 @@ __global__ void __launch_bounds__(256) analysis_kernel(DevGeom g, DevTables T, c
   analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x);
 }
 
-__global__ void __launch_bounds__(256) spectral_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                       const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, cf *specOut,
-                                                       StateDev st) {
-  extern __shared__ float sm[];
+// premap: the state-independent half of the spectral stage for every (stream, block) of the chunk in parallel
+__global__ void __launch_bounds__(128) premap_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                     const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, StateDev st) {
+  extern __shared__ float4 sm4[];
+  float *sm = (float *)sm4;
+  const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
+  const StreamDev sd = streams[s];
+  const long long m = (long long)slot0 + t;
+  if (m >= sd.nBlocks) return;
+  const BlockRec rec = blocks[sd.blockBase + m];
+  if (needs_inline_map(rec)) return;
+  const BlockRec2 rec2 = blocks2[sd.blockBase + m];
+  const size_t CB = (size_t)g.C * g.B;
+  const cf *inp = block_input(g, rec2, s, slot0, nSlots, specIn, st.lastInput);
+  float *inE = st.inEnergy + ((size_t)s * nSlots + t) * CB, *mp = st.map + ((size_t)s * nSlots + t) * g.B * 2;
+  if (g.C == 2) map_stage<2>(g, T, rec, rec2, inp, nullptr, inE, mp, sm, threadIdx.x, blockDim.x);
+  else if (g.C == 1) map_stage<1>(g, T, rec, rec2, inp, nullptr, inE, mp, sm, threadIdx.x, blockDim.x);
+  else map_stage<0>(g, T, rec, rec2, inp, nullptr, inE, mp, sm, threadIdx.x, blockDim.x);
+}
+
+template <int CT>
+__device__ __forceinline__ void spectral_stream(const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
+                                                const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, cf *specOut,
+                                                const StateDev &st, float *sm) {
   const int s = blockIdx.x;
   const StreamDev sd = streams[s];
   const size_t CB = (size_t)g.C * g.B;
+  long long mLast = -1;
   for (int t = 0; t < nSlots; ++t) {
     const long long m = (long long)slot0 + t;
     if (m >= sd.nBlocks) break;
+    mLast = m;
     const BlockRec rec = blocks[sd.blockBase + m];
     const BlockRec2 rec2 = blocks2[sd.blockBase + m];
-    const bool keep = (m + 1 < sd.nBlocks) && !(blocks[sd.blockBase + m + 1].flags & kNew);
-    const cf *cur = specIn + (((size_t)s * nSlots + t) * 2 + 0) * CB;
-    const cf *prev = specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB;
-    spectral_block(g, T, rec, rec2, cur, prev, st.outSpec + s * CB, st.predE + s * CB, st.lastInput + s * CB, st.rng + s,
-                   st.freqEst + 2 * s, st.inEnergy + s * CB, st.map + (size_t)s * g.B * 2, st.predIn + s * CB,
-                   st.terms + (size_t)s * g.B * nterms(g.C), st.peaks + (size_t)s * g.B * 2,
-                   specOut + ((size_t)s * nSlots + t) * CB, keep, sm, threadIdx.x, blockDim.x);
+    const cf *inp = block_input(g, rec2, s, slot0, nSlots, specIn, st.lastInput);
+    const cf *prev = (rec.flags & kNew) ? specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB : nullptr;
+    spectral_block<CT>(g, T, rec, rec2, inp, prev, st.outSpec + s * CB, st.predE + s * CB, st.rng + s, st.freqEst + 2 * s,
+                       st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, st.predIn + s * CB,
+                       st.terms + (size_t)s * g.B * nterms(g.C), specOut + ((size_t)s * nSlots + t) * CB, needs_inline_map(rec), sm,
+                       threadIdx.x, blockDim.x);
   }
+  // carry the input spectrum into the next chunk if its first block reuses it (no new spectrum there)
+  if (mLast >= 0 && mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew)) {
+    const BlockRec2 r2 = blocks2[sd.blockBase + mLast];
+    if (r2.lastNew >= slot0) {
+      const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput);
+      cf *dst = st.lastInput + (size_t)s * CB;
+      for (int i = threadIdx.x; i < (int)CB; i += blockDim.x) dst[i] = src[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) spectral_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                       const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, cf *specOut,
+                                                       StateDev st) {
+  extern __shared__ float4 sm4[];
+  float *sm = (float *)sm4;
+  if (g.C == 2) spectral_stream<2>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, sm);
+  else if (g.C == 1) spectral_stream<1>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, sm);
+  else spectral_stream<0>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, sm);
 }
 
 __global__ void __launch_bounds__(256) synthesis_kernel(DevGeom g, DevTables T, const StreamDev *streams, int slot0, int nSlots,
@@ -167,7 +207,8 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY) != cudaSuccess ||
-      cudaFuncSetAttribute(spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smS) != cudaSuccess) {
+      cudaFuncSetAttribute(spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smS) != cudaSuccess ||
+      cudaFuncSetAttribute(premap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
     std::fprintf(stderr, "bauklank_stretch: block size %d needs more shared memory than one SM has\n", block);
     bsb_destroy(e); return nullptr;
   }
@@ -284,7 +325,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->totalBlocks = (long long)blocks.size();
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
-  const size_t perSlot = (size_t)S * CB * sizeof(cf) * 3;   // specIn (cur+prev) + specOut
+  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8);   // specIn (cur+prev) + specOut + inEnergy + map
   if (chunkBlocks <= 0) {
     const size_t budget = (size_t)6 << 30;
     chunkBlocks = (int)std::min<size_t>(64, std::max<size_t>(1, budget / perSlot));
@@ -300,12 +341,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.outSpec = dalloc<cf>(S * CB, own); st.predE = dalloc<float>(S * CB, own); st.lastInput = dalloc<cf>(S * CB, own);
   st.rng = dalloc<uint32_t>(S, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
   st.ring = dalloc<float>((size_t)S * g.C * g.L, own);
-  st.inEnergy = dalloc<float>(S * CB, own); st.map = dalloc<float>((size_t)S * g.B * 2, own);
+  st.inEnergy = dalloc<float>((size_t)S * chunkBlocks * CB, own); st.map = dalloc<float>((size_t)S * chunkBlocks * g.B * 2, own);
   st.predIn = dalloc<cf>(S * CB, own); st.terms = dalloc<float>((size_t)S * g.B * nterms(g.C), own);
-  st.peaks = dalloc<float>((size_t)S * g.B * 2, own);
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
-      !st.predE || !st.lastInput || !st.rng || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.predIn || !st.terms ||
-      !st.peaks) {
+      !st.predE || !st.lastInput || !st.rng || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.predIn || !st.terms) {
     free_batch(e);
     return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);
   }
@@ -323,7 +362,7 @@ int bsb_run(bsb_engine *e, void *cudaStream) {
   // reset(): zero phase state, rings, maps; seed the RNGs
   dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE, S * CB * sizeof(float), q);
   dzero(st.lastInput, S * CB * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
-  dzero(st.ring, (size_t)S * g.C * g.L * sizeof(float), q); dzero(st.map, (size_t)S * g.B * 2 * sizeof(float), q);
+  dzero(st.ring, (size_t)S * g.C * g.L * sizeof(float), q);
 #ifdef BS_HOSTEMU
   std::memcpy(st.rng, e->dSeeds, S * sizeof(uint32_t));
 #else
@@ -335,46 +374,70 @@ int bsb_run(bsb_engine *e, void *cudaStream) {
   for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk) {
     const int nSlots = e->chunk;
 #ifdef BS_HOSTEMU
-    std::vector<float> sm(spectral_smem_floats(g.B, g.C) + 4 * (size_t)g.M + g.L + 64);
-    for (int s = 0; s < S; ++s) {
+    std::vector<f4> smv((spectral_smem_floats(g.B, g.C) + 4 * (size_t)g.M + g.L + 64) / 4 + 1);
+    float *sm = (float *)smv.data();
+    auto mapFn = g.C == 2 ? map_stage<2> : (g.C == 1 ? map_stage<1> : map_stage<0>);
+    auto specFn = g.C == 2 ? spectral_block<2> : (g.C == 1 ? spectral_block<1> : spectral_block<0>);
+    for (int s = 0; s < S; ++s) {   // analysis_kernel
       const StreamDev &sd = e->hs[s];
-      for (int t = 0; t < nSlots; ++t) {
+      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
         long long m = slot0 + t;
-        if (m >= sd.nBlocks) break;
         if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
         for (int which = 0; which < 2; ++which)
           for (int c = 0; c < g.C; ++c)
             analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
-                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm.data(), 0, 1);
+                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1);
       }
-      for (int t = 0; t < nSlots; ++t) {
-        long long m = slot0 + t;
-        if (m >= sd.nBlocks) break;
-        bool keep = (m + 1 < sd.nBlocks) && !(e->dBlocks[sd.blockBase + m + 1].flags & kNew);
-        spectral_block(e->dg, e->dt, e->dBlocks[sd.blockBase + m], e->dBlocks2[sd.blockBase + m],
-                       e->specIn + (((size_t)s * nSlots + t) * 2 + 0) * CB, e->specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB,
-                       st.outSpec + s * CB, st.predE + s * CB, st.lastInput + s * CB, st.rng + s, st.freqEst + 2 * s,
-                       st.inEnergy + s * CB, st.map + (size_t)s * g.B * 2, st.predIn + s * CB,
-                       st.terms + (size_t)s * g.B * nterms(g.C), st.peaks + (size_t)s * g.B * 2,
-                       e->specOut + ((size_t)s * nSlots + t) * CB, keep, sm.data(), 0, 1);
-      }
-      for (int c = 0; c < g.C; ++c)
-        synth_stream(e->dg, e->dt, sd, c, (int)slot0, nSlots, e->specOut + (size_t)s * nSlots * CB,
-                     st.ring + ((size_t)s * g.C + c) * g.L, sm.data(), sm.data() + 4 * (size_t)g.M, 0, 1);
     }
-    e->launches += 3;
+    for (int s = 0; s < S; ++s) {   // premap_kernel
+      const StreamDev &sd = e->hs[s];
+      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+        long long m = slot0 + t;
+        const BlockRec rec = e->dBlocks[sd.blockBase + m];
+        if (needs_inline_map(rec)) continue;
+        const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
+        mapFn(e->dg, e->dt, rec, rec2, block_input(e->dg, rec2, s, (int)slot0, nSlots, e->specIn, st.lastInput), nullptr,
+              st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, sm, 0, 1);
+      }
+    }
+    for (int s = 0; s < S; ++s) {   // spectral_kernel
+      const StreamDev &sd = e->hs[s];
+      long long mLast = -1;
+      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+        long long m = slot0 + t; mLast = m;
+        const BlockRec rec = e->dBlocks[sd.blockBase + m];
+        const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
+        const cf *inp = block_input(e->dg, rec2, s, (int)slot0, nSlots, e->specIn, st.lastInput);
+        const cf *prev = (rec.flags & kNew) ? e->specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB : nullptr;
+        specFn(e->dg, e->dt, rec, rec2, inp, prev, st.outSpec + s * CB, st.predE + s * CB, st.rng + s, st.freqEst + 2 * s,
+               st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, st.predIn + s * CB,
+               st.terms + (size_t)s * g.B * nterms(g.C), e->specOut + ((size_t)s * nSlots + t) * CB, needs_inline_map(rec), sm, 0, 1);
+      }
+      if (mLast >= 0 && mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew)) {
+        const BlockRec2 r2 = e->dBlocks2[sd.blockBase + mLast];
+        if (r2.lastNew >= slot0)
+          std::memcpy(st.lastInput + (size_t)s * CB, block_input(e->dg, r2, s, (int)slot0, nSlots, e->specIn, st.lastInput), CB * sizeof(cf));
+      }
+    }
+    for (int s = 0; s < S; ++s)     // synthesis_kernel
+      for (int c = 0; c < g.C; ++c)
+        synth_stream(e->dg, e->dt, e->hs[s], c, (int)slot0, nSlots, e->specOut + (size_t)s * nSlots * CB,
+                     st.ring + ((size_t)s * g.C + c) * g.L, sm, sm + 4 * (size_t)g.M, 0, 1);
+    e->launches += 4;
 #else
     const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
-    const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float);
+    const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float), smM = map_smem_floats(g.B) * sizeof(float);
     cudaEventRecord(e->ev[0], q);
     analysis_kernel<<<(unsigned)((size_t)S * nSlots * 2 * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows,
                                                                             (int)slot0, nSlots, e->specIn);
+    premap_kernel<<<(unsigned)((size_t)S * nSlots), 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, (int)slot0, nSlots,
+                                                                  e->specIn, st);
     cudaEventRecord(e->ev[1], q);
     spectral_kernel<<<S, nt, smS, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, (int)slot0, nSlots, e->specIn, e->specOut, st);
     cudaEventRecord(e->ev[2], q);
     synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, (int)slot0, nSlots, e->specOut, st);
     cudaEventRecord(e->ev[3], q);
-    e->launches += 3;
+    e->launches += 4;
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
     if (getenv("BS_KERNEL_TIMES")) {   // per-kernel split (serialises the chunks; not used for throughput numbers)
@@ -396,3 +459,7 @@ int bsb_block_info(const bsb_engine *e, int s, long long b, long long out[8]) {
 }
 
 }  // extern "C"
+
+#if defined(BS_PHASE_TIMING) && !defined(BS_HOSTEMU)
+extern "C" void bs_debug_phase_cycles(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16); }
+#endif

@@ -34,6 +34,15 @@ inline float __int_as_float_hd(int i) { float f; std::memcpy(&f, &i, 4); return 
 #define __int_as_float_hd(x) __int_as_float(x)
 #endif
 
+#if defined(BS_PHASE_TIMING) && !defined(BS_HOSTEMU)
+__device__ unsigned long long g_phase_cycles[16];
+#define BS_MARK(i) do { if (tid == 0 && blockIdx.x == 0) { unsigned long long t_ = clock64(); atomicAdd(&g_phase_cycles[i], t_ - t_mark_); t_mark_ = t_; } } while (0)
+#define BS_MARK_INIT() unsigned long long t_mark_ = clock64()
+#else
+#define BS_MARK(i) ((void)0)
+#define BS_MARK_INIT() ((void)0)
+#endif
+
 namespace bs {
 
 struct DevGeom {
@@ -61,16 +70,17 @@ struct StateDev {
   uint32_t *rng;      // [S]
   float *freqEst;     // [S][2]      freqEstimateWeighted, freqEstimateWeight
   float *ring;        // [S][C][L]   overlap-add ring between chunks
+  // per chunk slot, written by the premap kernel
+  float *inEnergy;    // [S][T][C][B]
+  float *map;         // [S][T][B][2]   {inputBin, freqGrad}
   // scratch
-  float *inEnergy;    // [S][C][B]
-  float *map;         // [S][B][2]   {inputBin, freqGrad}
   cf *predIn;         // [S][C][B]
   float *terms;       // [S][B][NT]
-  float *peaks;       // [S][B][2]   (only B/2 used)
 };
 
 BS_HD int trunc_i32(float x) { return fabsf(x) < 2147483648.0f ? (int)x : INT32_MIN; }
-BS_HHD int nterms(int C) { return 12 + 3 * C; }
+struct alignas(16) f4 { float x, y, z, w; };
+BS_HHD int nterms(int C) { return (16 + 3 * C + 3) & ~3; }
 
 // ------------------------------------------------------------------------------------------------------------
 // radix-4 DIT passes on split arrays (W#21/W#34 forward, W#20/W#33 inverse), `outer` sub-transforms of length
@@ -324,38 +334,29 @@ BS_HD void make_output(float energy, cf fallback, float re, float im, float &ore
   oim = s * im; ore = s * re;
 }
 
-// smem layout of the spectral kernel (floats): energy[B+2] | smoothed[B] | ints: cpk[B/2+1] | misc
-BS_HHD size_t spectral_smem_floats(int B, int C) { return (size_t)(B + 2) + B + (B / 2 + 2) + 64 * (size_t)nterms(C) + 64 * 2 * (size_t)C + 16; }
-
-// The whole spectral stage of one block of one stream (W#48 8170-9873).  Sequential recurrences run on tid 0.
-BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec rec, const BlockRec2 rec2,
-                          const cf *inCur, const cf *inPrev /* [C][B] each */, cf *outSpec, float *predE, cf *lastInput,
-                          uint32_t *rngp, float *freqEst, float *inEnergy, float *mapv, cf *predIn, float *terms,
-                          float *peaksG, cf *specOut, bool keepInput, float *sm, int tid, int nt) {
-  const int C = g.C, B = g.B, NT = nterms(C);
-  const bool isNew = rec.flags & kNew, mapped = rec.flags & kMapped, formants = rec.flags & kFormants;
+// State-independent part of the spectral stage of one block: input energies, energy smoothing, peak picking,
+// the output frequency map and the formant envelope (W#48 8238-9312).  It depends only on the block's input spectrum
+// and parameters (except the formant auto-detect, which carries freqEst across blocks), so the premap kernel runs it
+// for all blocks of a chunk in parallel.  Sequential recurrences run on tid 0.
+// smem (floats): energy[B+2] | smoothed[B] | cpk[B/2+2] ints | peaks[B] | misc[16]
+BS_HHD size_t map_smem_floats(int B) { return (((size_t)(B + 2) + B + (B / 2 + 2) + B + 16) + 3) & ~(size_t)3; }
+template <int CT>
+BS_HD void map_stage(const DevGeom &g, const DevTables &T, const BlockRec rec, const BlockRec2 rec2, const cf *inp,
+                     float *freqEst, float *inEnergy, float *mapv, float *sm, int tid, int nt) {
+  const int C = CT > 0 ? CT : g.C, B = g.B;
+  const bool mapped = rec.flags & kMapped, formants = rec.flags & kFormants;
   const float fN = (float)(uint32_t)g.N, fH = (float)(uint32_t)g.H, ratio = fN / fH;
   float *energy = sm, *smoothed = sm + (B + 2);
   int *cpk = (int *)(smoothed + B);
-  float *tileT = (float *)(cpk + (B / 2 + 2));          // [64][NT] two 32-bin term tiles
-  float *tileO = tileT + 64 * (size_t)NT;               // [64][2C] chain outputs (ring of 64 bins)
-  int *misc = (int *)(tileO + 64 * 2 * (size_t)C);      // [0] nPeaks, [1] monotone flag
-  const cf *inp = isNew ? inCur : lastInput;
-  const cf *prv = isNew ? inPrev : lastInput;
-  const cf *prvRot = isNew ? T.specRot : nullptr;
-
-  // S1 rotate Band.output (prevInput is rotated on the fly when read), + input energies
+  float *peaksG = (float *)(cpk + (B / 2 + 2));
+  int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] monotone flag, [2] formant base bin
+  BS_MARK_INIT();
   for (int idx = tid; idx < C * B; idx += nt) {
-    int k = idx % B;
-    if (isNew) {
-      cf o = outSpec[idx], r = T.specRot[k], n;
-      n.im = (o.im * r.re) + (o.re * r.im); n.re = (o.re * r.re) - (o.im * r.im);
-      outSpec[idx] = n;
-    }
     cf v = inp[idx];
     inEnergy[idx] = (v.im * v.im) + (v.re * v.re);
   }
   BS_SYNC();
+  BS_MARK(0);
   if (mapped) {
     for (int k = tid; k < B; k += nt) {
       float e = 0.f;
@@ -366,8 +367,10 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
     if (tid == 0) {
       // smoothEnergy steps 1,2 (one-pole, carry kept across both) then findPeaks
       float slew = 1.0f / ((ratio * 0.5f) + 1.0f), carry = 0.f;
+      BS_MARK(1);
       carry = smooth_pass(smoothed, B, slew, carry);
       carry = smooth_pass(smoothed, B, slew, carry);
+      BS_MARK(2);
       int nP = 0, k = 0, mono = 1, prevC = INT32_MIN;
       while (k < B) {
         if (!(energy[k] <= smoothed[k])) {
@@ -389,6 +392,7 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
         ++k;
       }
       misc[0] = nP; misc[1] = mono;
+      BS_MARK(3);
     }
     BS_SYNC();
     // updateOutputMap: every bin finds the LAST section (in the reference's write order) that covers it
@@ -432,6 +436,7 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
     for (int k = tid; k < B; k += nt) { mapv[2 * k] = (float)(uint32_t)k; mapv[2 * k + 1] = 1.0f; }
   }
   BS_SYNC();
+  BS_MARK(4);
   if (formants) {
     float *fm = energy;  // [B+2]
     for (int k = tid; k < B + 2; k += nt) {
@@ -501,6 +506,38 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
     }
     BS_SYNC();
   }
+}
+
+// smem of the spectral kernel (floats): [map_stage area] | term tiles [2][32][NT] | chain rings
+BS_HHD size_t spectral_smem_head(int B) { return map_smem_floats(B); }
+BS_HHD size_t spectral_smem_floats(int B, int C) { return spectral_smem_head(B) + 64 * (size_t)nterms(C) + 192 + 128 * (size_t)C + 16; }
+
+// State-dependent part of one block of one stream (W#48 8193-8229 rotate, 9314-9455 preliminary prediction,
+// 9458-9873 vertical prediction chain).  `doMap`: the block's map stage was not precomputed (formant auto-detect).
+template <int CT>
+BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec rec, const BlockRec2 rec2,
+                          const cf *inp, const cf *inPrev /* [C][B] each; inPrev == nullptr: no new spectrum */, cf *outSpec,
+                          float *predE, uint32_t *rngp, float *freqEst, float *inEnergy, float *mapv, cf *predIn,
+                          float *terms, cf *specOut, bool doMap, float *sm, int tid, int nt) {
+  const int C = CT > 0 ? CT : g.C, B = g.B, NT = nterms(C);
+  const bool isNew = rec.flags & kNew;
+  float *tileT = sm + spectral_smem_head(B);            // [2][32][NT] two 32-bin term tiles (16-byte aligned)
+  float *tileO = tileT + 64 * (size_t)NT;               // chain output rings: [64] cf, [64] int, [64][C] cf
+  const cf *prv = isNew ? inPrev : inp;
+  const cf *prvRot = isNew ? T.specRot : nullptr;
+  BS_MARK_INIT();
+  // S1 rotate Band.output (prevInput is rotated on the fly when read)
+  if (isNew) {
+    for (int idx = tid; idx < C * B; idx += nt) {
+      int k = idx % B;
+      cf o = outSpec[idx], r = T.specRot[k], n;
+      n.im = (o.im * r.re) + (o.re * r.im); n.re = (o.re * r.re) - (o.im * r.im);
+      outSpec[idx] = n;
+    }
+  }
+  if (doMap) map_stage<CT>(g, T, rec, rec2, inp, freqEst, inEnergy, mapv, sm, tid, nt);
+  BS_SYNC();
+  BS_MARK(5);
   // S5 preliminary prediction, all (channel, bin) in parallel
   for (int idx = tid; idx < C * B; idx += nt) {
     int c = idx / B, k = idx - c * B;
@@ -521,6 +558,7 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
     outSpec[idx] = n;
   }
   BS_SYNC();
+  BS_MARK(6);
   // S6 part 1: everything that does not depend on the chain, per bin, in parallel -> terms[k][NT]
   const int longStep = g.longStep;
   const float tf = rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor;
@@ -567,25 +605,34 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
         tt[9] = tRe * oIm; tt[10] = oRe * tIm;              // phIm = ((tt9 + phIm) - tt10)
       }
     }
+    tt[12] = me; tt[13] = pRe; tt[14] = pIm;                   // energy and fallback input of the max channel
     for (int c = 0; c < C; ++c) {
-      tt[12 + c] = predE[(size_t)c * B + k];
+      tt[16 + c] = predE[(size_t)c * B + k];
       cf cp = predIn[(size_t)c * B + k];
-      tt[12 + C + 2 * c] = (pIm * cp.im) + (pRe * cp.re);      // channel twist re
-      tt[12 + C + 2 * c + 1] = (pRe * cp.im) - (pIm * cp.re);  // channel twist im
+      tt[16 + C + 2 * c] = (pIm * cp.im) + (pRe * cp.re);      // channel twist re
+      tt[16 + C + 2 * c + 1] = (pRe * cp.im) - (pIm * cp.re);  // channel twist im
     }
   }
   BS_SYNC();
-  // S6 part 2: the bin-to-bin chain.  The first warp stages 32-bin tiles of terms through shared memory and writes
-  // results back coalesced; lane 0 walks the bins.
+  BS_MARK(7);
+  // S6 part 2: the bin-to-bin chain (first warp only).  32-bin tiles of terms are staged through shared memory.
+  // Lane 0 walks the bins computing only the maximum-energy channel (the one the recurrence runs through); the other
+  // channels ("followers": out[c] = makeOutput(out[mc] * channelTwist[c])) do not feed the recurrence unless the
+  // maximum channel changes, so they are filled in for a whole tile at once by all lanes afterwards, and computed on
+  // demand by lane 0 in the rare bins where it needs one early.
 #ifdef BS_HOSTEMU
   const int lanes = 1, lane = 0; const bool inChain = true;
 #else
   const int lanes = 32, lane = tid & 31; const bool inChain = tid < 32;
 #endif
   if (inChain) {
+    cf *ringMc = (cf *)tileO;                  // [64] output of the max channel per bin
+    int *ringIdx = (int *)(tileO + 128);       // [64] which channel that was
+    cf *ringFull = (cf *)(tileO + 192);        // [64][C] all channels (complete for finished tiles)
     const int nTiles = (B + 31) / 32;
     for (int i = lane; i < 32 * NT && i < B * NT; i += lanes) tileT[i] = terms[i];
     BS_WARPSYNC();
+    float pr = 0.f, pi_ = 0.f; int mcPrev = -1;
     for (int tIdx = 0; tIdx < nTiles; ++tIdx) {
       const int k0 = tIdx * 32, k1 = (k0 + 32 < B) ? k0 + 32 : B;
       float *cur = tileT + (size_t)(tIdx & 1) * 32 * NT, *nxt = tileT + (size_t)((tIdx + 1) & 1) * 32 * NT;
@@ -594,69 +641,109 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
         const float *src = terms + (size_t)k1 * NT;
         for (int i = lane; i < nEl; i += lanes) nxt[i] = src[i];
       }
+      // out[c][j] for a channel c that was not the maximum at bin j
+      auto follower = [&](int j, int c, float &re, float &im) {
+        if (j < k0) { cf v = ringFull[(size_t)(j & 63) * C + c]; re = v.re; im = v.im; return; }
+        const float *tj = cur + (size_t)(j - k0) * NT;
+        cf om = ringMc[j & 63];
+        float tRe = tj[16 + C + 2 * c], tIm = tj[16 + C + 2 * c + 1];
+        float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
+        float n2 = (qIm * qIm) + (qRe * qRe);
+        cf fb = {0.f, 0.f};
+        if (!(n2 > 1e-15f)) fb = predIn[(size_t)c * B + j];
+        make_output(tj[16 + c], fb, qRe, qIm, re, im);
+      };
       if (lane == 0) {
-        for (int k = k0; k < k1; ++k) {
-          const float *tt = cur + (size_t)(k - k0) * NT;
-          const int mc = __float_as_int_hd(tt[11]);
-          float phRe = 0.f, phIm = 0.f;
-          if (k > 0) {
-            const float *po = tileO + (size_t)((k - 1) & 63) * 2 * C + 2 * mc;
-            float oRe = po[0], oIm = po[1], tRe = tt[0], tIm = tt[1];
-            phIm = (tIm * oRe) + (tRe * oIm); phRe = (tRe * oRe) - (tIm * oIm);
-            if (k >= longStep) {
-              const float *pl = tileO + (size_t)((k - longStep) & 63) * 2 * C + 2 * mc;
-              oRe = pl[0]; oIm = pl[1]; tRe = tt[2]; tIm = tt[3];
-              phIm = ((tRe * oIm) + phIm) + (tIm * oRe);
-              phRe = ((tRe * oRe) + phRe) - (oIm * tIm);
+        if (k0 >= longStep && k1 <= B - longStep && longStep >= 2) {
+          // interior tile: no edge cases; next bin's terms and long-step history are fetched one bin ahead
+          const float *tt = cur;
+          f4 ta = *(const f4 *)tt, tb = *(const f4 *)(tt + 4), tc = *(const f4 *)(tt + 8), td = *(const f4 *)(tt + 12);
+          cf oL = ringMc[(k0 - longStep) & 63]; int iL = ringIdx[(k0 - longStep) & 63];
+          for (int k = k0; k < k1; ++k) {
+            const float *tn = tt + NT;
+            const f4 na = *(const f4 *)tn, nb = *(const f4 *)(tn + 4), nc = *(const f4 *)(tn + 8), nd = *(const f4 *)(tn + 12);
+            const cf noL = ringMc[(k + 1 - longStep) & 63]; const int niL = ringIdx[(k + 1 - longStep) & 63];
+            const int mc = __float_as_int_hd(tc.w);
+            float oRe = pr, oIm = pi_, lRe = oL.re, lIm = oL.im;
+            if ((mc != mcPrev) | (iL != mc)) {
+              if (mc != mcPrev) follower(k - 1, mc, oRe, oIm);
+              if (iL != mc) follower(k - longStep, mc, lRe, lIm);
             }
+            float phIm = (ta.y * oRe) + (ta.x * oIm), phRe = (ta.x * oRe) - (ta.y * oIm);
+            phIm = ((ta.z * lIm) + phIm) + (ta.w * lRe);
+            phRe = ((ta.z * lRe) + phRe) - (lIm * ta.w);
+            phIm = tc.x + phIm; phRe = (tb.x + phRe) + tb.y;
+            phIm = (tc.y + phIm) - tc.z; phRe = (tb.z + phRe) + tb.w;
+            const float n2 = (phIm * phIm) + (phRe * phRe);
+            float div = n2;
+            if (!(n2 > 1e-15f)) { phRe = td.y; phIm = td.z; div = ((phRe * phRe) + 1e-15f) + (phIm * phIm); }
+            const float sc = sqrtf(td.x / div);
+            pi_ = sc * phIm; pr = sc * phRe; mcPrev = mc;
+            cf o; o.re = pr; o.im = pi_;
+            ringMc[k & 63] = o; ringIdx[k & 63] = mc;
+            ta = na; tb = nb; tc = nc; td = nd; oL = noL; iL = niL; tt = tn;
           }
-          if (k < B - 1) {
-            phIm = tt[8] + phIm;
-            phRe = (tt[4] + phRe) + tt[5];
-            if (k < B - longStep) {
-              phIm = (tt[9] + phIm) - tt[10];
-              phRe = (tt[6] + phRe) + tt[7];
+        } else {
+          for (int k = k0; k < k1; ++k) {
+            const float *tt = cur + (size_t)(k - k0) * NT;
+            const f4 ta = *(const f4 *)tt, tb = *(const f4 *)(tt + 4), tc = *(const f4 *)(tt + 8), td = *(const f4 *)(tt + 12);
+            const int mc = __float_as_int_hd(tc.w);
+            float phRe = 0.f, phIm = 0.f, oRe, oIm;
+            if (k > 0) {
+              if (mc == mcPrev) { oRe = pr; oIm = pi_; } else follower(k - 1, mc, oRe, oIm);
+              phIm = (ta.y * oRe) + (ta.x * oIm); phRe = (ta.x * oRe) - (ta.y * oIm);
+              if (k >= longStep) {
+                const int j = k - longStep;
+                if (ringIdx[j & 63] == mc) { cf v = ringMc[j & 63]; oRe = v.re; oIm = v.im; } else follower(j, mc, oRe, oIm);
+                phIm = ((ta.z * oIm) + phIm) + (ta.w * oRe);
+                phRe = ((ta.z * oRe) + phRe) - (oIm * ta.w);
+              }
             }
-          }
-          float oRe, oIm;
-          {
-            float n2 = (phIm * phIm) + (phRe * phRe);
-            cf fb = {0.f, 0.f};
-            if (!(n2 > 1e-15f)) fb = predIn[(size_t)mc * B + k];
-            make_output(tt[12 + mc], fb, phRe, phIm, oRe, oIm);
-          }
-          float *wo = tileO + (size_t)(k & 63) * 2 * C;
-          wo[2 * mc] = oRe; wo[2 * mc + 1] = oIm;
-          for (int c = 0; c < C; ++c) {
-            if (c == mc) continue;
-            float tRe = tt[12 + C + 2 * c], tIm = tt[12 + C + 2 * c + 1];
-            float qIm = (tIm * oRe) + (tRe * oIm), qRe = (tRe * oRe) - (tIm * oIm);
-            float n2 = (qIm * qIm) + (qRe * qRe);
-            cf fb = {0.f, 0.f};
-            if (!(n2 > 1e-15f)) fb = predIn[(size_t)c * B + k];
-            float cr, ci;
-            make_output(tt[12 + c], fb, qRe, qIm, cr, ci);
-            wo[2 * c] = cr; wo[2 * c + 1] = ci;
+            if (k < B - 1) {
+              phIm = tc.x + phIm;
+              phRe = (tb.x + phRe) + tb.y;
+              if (k < B - longStep) {
+                phIm = (tc.y + phIm) - tc.z;
+                phRe = (tb.z + phRe) + tb.w;
+              }
+            }
+            cf fb; fb.re = td.y; fb.im = td.z;
+            make_output(td.x, fb, phRe, phIm, oRe, oIm);
+            pr = oRe; pi_ = oIm; mcPrev = mc;
+            cf o; o.re = oRe; o.im = oIm;
+            ringMc[k & 63] = o; ringIdx[k & 63] = mc;
           }
         }
       }
       BS_WARPSYNC();
-      for (int i = lane; i < (k1 - k0) * C; i += lanes) {   // coalesced write-back of this tile
-        int c = i / (k1 - k0), kk = k0 + (i - c * (k1 - k0));
-        const float *po = tileO + (size_t)(kk & 63) * 2 * C + 2 * c;
-        cf o; o.re = po[0]; o.im = po[1];
-        outSpec[(size_t)c * B + kk] = o;
-        specOut[(size_t)c * B + kk] = o;
+      for (int j = lane; j < k1 - k0; j += lanes) {   // followers of this tile + coalesced write-back
+        const int kk = k0 + j;
+        const int mc = ringIdx[kk & 63];
+        const cf om = ringMc[kk & 63];
+        for (int c = 0; c < C; ++c) {
+          cf o = om;
+          if (c != mc) follower(kk, c, o.re, o.im);
+          ringFull[(size_t)(kk & 63) * C + c] = o;
+          outSpec[(size_t)c * B + kk] = o;
+          specOut[(size_t)c * B + kk] = o;
+        }
       }
       BS_WARPSYNC();
     }
     if (lane == 0 && randomTF && B >= 2) *rngp = minstd_jump(rng0, (uint32_t)(2 * B - 2));
   }
   BS_SYNC();
-  if (keepInput && isNew) {
-    for (int idx = tid; idx < C * B; idx += nt) lastInput[idx] = inp[idx];
-    BS_SYNC();
-  }
+  BS_MARK(8);
 }
+
+// input spectrum of block m: the "current" analysis of the most recent block that had a new spectrum
+BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, int slot0, int nSlots, const cf *specIn,
+                                                 const cf *lastInput) {
+  const size_t CB = (size_t)g.C * g.B;
+  if (r2.lastNew >= slot0) return specIn + (((size_t)s * nSlots + (r2.lastNew - slot0)) * 2 + 0) * CB;
+  return lastInput + (size_t)s * CB;
+}
+BS_HD bool needs_inline_map(const BlockRec &rec) { return (rec.flags & kFormants) && !(rec.fmBaseFreq > 0.f); }
+
 
 }  // namespace bs
