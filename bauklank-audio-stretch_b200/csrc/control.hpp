@@ -68,8 +68,12 @@ class Control {
 
   // Emulates `count` output samples of one process(nIn, nOut) call starting at output index idx0, during which the
   // parameters `p` do not change.  onStart(idx, inputOffset, inputInterval, rec index) is called when a block starts.
+  struct NoSpan { void operator()(int, int, uint32_t) const {} };
   template <class StartFn>
-  void run(StreamPlan &plan, int idx0, int count, int nIn, int nOut, StartFn &&onStart) {
+  void run(StreamPlan &plan, int idx0, int count, int nIn, int nOut, StartFn &&onStart) { run(plan, idx0, count, nIn, nOut, onStart, NoSpan()); }
+  // onSpan(idx, span, since): `span` output samples starting at call index idx, `since` samples after the block start
+  template <class StartFn, class SpanFn>
+  void run(StreamPlan &plan, int idx0, int count, int nIn, int nOut, StartFn &&onStart, SpanFn &&onSpan) {
     const int H = g_.H, C = g_.C;
     float invOut = 1.0f / (float)(uint32_t)nOut, fIn = (float)nIn;
     int idx = idx0, end = idx0 + count;
@@ -126,11 +130,15 @@ class Control {
       }
       if (cur_ >= 0 && toStep > step_) snapshot(plan, step_, toStep);
       if (toStep > step_) step_ = toStep;
+      onSpan(idx, span, since_);
       since_ += (uint32_t)span;
       idx += span;
     }
   }
   void endCall(int nIn) { prevInputOffset_ -= nIn; }
+  // `blockProcess = {}` of the silence gate (W#48 7842-7845) and of reset() (W#59)
+  void resetBlockProcess() { since_ = 0xffffffffu; steps_ = 0; step_ = 0; cur_ = -1; }
+  void resetAll() { resetBlockProcess(); prevInputOffset_ = -1; didSeek_ = false; }
 
  private:
   void snapshot(StreamPlan &plan, int from, int to) {

@@ -42,14 +42,14 @@ static void dzero(void *p, size_t n, stream_t s) { cudaMemsetAsync(p, 0, n, s); 
 static void h2d(void *d, const void *h, size_t n, stream_t s) { cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s); }
 
 __global__ void __launch_bounds__(256) analysis_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                       const Window *windows, int slot0, int nSlots, cf *specIn) {
+                                                       const Window *windows, long long slot0, int nSlots, cf *specIn) {
   extern __shared__ float sm[];
   int idx = blockIdx.x;
   const int c = idx % g.C; idx /= g.C;
   const int which = idx & 1; idx >>= 1;
   const int slot = idx % nSlots; const int s = idx / nSlots;
   const StreamDev sd = streams[s];
-  const long long m = (long long)slot0 + slot;
+  const long long m = slot0 + slot;
   if (m >= sd.nBlocks) return;
   if (!(blocks[sd.blockBase + m].flags & kNew)) return;
   const Window w = windows[2 * (sd.blockBase + m) + which];
@@ -59,12 +59,12 @@ __global__ void __launch_bounds__(256) analysis_kernel(DevGeom g, DevTables T, c
 
 // premap: the state-independent half of the spectral stage for every (stream, block) of the chunk in parallel
 __global__ void __launch_bounds__(128) premap_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                     const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, StateDev st) {
+                                                     const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, StateDev st) {
   extern __shared__ float4 sm4[];
   float *sm = (float *)sm4;
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
   const StreamDev sd = streams[s];
-  const long long m = (long long)slot0 + t;
+  const long long m = slot0 + t;
   if (m >= sd.nBlocks) return;
   const BlockRec rec = blocks[sd.blockBase + m];
   if (needs_inline_map(rec)) return;
@@ -79,14 +79,14 @@ __global__ void __launch_bounds__(128) premap_kernel(DevGeom g, DevTables T, con
 
 template <int CT>
 __device__ __forceinline__ void spectral_stream(const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
-                                                const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, cf *specOut,
+                                                const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut,
                                                 const StateDev &st, float *sm) {
   const int s = blockIdx.x;
   const StreamDev sd = streams[s];
   const size_t CB = (size_t)g.C * g.B;
   long long mLast = -1;
   for (int t = 0; t < nSlots; ++t) {
-    const long long m = (long long)slot0 + t;
+    const long long m = slot0 + t;
     if (m >= sd.nBlocks) break;
     mLast = m;
     const BlockRec rec = blocks[sd.blockBase + m];
@@ -99,7 +99,7 @@ __device__ __forceinline__ void spectral_stream(const DevGeom &g, const DevTable
                        threadIdx.x, blockDim.x);
   }
   // carry the input spectrum into the next chunk if its first block reuses it (no new spectrum there)
-  if (mLast >= 0 && mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew)) {
+  if (mLast >= 0 && (g.incremental || (mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew)))) {
     const BlockRec2 r2 = blocks2[sd.blockBase + mLast];
     if (r2.lastNew >= slot0) {
       const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput);
@@ -110,7 +110,7 @@ __device__ __forceinline__ void spectral_stream(const DevGeom &g, const DevTable
 }
 
 __global__ void __launch_bounds__(256) spectral_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                       const BlockRec2 *blocks2, int slot0, int nSlots, const cf *specIn, cf *specOut,
+                                                       const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut,
                                                        StateDev st) {
   extern __shared__ float4 sm4[];
   float *sm = (float *)sm4;
@@ -119,14 +119,14 @@ __global__ void __launch_bounds__(256) spectral_kernel(DevGeom g, DevTables T, c
   else spectral_stream<0>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, sm);
 }
 
-__global__ void __launch_bounds__(256) synthesis_kernel(DevGeom g, DevTables T, const StreamDev *streams, int slot0, int nSlots,
-                                                        const cf *specOut, StateDev st) {
+__global__ void __launch_bounds__(256) synthesis_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
+                                                        int mode, const cf *specOut, StateDev st) {
   extern __shared__ float sm[];
   const int s = blockIdx.x / g.C, c = blockIdx.x % g.C;
   const StreamDev sd = streams[s];
   float *ring = sm + 4 * (size_t)g.M;
-  synth_stream(g, T, sd, c, slot0, nSlots, specOut + (size_t)s * nSlots * g.C * g.B, st.ring + ((size_t)s * g.C + c) * g.L, sm, ring,
-               threadIdx.x, blockDim.x);
+  synth_stream(g, T, sd, c, slot0, nSlots, mode, specOut + (size_t)s * nSlots * g.C * g.B, st.ring + ((size_t)s * g.C + c) * g.L, sm,
+               ring, threadIdx.x, blockDim.x);
 }
 #endif
 
@@ -183,6 +183,113 @@ static void free_batch(bsb_engine *e) {
   e->batchOwned.clear(); e->committed = false;
 }
 
+static void reset_state(bsb_engine *e, stream_t q) {
+  const Geometry &g = e->g;
+  const int S = (int)e->hs.size();
+  const size_t CB = (size_t)g.C * g.B;
+  StateDev &st = e->st;
+  // reset(): zero phase state, rings, maps; seed the RNGs
+  dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE, S * CB * sizeof(float), q);
+  dzero(st.lastInput, S * CB * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
+  dzero(st.ring, (size_t)S * g.C * g.L * sizeof(float), q);
+#ifdef BS_HOSTEMU
+  std::memcpy(st.rng, e->dSeeds, S * sizeof(uint32_t));
+#else
+  cudaMemcpyAsync(st.rng, e->dSeeds, S * sizeof(uint32_t), cudaMemcpyDeviceToDevice, q);
+#endif
+}
+
+// one time-chunk: stages bit0 = analysis + premap + spectral, bit1 = synthesis (with `synthMode`)
+static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, int stages, int synthMode) {
+  const Geometry &g = e->g;
+  const int S = (int)e->hs.size();
+  const size_t CB = (size_t)g.C * g.B;
+  StateDev &st = e->st;
+  const int nt = 256;
+  (void)nt; (void)q;
+#ifdef BS_HOSTEMU
+  std::vector<f4> smv((spectral_smem_floats(g.B, g.C) + 4 * (size_t)g.M + g.L + 64) / 4 + 1);
+  float *sm = (float *)smv.data();
+  auto mapFn = g.C == 2 ? map_stage<2> : (g.C == 1 ? map_stage<1> : map_stage<0>);
+  auto specFn = g.C == 2 ? spectral_block<2> : (g.C == 1 ? spectral_block<1> : spectral_block<0>);
+  if (stages & 1) {
+  for (int s = 0; s < S; ++s) {   // analysis_kernel
+    const StreamDev &sd = e->hs[s];
+    for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+      long long m = slot0 + t;
+      if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
+      for (int which = 0; which < 2; ++which)
+        for (int c = 0; c < g.C; ++c)
+          analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
+                         e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1);
+    }
+  }
+  for (int s = 0; s < S; ++s) {   // premap_kernel
+    const StreamDev &sd = e->hs[s];
+    for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+      long long m = slot0 + t;
+      const BlockRec rec = e->dBlocks[sd.blockBase + m];
+      if (needs_inline_map(rec)) continue;
+      const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
+      mapFn(e->dg, e->dt, rec, rec2, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput), nullptr,
+            st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, sm, 0, 1);
+    }
+  }
+  for (int s = 0; s < S; ++s) {   // spectral_kernel
+    const StreamDev &sd = e->hs[s];
+    long long mLast = -1;
+    for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+      long long m = slot0 + t; mLast = m;
+      const BlockRec rec = e->dBlocks[sd.blockBase + m];
+      const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
+      const cf *inp = block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput);
+      const cf *prev = (rec.flags & kNew) ? e->specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB : nullptr;
+      specFn(e->dg, e->dt, rec, rec2, inp, prev, st.outSpec + s * CB, st.predE + s * CB, st.rng + s, st.freqEst + 2 * s,
+             st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, st.predIn + s * CB,
+             st.terms + (size_t)s * g.B * nterms(g.C), e->specOut + ((size_t)s * nSlots + t) * CB, needs_inline_map(rec), sm, 0, 1);
+    }
+    if (mLast >= 0 && (e->dg.incremental || (mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew)))) {
+      const BlockRec2 r2 = e->dBlocks2[sd.blockBase + mLast];
+      if (r2.lastNew >= slot0)
+        std::memcpy(st.lastInput + (size_t)s * CB, block_input(e->dg, r2, s, slot0, nSlots, e->specIn, st.lastInput), CB * sizeof(cf));
+    }
+  }
+  }
+  if (stages & 2)
+  for (int s = 0; s < S; ++s)     // synthesis_kernel
+    for (int c = 0; c < g.C; ++c)
+      synth_stream(e->dg, e->dt, e->hs[s], c, slot0, nSlots, synthMode, e->specOut + (size_t)s * nSlots * CB,
+                   st.ring + ((size_t)s * g.C + c) * g.L, sm, sm + 4 * (size_t)g.M, 0, 1);
+  e->launches += ((stages & 1) ? 3 : 0) + ((stages & 2) ? 1 : 0);
+#else
+  const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
+  const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float), smM = map_smem_floats(g.B) * sizeof(float);
+  cudaEventRecord(e->ev[0], q);
+  if (stages & 1) {
+  analysis_kernel<<<(unsigned)((size_t)S * nSlots * 2 * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows,
+                                                                          slot0, nSlots, e->specIn);
+  premap_kernel<<<(unsigned)((size_t)S * nSlots), 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots,
+                                                                e->specIn, st);
+  cudaEventRecord(e->ev[1], q);
+  spectral_kernel<<<S, nt, smS, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st);
+  e->launches += 3;
+  }
+  cudaEventRecord(e->ev[2], q);
+  if (stages & 2) {
+    synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, e->specOut, st);
+    e->launches += 1;
+  }
+  cudaEventRecord(e->ev[3], q);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
+  if (getenv("BS_KERNEL_TIMES")) {   // per-kernel split (serialises the chunks; not used for throughput numbers)
+    cudaEventSynchronize(e->ev[3]);
+    for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->kms[i] += ms; }
+  }
+#endif
+  return 0;
+}
+
 extern "C" {
 
 bsb_engine *bsb_create(int channels, int block, int interval, int split, double sampleRate) {
@@ -195,7 +302,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   if (e->g.longStep < 1 || e->g.longStep > 32) { delete e; return nullptr; }
   make_tables(e->g, e->T);
   const Geometry &g = e->g;
-  e->dg = DevGeom{g.C, g.L, g.H, g.N, g.B, g.M, g.inner, g.outer, g.split, g.longStep, g.L >> 1, (int)e->T.wpStart.size()};
+  e->dg = DevGeom{g.C, g.L, g.H, g.N, g.B, g.M, g.inner, g.outer, g.split, g.longStep, g.L >> 1, (int)e->T.wpStart.size(), 0};
   e->dt.win = upload(e, e->T.win, e->owned); e->dt.tw = upload(e, e->T.tw, e->owned);
   e->dt.otr = upload(e, e->T.otr, e->owned); e->dt.oti = upload(e, e->T.oti, e->owned);
   e->dt.untangle = upload(e, e->T.untangle, e->owned); e->dt.rot = upload(e, e->T.rot, e->owned);
@@ -318,7 +425,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
     windows.insert(windows.end(), st.plan.windows.begin(), st.plan.windows.end());
     StreamDev &d = e->hs[s];
     d.clip = st.clip; d.out = st.out; d.clipLen = st.clipLen; d.nOut = st.plan.nOut; d.blockBase = e->blockBase[s];
-    d.nBlocks = (int)st.plan.blocks.size();
+    d.nBlocks = (long long)st.plan.blocks.size(); d.outStride = st.plan.nOut; d.outBase = 0;
     e->maxBlocks = std::max<long long>(e->maxBlocks, d.nBlocks);
     uint32_t sd = st.seed % 2147483647u; seeds[s] = sd <= 1u ? 1u : sd;   // W#26: minstd_rand seeding
   }
@@ -359,93 +466,11 @@ int bsb_run(bsb_engine *e, void *cudaStream) {
   const size_t CB = (size_t)g.C * g.B;
   stream_t q = (stream_t)cudaStream;
   StateDev &st = e->st;
-  // reset(): zero phase state, rings, maps; seed the RNGs
-  dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE, S * CB * sizeof(float), q);
-  dzero(st.lastInput, S * CB * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
-  dzero(st.ring, (size_t)S * g.C * g.L * sizeof(float), q);
-#ifdef BS_HOSTEMU
-  std::memcpy(st.rng, e->dSeeds, S * sizeof(uint32_t));
-#else
-  cudaMemcpyAsync(st.rng, e->dSeeds, S * sizeof(uint32_t), cudaMemcpyDeviceToDevice, q);
-#endif
+  reset_state(e, q);
   e->launches = 0;
   e->kms[0] = e->kms[1] = e->kms[2] = 0.f;
-  const int nt = 256;
-  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk) {
-    const int nSlots = e->chunk;
-#ifdef BS_HOSTEMU
-    std::vector<f4> smv((spectral_smem_floats(g.B, g.C) + 4 * (size_t)g.M + g.L + 64) / 4 + 1);
-    float *sm = (float *)smv.data();
-    auto mapFn = g.C == 2 ? map_stage<2> : (g.C == 1 ? map_stage<1> : map_stage<0>);
-    auto specFn = g.C == 2 ? spectral_block<2> : (g.C == 1 ? spectral_block<1> : spectral_block<0>);
-    for (int s = 0; s < S; ++s) {   // analysis_kernel
-      const StreamDev &sd = e->hs[s];
-      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
-        long long m = slot0 + t;
-        if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
-        for (int which = 0; which < 2; ++which)
-          for (int c = 0; c < g.C; ++c)
-            analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
-                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1);
-      }
-    }
-    for (int s = 0; s < S; ++s) {   // premap_kernel
-      const StreamDev &sd = e->hs[s];
-      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
-        long long m = slot0 + t;
-        const BlockRec rec = e->dBlocks[sd.blockBase + m];
-        if (needs_inline_map(rec)) continue;
-        const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
-        mapFn(e->dg, e->dt, rec, rec2, block_input(e->dg, rec2, s, (int)slot0, nSlots, e->specIn, st.lastInput), nullptr,
-              st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, sm, 0, 1);
-      }
-    }
-    for (int s = 0; s < S; ++s) {   // spectral_kernel
-      const StreamDev &sd = e->hs[s];
-      long long mLast = -1;
-      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
-        long long m = slot0 + t; mLast = m;
-        const BlockRec rec = e->dBlocks[sd.blockBase + m];
-        const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
-        const cf *inp = block_input(e->dg, rec2, s, (int)slot0, nSlots, e->specIn, st.lastInput);
-        const cf *prev = (rec.flags & kNew) ? e->specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB : nullptr;
-        specFn(e->dg, e->dt, rec, rec2, inp, prev, st.outSpec + s * CB, st.predE + s * CB, st.rng + s, st.freqEst + 2 * s,
-               st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, st.predIn + s * CB,
-               st.terms + (size_t)s * g.B * nterms(g.C), e->specOut + ((size_t)s * nSlots + t) * CB, needs_inline_map(rec), sm, 0, 1);
-      }
-      if (mLast >= 0 && mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew)) {
-        const BlockRec2 r2 = e->dBlocks2[sd.blockBase + mLast];
-        if (r2.lastNew >= slot0)
-          std::memcpy(st.lastInput + (size_t)s * CB, block_input(e->dg, r2, s, (int)slot0, nSlots, e->specIn, st.lastInput), CB * sizeof(cf));
-      }
-    }
-    for (int s = 0; s < S; ++s)     // synthesis_kernel
-      for (int c = 0; c < g.C; ++c)
-        synth_stream(e->dg, e->dt, e->hs[s], c, (int)slot0, nSlots, e->specOut + (size_t)s * nSlots * CB,
-                     st.ring + ((size_t)s * g.C + c) * g.L, sm, sm + 4 * (size_t)g.M, 0, 1);
-    e->launches += 4;
-#else
-    const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
-    const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float), smM = map_smem_floats(g.B) * sizeof(float);
-    cudaEventRecord(e->ev[0], q);
-    analysis_kernel<<<(unsigned)((size_t)S * nSlots * 2 * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows,
-                                                                            (int)slot0, nSlots, e->specIn);
-    premap_kernel<<<(unsigned)((size_t)S * nSlots), 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, (int)slot0, nSlots,
-                                                                  e->specIn, st);
-    cudaEventRecord(e->ev[1], q);
-    spectral_kernel<<<S, nt, smS, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, (int)slot0, nSlots, e->specIn, e->specOut, st);
-    cudaEventRecord(e->ev[2], q);
-    synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, (int)slot0, nSlots, e->specOut, st);
-    cudaEventRecord(e->ev[3], q);
-    e->launches += 4;
-    cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
-    if (getenv("BS_KERNEL_TIMES")) {   // per-kernel split (serialises the chunks; not used for throughput numbers)
-      cudaEventSynchronize(e->ev[3]);
-      for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->kms[i] += ms; }
-    }
-#endif
-  }
+  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk)
+    if (launch_chunk(e, slot0, e->chunk, q, 3, kSynthEmit | kSynthAdd)) return -1;
   return 0;
 }
 
@@ -459,6 +484,243 @@ int bsb_block_info(const bsb_engine *e, int s, long long b, long long out[8]) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Part 1 of the header: the reference's own 18 entry points for one "current" engine instance.
+// Host side keeps what the reference keeps in wasm linear memory (I/O buffer, input ring) and runs the same control
+// flow as W#48/W#49; every block's DSP runs on the GPU through the kernels above, one block at a time.
+namespace {
+
+#ifdef BS_HOSTEMU
+void d2h_sync(void *h, const void *d, size_t n) { std::memcpy(h, d, n); }
+#else
+void d2h_sync(void *h, const void *d, size_t n) {
+  if (cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost) != cudaSuccess) bs::die("device error while reading output samples");
+}
+#endif
+
+struct Compat {
+  bsb_engine *e = nullptr;
+  Geometry g{};
+  std::unique_ptr<Control> ctl;
+  Params p;
+  uint32_t seed = 1;
+  std::vector<float> io; int ioCh = 0, ioLen = 0;
+  std::vector<float> ring; int ringPos = 0, inLen = 0;   // stft input ring [C][L+H+1]
+  std::vector<float> lastCur, stage, pending;            // [C][L], [C][2L], [C][H]
+  float *dStage = nullptr, *dOut = nullptr;
+  StreamPlan plan;
+  long long m = -1;            // block whose interval is being emitted
+  bool deferred = false;       // split mode: block m's spectral work not launched yet
+  Window dWin[2]{};
+  bool curLaunched = false;
+  uint32_t silenceCounter = 0; bool silenceFirst = true;
+  int prevCopied = 0;
+};
+Compat *cc() { static Compat c; return &c; }
+
+void compat_free(Compat *c) {
+  if (c->e) { bsb_destroy(c->e); c->e = nullptr; }
+  if (c->dStage) dfree(c->dStage);
+  if (c->dOut) dfree(c->dOut);
+  c->dStage = c->dOut = nullptr;
+}
+
+// stft.reset + stretch reset (W#22, W#59): host ring, device state, control
+void compat_reset_state(Compat *c) {
+  const Geometry &g = c->g;
+  std::fill(c->ring.begin(), c->ring.end(), 0.f); c->ringPos = g.L;
+  std::fill(c->lastCur.begin(), c->lastCur.end(), 0.f);
+  std::fill(c->pending.begin(), c->pending.end(), 0.f);
+  reset_state(c->e, 0);
+  c->ctl->resetAll();
+  c->m = -1; c->deferred = false; c->curLaunched = false;
+  c->plan = StreamPlan();
+  c->dWin[0] = Window{0, 0, g.L}; c->dWin[1] = Window{g.L, 0, g.L};
+  c->silenceCounter = 0;
+}
+
+void compat_configure(int ch, int L, int H, int split) {
+  Compat *c = cc();
+  compat_free(c);
+  c->e = bsb_create(ch, L, H, split, 48000.0);
+  if (!c->e) bs::die("configure failed: no CUDA device or unsupported block/interval (there is no CPU fallback)");
+  bsb_engine *e = c->e;
+  c->g = e->g; const Geometry &g = c->g;
+  e->dg.incremental = 1;
+  c->inLen = L + H + 1;
+  c->ring.assign((size_t)ch * c->inLen, 0.f);
+  c->lastCur.assign((size_t)ch * L, 0.f); c->stage.assign((size_t)ch * 2 * L, 0.f); c->pending.assign((size_t)ch * H, 0.f);
+  c->dStage = (float *)dmalloc((size_t)ch * 2 * L * sizeof(float)); c->dOut = (float *)dmalloc((size_t)ch * H * sizeof(float));
+  // a one-stream, one-slot batch whose single table entry is rewritten for every block
+  e->streams.assign(1, Stream()); e->streams[0].clip = c->dStage; e->streams[0].out = c->dOut; e->streams[0].clipLen = 2 * L;
+  e->streams[0].seed = c->seed; e->streams[0].planned = true;
+  e->streams[0].plan.blocks.assign(1, BlockRec{}); e->streams[0].plan.blocks2.assign(1, BlockRec2{}); e->streams[0].plan.windows.assign(2, Window{0, 0, 0});
+  e->streams[0].plan.nOut = H;
+  if (!c->dStage || !c->dOut || bsb_commit(e, 1) != 0) bs::die("configure: device allocation failed");
+  e->hs[0].nBlocks = (long long)1 << 60; e->hs[0].nOut = (long long)1 << 60; e->hs[0].outStride = H;
+  c->ctl.reset(new Control(g));
+  c->silenceFirst = true;
+  compat_reset_state(c);
+}
+
+void compat_launch(Compat *c, long long m, const BlockRec &rec, BlockRec2 rec2, const Window *win, int stages, int mode) {
+  bsb_engine *e = c->e;
+  rec2.lastNew = (rec.flags & kNew) ? (int)m : -1;
+  e->hs[0].blockBase = -m; e->hs[0].outBase = m * c->g.H;
+  h2d(e->dStreams, &e->hs[0], sizeof(StreamDev), 0);
+  if (stages & 1) {
+    h2d(e->dBlocks, &rec, sizeof(BlockRec), 0); h2d(e->dBlocks2, &rec2, sizeof(BlockRec2), 0);
+    h2d(e->dWindows, win, 2 * sizeof(Window), 0);
+  }
+  if (launch_chunk(e, m, 1, 0, stages, mode)) bs::die(e->err.c_str());
+}
+
+// W#24 copyInput(toIndex)
+void compat_copy_input(Compat *c, int toIndex) {
+  const Geometry &g = c->g;
+  int length = toIndex - c->prevCopied, cap = g.L + g.H;
+  if (length > cap) length = cap;
+  if (length > 0) {
+    int offset = toIndex - length;
+    for (int ch = 0; ch < g.C; ++ch) {
+      const float *src = c->io.data() + (size_t)c->ioLen * ch;
+      float *ring = c->ring.data() + (size_t)ch * c->inLen;
+      for (int i = 0; i < length; ++i) ring[(c->ringPos + i) % c->inLen] = src[offset + i];
+    }
+  }
+  c->ringPos = (int)(((uint32_t)length + (uint32_t)c->ringPos) % (uint32_t)c->inLen);
+  c->prevCopied = toIndex;
+}
+
+// the L samples the analysis at `samplesInPast` would read (W#35 3897-3902)
+void compat_window(Compat *c, int samplesInPast, float *dst /* [C][2L] stride */, int slot) {
+  const Geometry &g = c->g; const int len = c->inLen, L = g.L;
+  int start = (int)(((uint32_t)c->ringPos + ((uint32_t)len << 1) - (uint32_t)(samplesInPast + L)) % (uint32_t)len);
+  for (int ch = 0; ch < g.C; ++ch) {
+    const float *ring = c->ring.data() + (size_t)ch * len; float *d = dst + (size_t)ch * 2 * L + (size_t)slot * L;
+    for (int i = 0; i < L; ++i) d[i] = ring[(start + i) % len];
+  }
+}
+
+void compat_process(int nIn, int nOut) {
+  Compat *c = cc();
+  if (!c->e) bs::die("process() before configure()/presetDefault()/presetCheaper()");
+  const Geometry &g = c->g; const int C = g.C, L = g.L, H = g.H;
+  if (std::max(nIn, nOut) > c->ioLen) bs::die("process(): sample count exceeds the setBuffers() length");
+  c->prevCopied = 0;
+  float total = 0.f; bool loud = false;
+  if (C > 0 && nIn > 0) {
+    for (int ch = 0; ch < C; ++ch) { const float *x = c->io.data() + (size_t)c->ioLen * ch; for (int i = 0; i < nIn; ++i) total = (x[i] * x[i]) + total; }
+    loud = total >= 1e-15f;
+  }
+  float *outs = c->io.data() + (size_t)c->ioLen * C;
+  if (!loud) {   // silence gate, W#48 7838-7943
+    if (c->silenceCounter >= ((uint32_t)L << 1)) {
+      if (c->silenceFirst) {
+        c->silenceFirst = false; c->ctl->resetBlockProcess();
+        const size_t CB = (size_t)C * g.B;
+        dzero(c->e->st.outSpec, CB * sizeof(cf), 0); dzero(c->e->st.lastInput, CB * sizeof(cf), 0);
+      }
+      if (nIn > 0) {
+        for (int i = 0, j = 0; i < nOut; ++i) { for (int ch = 0; ch < C; ++ch) outs[(size_t)c->ioLen * ch + i] = c->io[(size_t)c->ioLen * ch + j]; j = (j + 1 != nIn) ? j + 1 : 0; }
+      } else {
+        for (int ch = 0; ch < C; ++ch) for (int i = 0; i < nOut; ++i) outs[(size_t)c->ioLen * ch + i] = 0.f;
+      }
+      compat_copy_input(c, nIn);
+      return;
+    }
+    c->silenceCounter += (uint32_t)nIn;
+  } else { c->silenceFirst = true; c->silenceCounter = 0; }
+
+  c->ctl->p = c->p;
+  // c->plan keeps one record per block since the last reset (40 bytes per block); block m is plan.blocks[m]
+  auto onStart = [&](int, int inputOffset, int, bool rean, bool isNew, long long bi) {
+    compat_copy_input(c, inputOffset);
+    if (c->deferred) {   // split mode: every step of the previous block has run by now, its records are final
+      compat_launch(c, c->m, c->plan.blocks[c->m], c->plan.blocks2[c->m], c->dWin, 1 | 2, kSynthAdd);
+      c->deferred = false;
+    }
+    c->m = bi; c->curLaunched = false;
+    if (isNew) {
+      compat_window(c, 0, c->stage.data(), 0);
+      if (rean) compat_window(c, H, c->stage.data(), 1);
+      else for (int ch = 0; ch < C; ++ch) std::memcpy(c->stage.data() + (size_t)ch * 2 * L + L, c->lastCur.data() + (size_t)ch * L, L * sizeof(float));
+      for (int ch = 0; ch < C; ++ch) std::memcpy(c->lastCur.data() + (size_t)ch * L, c->stage.data() + (size_t)ch * 2 * L, L * sizeof(float));
+      h2d(c->dStage, c->stage.data(), c->stage.size() * sizeof(float), 0);
+    }
+    if (g.split) {   // this interval's samples come from the blocks before; the block itself runs when its steps are done
+      compat_launch(c, c->m, BlockRec{}, BlockRec2{}, c->dWin, 2, kSynthEmit);
+      d2h_sync(c->pending.data(), c->dOut, c->pending.size() * sizeof(float));
+      c->deferred = true; c->curLaunched = true;
+    }
+  };
+  auto onSpan = [&](int idx, int span, uint32_t since) {
+    if (!c->curLaunched) {   // non-split: every step of the block ran at its first sample, with the current parameters
+      compat_launch(c, c->m, c->plan.blocks[c->m], c->plan.blocks2[c->m], c->dWin, 1 | 2, kSynthEmit | kSynthAdd);
+      d2h_sync(c->pending.data(), c->dOut, c->pending.size() * sizeof(float));
+      c->curLaunched = true;
+    }
+    for (int ch = 0; ch < C; ++ch)
+      std::memcpy(outs + (size_t)c->ioLen * ch + idx, c->pending.data() + (size_t)ch * H + since, (size_t)span * sizeof(float));
+  };
+  c->ctl->run(c->plan, 0, nOut, nIn, nOut, onStart, onSpan);
+  compat_copy_input(c, nIn);
+  c->ctl->endCall(nIn);
+}
+
+void compat_seek(int n, double rate) {   // W#49
+  Compat *c = cc();
+  if (!c->e) bs::die("seek() before configure()");
+  const Geometry &g = c->g; const int cap = g.L + g.H;
+  if (n > c->ioLen) bs::die("seek(): sample count exceeds the setBuffers() length");
+  std::vector<float> tmp(cap, 0.f);
+  int start = n - cap; if (start < 0) start = 0;
+  float energy = 0.f;
+  for (int ch = 0; ch < g.C; ++ch) {
+    const float *x = c->io.data() + (size_t)c->ioLen * ch;
+    for (int i = start; i < n; ++i) { float v = x[i]; tmp[i + (cap - n)] = v; energy = (v * v) + energy; }
+    float *ring = c->ring.data() + (size_t)ch * c->inLen;
+    for (int i = 0; i < cap; ++i) ring[(c->ringPos + i) % c->inLen] = tmp[i];
+  }
+  c->ringPos = (c->ringPos + cap) % c->inLen;
+  if (energy >= 1e-15f) { c->silenceCounter = 0; c->silenceFirst = true; }
+  c->ctl->seek(rate);
+}
+
+}  // namespace
+
+extern "C" {
+float *setBuffers(int channels, int length) {
+  Compat *c = cc();
+  c->io.assign((size_t)2 * channels * length, 0.f); c->ioCh = channels; c->ioLen = length;
+  return c->io.data();
+}
+int blockSamples(void) { return cc()->g.L; }
+int intervalSamples(void) { return cc()->g.H; }
+int inputLatency(void) { return cc()->g.inLat; }
+int outputLatency(void) { return cc()->g.outLat; }
+void reset(void) { Compat *c = cc(); if (!c->e) bs::die("reset() before configure()"); compat_reset_state(c); }
+void presetDefault(int channels, float sampleRate) { double d = (double)sampleRate; compat_configure(channels, (int)(d * 0.12), (int)(d * 0.03), 0); }
+void presetCheaper(int channels, float sampleRate) { double d = (double)sampleRate; compat_configure(channels, (int)(d * 0.1), (int)(d * 0.04), 1); }
+void configure(int channels, int block, int interval, int split) { compat_configure(channels, block, interval, split); }
+void setTransposeFactor(float m, float tl) { cc()->p.setTransposeFactor(m, tl); }
+void setTransposeSemitones(float st, float tl) { cc()->p.setTransposeSemitones(st, tl); }
+void setFormantFactor(float m, int comp) { cc()->p.setFormantFactor(m, comp); }
+void setFormantSemitones(float st, int comp) { cc()->p.setFormantSemitones(st, comp); }
+void setFormantBase(float f) { cc()->p.setFormantBase(f); }
+void seek(int n, double rate) { compat_seek(n, rate); }
+void process(int nIn, int nOut) { compat_process(nIn, nOut); }
+void flush(int) { bs::die("flush() is exported by the reference but never called by its JS (app/SignalsmithStretch.mjs:479); not implemented"); }
+int stretch_main(int, char **) { return 0; }
+void stretch_set_seed(uint32_t seed) {
+  Compat *c = cc(); c->seed = seed;
+  if (c->e) {   // W#26: minstd_rand(seed): state = seed % (2^31-1), 0 and 1 map to 1
+    uint32_t sd = seed % 2147483647u; sd = sd <= 1u ? 1u : sd;
+    h2d(c->e->dSeeds, &sd, sizeof sd, 0); h2d(c->e->st.rng, &sd, sizeof sd, 0);
+  }
+}
+}
 
 #if defined(BS_PHASE_TIMING) && !defined(BS_HOSTEMU)
 extern "C" void bs_debug_phase_cycles(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16); }

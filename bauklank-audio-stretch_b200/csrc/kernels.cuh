@@ -48,7 +48,9 @@ namespace bs {
 struct DevGeom {
   int C, L, H, N, B, M, inner, outer, split, longStep, off;  // off = L>>1 (analysis/synthesis offset)
   int wpStartLen;
+  int incremental;  // blocks arrive one at a time (compat shim): always carry the input spectrum forward
 };
+enum : int { kSynthEmit = 1, kSynthAdd = 2 };
 struct DevTables {
   const float *win; const cf *tw; const float *otr, *oti; const cf *untangle, *rot, *specRot;
   const float *wpStart, *wpSteady;
@@ -59,8 +61,9 @@ struct StreamDev {
   float *out;             // planar [C][nOut]
   long long clipLen, nOut;
   long long blockBase;    // index of this stream's first block in the global block/window arrays
-  int nBlocks;
-  int pad;
+  long long outStride;    // channel stride of `out`
+  long long outBase;      // output sample n is stored at out[c*outStride + n - outBase]
+  long long nBlocks;
 };
 // persistent per-stream state + scratch (all device pointers, stream-major)
 struct StateDev {
@@ -265,27 +268,29 @@ BS_HD float wp_at(const DevGeom &g, const DevTables &T, long long n) {
 }
 
 // one chunk of one (stream, channel): ring persists in global memory between chunks
-BS_HD void synth_stream(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, int slot0, int nSlots,
+BS_HD void synth_stream(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, long long slot0, int nSlots, int mode,
                         const cf *specOut /* this stream's [slot][C][B] */, float *ringG, float *sm, float *ring, int tid, int nt) {
   const int L = g.L, H = g.H;
   for (int i = tid; i < L; i += nt) ring[i] = ringG[i];
   BS_SYNC();
   for (int t = 0; t < nSlots; ++t) {
-    long long m = (long long)slot0 + t;
+    long long m = slot0 + t;
     if (m >= sd.nBlocks) break;
     int pos = (int)((m * H) % L);
     const cf *X = specOut + ((size_t)t * g.C + c) * g.B;
-    if (!g.split) synth_frame(g, T, X, ring, pos, sm, tid, nt);
-    long long n0 = m * H;
-    float *outc = sd.out + (size_t)c * sd.nOut;
-    for (int j = tid; j < H; j += nt) {
-      long long n = n0 + j;
-      int p = pos + j; if (p >= L) p -= L;
-      if (n < sd.nOut) outc[n] = ring[p] / wp_at(g, T, n);
-      ring[p] = 0.f;
+    if (!g.split && (mode & kSynthAdd)) synth_frame(g, T, X, ring, pos, sm, tid, nt);
+    if (mode & kSynthEmit) {
+      long long n0 = m * H;
+      float *outc = sd.out + (size_t)c * sd.outStride - sd.outBase;
+      for (int j = tid; j < H; j += nt) {
+        long long n = n0 + j;
+        int p = pos + j; if (p >= L) p -= L;
+        if (n < sd.nOut) outc[n] = ring[p] / wp_at(g, T, n);
+        ring[p] = 0.f;
+      }
+      BS_SYNC();
     }
-    BS_SYNC();
-    if (g.split) { int p2 = pos + H; if (p2 >= L) p2 -= L; synth_frame(g, T, X, ring, p2, sm, tid, nt); }
+    if (g.split && (mode & kSynthAdd)) { int p2 = pos + H; if (p2 >= L) p2 -= L; synth_frame(g, T, X, ring, p2, sm, tid, nt); }
   }
   for (int i = tid; i < L; i += nt) ringG[i] = ring[i];
 }
@@ -737,7 +742,7 @@ BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec r
 }
 
 // input spectrum of block m: the "current" analysis of the most recent block that had a new spectrum
-BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, int slot0, int nSlots, const cf *specIn,
+BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, long long slot0, int nSlots, const cf *specIn,
                                                  const cf *lastInput) {
   const size_t CB = (size_t)g.C * g.B;
   if (r2.lastNew >= slot0) return specIn + (((size_t)s * nSlots + (r2.lastNew - slot0)) * 2 + 0) * CB;
