@@ -7,5 +7,6 @@ hyphen as the project layout asks).
 from ._capi import load_library, Segment, EXPORTS  # noqa: F401
 from .batch import BatchStretch, KioskDrive, StreamingDrive, segment  # noqa: F401
 from .engine import StretchEngine  # noqa: F401
+from . import shard  # noqa: F401
 
-__all__ = ["StretchEngine", "BatchStretch", "KioskDrive", "StreamingDrive", "segment", "load_library", "Segment", "EXPORTS"]
+__all__ = ["StretchEngine", "BatchStretch", "KioskDrive", "StreamingDrive", "segment", "load_library", "Segment", "EXPORTS", "shard"]

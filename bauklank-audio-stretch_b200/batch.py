@@ -150,10 +150,18 @@ class BatchStretch:
     def chunk_blocks(self): return self.lib.bsb_chunk_blocks(self.h)
     def launch_count(self): return self.lib.bsb_launch_count(self.h)
 
-    def kernel_ms(self):
-        a = (C.c_float * 3)()
-        self.lib.bsb_kernel_ms(self.h, a)
-        return dict(analysis=a[0], spectral=a[1], synthesis=a[2])
+    def set_profiling(self, on=True):
+        """Bracket every kernel launch of the following runs with CUDA events (on the run's stream)."""
+        self.lib.bsb_set_profiling(self.h, 1 if on else 0)
+
+    def kernel_stats(self):
+        """{kernel name: dict(ms, launches, units)} of the last run; ``ms`` is 0 unless profiling was on."""
+        out = {}
+        for i in range(self.lib.bsb_kernel_count(self.h)):
+            name, ms, n, u = C.c_char_p(), C.c_double(), C.c_longlong(), C.c_longlong()
+            self.lib.bsb_kernel_stat(self.h, i, C.byref(name), C.byref(ms), C.byref(n), C.byref(u))
+            out[name.value.decode()] = dict(ms=ms.value, launches=n.value, units=u.value)
+        return out
 
     def block_info(self, stream, block):
         a = (C.c_longlong * 8)()

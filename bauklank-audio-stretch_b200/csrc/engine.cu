@@ -151,11 +151,25 @@ struct bsb_engine {
   StateDev st{}; cf *specIn = nullptr, *specOut = nullptr;
   int chunk = 0; long long maxBlocks = 0, totalBlocks = 0, launches = 0;
   std::vector<long long> blockBase;
+  std::vector<BlockRec> hostBlocks;
   bool committed = false;
-  float kms[3] = {0, 0, 0};
+  // per-kernel accounting of the last bsb_run: launches and units always; device time when profiling is on
+  // (one CUDA event pair per launch, read back lazily so the run itself is never serialised)
+  struct KStat { const char *name; double ms; long long launches, units; };
+  std::vector<KStat> kstat;
+  bool profiling = false;
 #ifndef BS_HOSTEMU
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  struct Span { int k; cudaEvent_t a, b; };
+  std::vector<Span> spans; std::vector<cudaEvent_t> evPool; size_t evUsed = 0;
+  cudaEvent_t get_event() {
+    if (evUsed == evPool.size()) { cudaEvent_t ev; cudaEventCreate(&ev); evPool.push_back(ev); }
+    return evPool[evUsed++];
+  }
 #endif
+  int kidx(const char *name) {
+    for (size_t i = 0; i < kstat.size(); ++i) if (!std::strcmp(kstat[i].name, name)) return (int)i;
+    kstat.push_back(KStat{name, 0.0, 0, 0}); return (int)kstat.size() - 1;
+  }
   std::string err;
   int fail(const char *fmt, ...) {
     char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -264,28 +278,37 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
 #else
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
   const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float), smM = map_smem_floats(g.B) * sizeof(float);
-  cudaEventRecord(e->ev[0], q);
+  auto span = [&](const char *name, long long units, auto &&launch) {
+    const int k = e->kidx(name);
+    e->kstat[k].launches += 1; e->kstat[k].units += units; e->launches += 1;
+    if (e->profiling) {
+      cudaEvent_t a = e->get_event(), b = e->get_event();
+      cudaEventRecord(a, q); launch(); cudaEventRecord(b, q);
+      e->spans.push_back({k, a, b});
+    } else launch();
+  };
+  // units: analyses (window x channel) actually computed; channel-blocks for the other stages
+  long long nNew = 0, nBlk = 0;
+  for (int s = 0; s < S; ++s) {
+    const long long n = std::min<long long>(nSlots, e->hs[s].nBlocks - slot0);
+    if (n > 0) nBlk += n;
+  }
   if (stages & 1) {
-  analysis_kernel<<<(unsigned)((size_t)S * nSlots * 2 * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows,
-                                                                          slot0, nSlots, e->specIn);
-  premap_kernel<<<(unsigned)((size_t)S * nSlots), 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots,
-                                                                e->specIn, st);
-  cudaEventRecord(e->ev[1], q);
-  spectral_kernel<<<S, nt, smS, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st);
-  e->launches += 3;
+    if (e->dg.incremental) nNew = 1;
+    else for (int s = 0; s < S; ++s)
+      for (long long m = slot0; m < slot0 + nSlots && m < e->hs[s].nBlocks; ++m) nNew += (e->hostBlocks[e->hs[s].blockBase + m].flags & kNew) ? 1 : 0;
+    span("analysis_kernel", nNew * 2 * g.C, [&] {
+      analysis_kernel<<<(unsigned)((size_t)S * nSlots * 2 * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
+    span("premap_kernel", nBlk * g.C, [&] {
+      premap_kernel<<<(unsigned)((size_t)S * nSlots), 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
+    span("spectral_kernel", nBlk * g.C, [&] {
+      spectral_kernel<<<S, nt, smS, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
   }
-  cudaEventRecord(e->ev[2], q);
-  if (stages & 2) {
-    synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, e->specOut, st);
-    e->launches += 1;
-  }
-  cudaEventRecord(e->ev[3], q);
+  if (stages & 2)
+    span("synthesis_kernel", nBlk * g.C, [&] {
+      synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, e->specOut, st); });
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
-  if (getenv("BS_KERNEL_TIMES")) {   // per-kernel split (serialises the chunks; not used for throughput numbers)
-    cudaEventSynchronize(e->ev[3]);
-    for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->kms[i] += ms; }
-  }
 #endif
   return 0;
 }
@@ -309,7 +332,6 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   e->dt.specRot = upload(e, e->T.specRot, e->owned);
   e->dt.wpStart = upload(e, e->T.wpStart, e->owned); e->dt.wpSteady = upload(e, e->T.wpSteady, e->owned);
 #ifndef BS_HOSTEMU
-  for (auto &ev : e->ev) cudaEventCreate(&ev);
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
   const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
@@ -335,7 +357,7 @@ void bsb_destroy(bsb_engine *e) {
   free_batch(e);
   for (void *p : e->owned) dfree(p);
 #ifndef BS_HOSTEMU
-  for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : e->evPool) cudaEventDestroy(ev);
 #endif
   delete e;
 }
@@ -350,7 +372,23 @@ long long bsb_total_blocks(const bsb_engine *e) { return e->totalBlocks; }
 long long bsb_stream_blocks(const bsb_engine *e, int s) { return (s >= 0 && s < (int)e->streams.size()) ? (long long)e->streams[s].plan.blocks.size() : -1; }
 int bsb_chunk_blocks(const bsb_engine *e) { return e->chunk; }
 long long bsb_launch_count(const bsb_engine *e) { return e->launches; }
-int bsb_kernel_ms(const bsb_engine *e, float out[3]) { for (int i = 0; i < 3; ++i) out[i] = e->kms[i]; return 0; }
+void bsb_set_profiling(bsb_engine *e, int on) { e->profiling = on != 0; }
+int bsb_kernel_count(const bsb_engine *e) { return (int)e->kstat.size(); }
+int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units) {
+  if (i < 0 || i >= (int)e->kstat.size()) return -1;
+#ifndef BS_HOSTEMU
+  if (!e->spans.empty()) {   // fold the recorded event pairs into the per-kernel totals (blocks until they completed)
+    for (auto &sp : e->spans) {
+      cudaEventSynchronize(sp.b);
+      float ms1 = 0.f; cudaEventElapsedTime(&ms1, sp.a, sp.b); e->kstat[sp.k].ms += ms1;
+    }
+    e->spans.clear(); e->evUsed = 0;
+  }
+#endif
+  const bsb_engine::KStat &k = e->kstat[i];
+  *name = k.name; *ms = k.ms; *launches = k.launches; *units = k.units;
+  return 0;
+}
 
 int bsb_begin(bsb_engine *e, int n) {
   if (n < 1) return e->fail("n_streams must be >= 1");
@@ -430,6 +468,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
     uint32_t sd = st.seed % 2147483647u; seeds[s] = sd <= 1u ? 1u : sd;   // W#26: minstd_rand seeding
   }
   e->totalBlocks = (long long)blocks.size();
+  e->hostBlocks = blocks;
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
   const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8);   // specIn (cur+prev) + specOut + inEnergy + map
@@ -468,7 +507,10 @@ int bsb_run(bsb_engine *e, void *cudaStream) {
   StateDev &st = e->st;
   reset_state(e, q);
   e->launches = 0;
-  e->kms[0] = e->kms[1] = e->kms[2] = 0.f;
+  for (auto &k : e->kstat) { k.ms = 0.0; k.launches = 0; k.units = 0; }
+#ifndef BS_HOSTEMU
+  e->spans.clear(); e->evUsed = 0;
+#endif
   for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk)
     if (launch_chunk(e, slot0, e->chunk, q, 3, kSynthEmit | kSynthAdd)) return -1;
   return 0;

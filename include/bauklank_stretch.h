@@ -90,8 +90,12 @@ int bsb_chunk_blocks(const bsb_engine *e);
  * out[0]=flags out[1]=timeFactor bits, out[2..4]=cur window {start lo hi}, out[5..7]=prev window */
 long long bsb_launch_count(const bsb_engine *e);
 int bsb_block_info(const bsb_engine *e, int stream, long long block, long long out[8]);
-/* per-kernel device time of the last bsb_run in milliseconds (CUDA events): [analysis, spectral, synthesis] */
-int bsb_kernel_ms(const bsb_engine *e, float out[3]);
+/* Per-kernel accounting of the last bsb_run.  launches and units (analysis: window x channel transforms actually
+ * computed; other kernels: channel-blocks) are always counted; device milliseconds only while profiling is on (one
+ * CUDA event pair per launch on the run's stream, read back when a stat is queried -- the run is not serialised). */
+void bsb_set_profiling(bsb_engine *e, int on);
+int bsb_kernel_count(const bsb_engine *e);
+int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units);
 
 #ifdef __cplusplus
 }

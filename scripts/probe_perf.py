@@ -24,4 +24,4 @@ for it in range(3):
     torch.cuda.synchronize(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
     a.record(); eng.run(); b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b)
-    print("run %d: %.1f ms -> %.0f x realtime (out-sec %.0f) launches=%d" % (it, ms, out_sec / (ms / 1e3), out_sec, eng.launch_count()), eng.kernel_ms())
+    print("run %d: %.1f ms -> %.0f x realtime (out-sec %.0f) launches=%d" % (it, ms, out_sec / (ms / 1e3), out_sec, eng.launch_count()), eng.kernel_stats())

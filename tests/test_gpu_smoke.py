@@ -2,6 +2,6 @@ import pytest
 
 
 @pytest.mark.gpu
-def test_smoke_bit_exact():
+def test_smoke_entry_point():
     import __graft_entry__ as ge
     ge.smoke()

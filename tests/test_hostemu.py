@@ -1,0 +1,92 @@
+"""CPU: the kernels' own source, executed serially on the host by the TEST-ONLY emulation build
+(tests/hostemu, -DBS_HOSTEMU: every (tid, nthreads) work loop runs with one thread), must reproduce the reference
+bit-for-bit.  This checks the arithmetic and the host block-schedule compiler without a GPU; the `-m gpu` tests run
+the same cases through the real CUDA build."""
+import numpy as np
+import pytest
+
+import bauklank_audio_stretch_b200 as bs
+import cases
+from conftest import HOSTEMU, assert_matches_golden
+from oracle import refdrive
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return bs.load_library(HOSTEMU)
+
+
+@pytest.mark.parametrize("name", cases.FAST)
+def test_batched_path_bit_exact(name, emu, golden):
+    y = cases.run_cases_batch(bs, [cases.CASES[name]], lib=emu)[0]
+    assert_matches_golden(name, y, golden)
+
+
+def test_batch_of_mixed_streams_and_chunk_invariance(emu, golden):
+    """Several presetDefault streams in ONE batch, different lengths/drives; result must not depend on the chunking."""
+    names = ["KA5", "rng_low_rate", "stream_100_900", "stream_transpose_only_q96"]
+    cs = [cases.CASES[n] for n in names]
+    a = cases.run_cases_batch(bs, cs, lib=emu, chunk_blocks=5)
+    for n, y in zip(names, a):
+        assert_matches_golden(n, y, golden)
+    b = cases.run_cases_batch(bs, cs[:2], lib=emu, chunk_blocks=64)
+    for n, y in zip(names[:2], b):
+        assert_matches_golden(n, y, golden)
+
+
+def test_block_schedule_matches_the_reference_drive(emu):
+    """Frame/hop indexing: the host-compiled block table (start sample of each analysis window, timeFactor bits,
+    flags) equals what the reference engine does under the worklet's drive.  Checked through the oracle's seek
+    positions: for a kiosk drive the 'current' window of the block that starts in quantum k ends at
+    inputSamplesEnd(k) (app/SignalsmithStretch.mjs:897)."""
+    case = dict(cases.CASES["KA4"]); case["n_out"] = 30000
+    clip = cases.make_clip(case["clip"])
+    eng = cases.make_batch(bs, case, 2, lib=emu)
+    eng.plan([clip], [cases.batch_drive(bs, case, clip.shape[1])])
+    L, H = eng.blockSamples(), eng.intervalSamples()
+    sr = 48000.0
+    in_lat, out_lat = eng.inputLatency(), eng.outputLatency()
+    nb = eng.stream_blocks(0)
+    assert nb == (30000 + H - 1) // H
+    for m in range(nb):
+        k = (m * H) // 128                                   # quantum in which output sample m*H falls
+        out_t = (k * 128) / sr + out_lat / sr
+        end = refdrive.js_round((0.0 + out_t * 0.75 + in_lat / sr) * sr)
+        info = eng.block_info(0, m)
+        assert info["flags"] & 1                             # seek => new spectrum every block
+        assert info["cur"][0] == end - L
+        assert info["prev"][0] == end - L - H
+        assert np.float32(info["timeFactor"]) == np.float32(1.0 / 0.75)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["KA5", "stream_480_512_cheaper", "rng_low_rate"])
+def test_compat_shim_bit_exact(name, emu, golden):
+    """The reference's own 18 entry points (Part 1 of the header) driven exactly like the worklet drives the wasm."""
+    e = bs.StretchEngine(seed=cases.CASES[name].get("seed", 1), lib=emu)
+    y = cases.run_case(e, cases.CASES[name])
+    assert_matches_golden(name, y, golden)
+
+
+def test_shim_parameter_changes_every_quantum(emu):
+    """Q4: with splitComputation the steps of a block see the parameters current when they run."""
+    x = refdrive.survey_clip(20000)
+    def pf(k, t):
+        return dict(semitones=float((k // 7) % 13 - 6), rate=0.5 + (k % 50) / 40.0, formant_semitones=float((k // 11) % 5 - 2),
+                    formant_comp=bool(k % 2))
+    for preset in ("cheaper", "default"):
+        a, _ = refdrive.kiosk_drive(refdrive.PortEngine(5), x, 48000, 25000, 1.0, preset=preset, params=dict(tonality_hz=8000.0), param_fn=pf)
+        b, _ = refdrive.kiosk_drive(bs.StretchEngine(seed=5, lib=emu), x, 48000, 25000, 1.0, preset=preset, params=dict(tonality_hz=8000.0), param_fn=pf)
+        assert cases.compare(a, b)[0], preset
+
+
+def test_error_behaviour(emu):
+    eng = bs.BatchStretch(2, 48000.0, lib=emu)
+    x = np.zeros((2, 1000), np.float32)
+    with pytest.raises(RuntimeError):      # inactive segments are not supported by the batched path
+        eng.plan([x], [bs.KioskDrive(100, [bs.segment(active=False)])])
+    with pytest.raises(RuntimeError):      # n_calls * n_in must fit the clip
+        eng.plan([x], [bs.StreamingDrive(512, 512, 10)])
+    eng.close()
+    with pytest.raises(RuntimeError):      # block < 8
+        bs.BatchStretch(2, 48000.0, block_samples=4, interval_samples=1, lib=emu)
