@@ -25,8 +25,12 @@ struct BlockRec {
   float fmMult, fmInv;      // formantMultiplier / invFormantMultiplier seen by formant step 2
   float fmFreqMult;         // freqMultiplier seen by formant step 2 (fmLimit below)
 };
-struct BlockRec2 { float fmLimit; int lastNew; float pad[2]; };  // lastNew: stream-relative index of the block whose
-                                                                  // "current" spectrum is this block's input (-1: none yet)
+struct BlockRec2 {
+  float fmLimit;
+  int lastNew;        // stream-relative index of the block whose "current" spectrum is this block's input (-1: none yet)
+  uint32_t rngSkip;   // blocks before this one that drew from the RNG (timeFactor > 2): each consumed 2*bands-2 draws
+  uint32_t pad;
+};
 // sample i (0 <= i < L) of a window = (lo <= i < hi) ? clip[ch][start + i] : 0
 struct Window { long long start; int lo, hi; };
 
@@ -111,7 +115,8 @@ class Control {
         rec.timeFactor = tf;
         plan.blocks.push_back(rec);
         if (isNew) lastNew_ = (int)plan.blocks.size() - 1;
-        BlockRec2 r2{}; r2.lastNew = lastNew_;
+        BlockRec2 r2{}; r2.lastNew = lastNew_; r2.rngSkip = rngBlocks_;
+        if (!((tf < 0.5f ? 0.5f : tf) <= 2.0f)) ++rngBlocks_;   // W#48 9470: random time factors only when tf > 2
         plan.blocks2.push_back(r2);
         plan.windows.push_back(Window{0, 0, 0});
         plan.windows.push_back(Window{0, 0, 0});
@@ -160,6 +165,7 @@ class Control {
   int stepPeaks_ = -1, stepFm0_ = -1, stepFm2_ = -1;
   long long cur_ = -1;
   int lastNew_ = -1;
+  uint32_t rngBlocks_ = 0;
 };
 
 inline void apply_segment_params(Params &p, const Segment &s, double sampleRate) {

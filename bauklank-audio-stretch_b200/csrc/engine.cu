@@ -57,9 +57,11 @@ __global__ void __launch_bounds__(256) analysis_kernel(DevGeom g, DevTables T, c
   analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x);
 }
 
-// premap: the state-independent half of the spectral stage for every (stream, block) of the chunk in parallel
+// premap: the map stage for every (stream, block) of the chunk in parallel.  phase 0 = everything except the formant
+// envelope of auto-detect blocks (those wait for freqest_kernel); phase 1 = exactly those.
 __global__ void __launch_bounds__(128) premap_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                     const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, StateDev st) {
+                                                     const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, StateDev st,
+                                                     int phase) {
   extern __shared__ float4 sm4[];
   float *sm = (float *)sm4;
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
@@ -67,56 +69,226 @@ __global__ void __launch_bounds__(128) premap_kernel(DevGeom g, DevTables T, con
   const long long m = slot0 + t;
   if (m >= sd.nBlocks) return;
   const BlockRec rec = blocks[sd.blockBase + m];
-  if (needs_inline_map(rec)) return;
+  const bool autoBase = fm_auto(rec);
+  if (phase == 1 && !autoBase) return;
   const BlockRec2 rec2 = blocks2[sd.blockBase + m];
-  const size_t CB = (size_t)g.C * g.B;
+  const size_t CB = (size_t)g.C * g.B, slot = (size_t)s * nSlots + t;
   const cf *inp = block_input(g, rec2, s, slot0, nSlots, specIn, st.lastInput);
-  float *inE = st.inEnergy + ((size_t)s * nSlots + t) * CB, *mp = st.map + ((size_t)s * nSlots + t) * g.B * 2;
-  if (g.C == 2) map_stage<2>(g, T, rec, rec2, inp, nullptr, inE, mp, sm, threadIdx.x, blockDim.x);
-  else if (g.C == 1) map_stage<1>(g, T, rec, rec2, inp, nullptr, inE, mp, sm, threadIdx.x, blockDim.x);
-  else map_stage<0>(g, T, rec, rec2, inp, nullptr, inE, mp, sm, threadIdx.x, blockDim.x);
+  float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (phase == 0) {
+    if (g.C == 2) map_stage_a<2>(g, T, rec, inp, inE, mp, st.fmAuto + 2 * slot, sm, tid, nt);
+    else if (g.C == 1) map_stage_a<1>(g, T, rec, inp, inE, mp, st.fmAuto + 2 * slot, sm, tid, nt);
+    else map_stage_a<0>(g, T, rec, inp, inE, mp, st.fmAuto + 2 * slot, sm, tid, nt);
+    if (autoBase) return;
+  }
+  const float base = autoBase ? st.fmBase[slot] : 0.f;
+  if (g.C == 2) map_stage_b<2>(g, rec, rec2, base, inE, sm, tid, nt);
+  else if (g.C == 1) map_stage_b<1>(g, rec, rec2, base, inE, sm, tid, nt);
+  else map_stage_b<0>(g, rec, rec2, base, inE, sm, tid, nt);
 }
 
-template <int CT>
-__device__ __forceinline__ void spectral_stream(const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
-                                                const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut,
-                                                const StateDev &st, float *sm) {
-  const int s = blockIdx.x;
+// the formant base estimate is a two-tap leaky average over the blocks of a stream: one thread per stream
+__global__ void freqest_kernel(int S, const StreamDev *streams, const BlockRec *blocks, long long slot0, int nSlots, StateDev st) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
   const StreamDev sd = streams[s];
-  const size_t CB = (size_t)g.C * g.B;
-  long long mLast = -1;
-  for (int t = 0; t < nSlots; ++t) {
-    const long long m = slot0 + t;
-    if (m >= sd.nBlocks) break;
-    mLast = m;
-    const BlockRec rec = blocks[sd.blockBase + m];
-    const BlockRec2 rec2 = blocks2[sd.blockBase + m];
-    const cf *inp = block_input(g, rec2, s, slot0, nSlots, specIn, st.lastInput);
-    const cf *prev = (rec.flags & kNew) ? specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB : nullptr;
-    spectral_block<CT>(g, T, rec, rec2, inp, prev, st.outSpec + s * CB, st.predE + s * CB, st.rng + s, st.freqEst + 2 * s,
-                       st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, st.predIn + s * CB,
-                       st.terms + (size_t)s * g.B * nterms(g.C), specOut + ((size_t)s * nSlots + t) * CB, needs_inline_map(rec), sm,
-                       threadIdx.x, blockDim.x);
+  for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t)
+    if (fm_auto(blocks[sd.blockBase + slot0 + t])) {
+      const size_t slot = (size_t)s * nSlots + t;
+      st.fmBase[slot] = freqest_step(st.freqEst + 2 * s, st.fmAuto + 2 * slot);
+    }
+}
+
+// preterms: one CTA per (stream, block): the per-bin coefficient records of the phase prediction
+__global__ void __launch_bounds__(256) preterms_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                       const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, StateDev st) {
+  const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
+  const StreamDev sd = streams[s];
+  const long long m = slot0 + t;
+  if (m >= sd.nBlocks) return;
+  const BlockRec rec = blocks[sd.blockBase + m];
+  const BlockRec2 rec2 = blocks2[sd.blockBase + m];
+  const size_t CB = (size_t)g.C * g.B, slot = (size_t)s * nSlots + t;
+  const cf *inp = block_input(g, rec2, s, slot0, nSlots, specIn, st.lastInput);
+  const cf *prev = (rec.flags & kNew) ? specIn + (slot * 2 + 1) * CB : nullptr;
+  const float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
+  const bool last = (m + 1 == sd.nBlocks) || (t + 1 == nSlots);
+  const uint32_t rng0 = minstd_jump(st.seeds[s], (uint32_t)(((unsigned long long)rec2.rngSkip * (unsigned long long)(2 * g.B - 2)) % 2147483646ull));
+  float *ra = st.recA + slot * g.B * na_floats(g.C), *rb = st.recB + slot * g.B * nb_floats(g.C);
+  const float *pE = st.predE[st.parity] + (size_t)s * CB;
+  float *pEo = last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr;
+  const float *pInE = t > 0 ? inE - CB : nullptr, *pMap = t > 0 ? mp - (size_t)g.B * 2 : nullptr;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (g.C == 2) preterms_block<2>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, ra, rb, tid, nt);
+  else if (g.C == 1) preterms_block<1>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, ra, rb, tid, nt);
+  else preterms_block<0>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, ra, rb, tid, nt);
+}
+
+// ---- chain: one warp per stream.  Lane j walks block p0+j of the chunk, `D` bins behind lane j-1, so that the
+// previous block's output at bins k+1 and k+longStep has just been produced one lane up (warp shuffle) when bin k
+// needs it.  Lane 0 takes the previous block from the carried state, the last lane writes the state back.
+// All global inputs are staged with cp.async a few steps ahead: per-lane records in 16-byte pieces, the carried state
+// as coalesced 64-bin tiles.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+constexpr int kChainPF = 4;       // records are requested this many steps before they are consumed
+constexpr int kChainTile = 64;    // bins per staged tile of the carried state
+BS_HHD int chain_stride(int n) { return ((n / 4) | 1) * 4; }   // odd number of 16-byte units: conflict-free LDS.128
+BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
+BS_HHD size_t chain_smem_bytes(int C, int longStep) {
+  const size_t R = chain_ring(longStep);
+  return 2 * R * C * 32 * sizeof(cf) + (size_t)(kChainPF + 1) * 32 * (chain_stride(na_floats(C)) + chain_stride(nb_floats(C))) * sizeof(float) +
+         2 * (size_t)kChainTile * C * sizeof(cf);
+}
+
+template <int C>
+__global__ void __launch_bounds__(32) chain_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                   const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut,
+                                                   StateDev st) {
+  extern __shared__ float4 sm4[];
+  constexpr int NA = (12 + 5 * C + 3) & ~3, NB = (3 * C + 3) & ~3, SA = ((NA / 4) | 1) * 4, SB = ((NB / 4) | 1) * 4;
+  constexpr int PF = kChainPF, NS = PF + 1, TL = kChainTile;
+  const int s = blockIdx.x, lane = threadIdx.x;
+  const StreamDev sd = streams[s];
+  const int B = g.B, ls = g.longStep, D = ls + 2, OA = 1, R = chain_ring(ls), RM = R - 1;
+  cf *ringN = (cf *)sm4;                                  // [R][C][32]  S5 prediction of this lane's block
+  cf *ringO = ringN + (size_t)R * C * 32;                 // [R][C][32]  new output of this lane's block
+  float *stageA = (float *)(ringO + (size_t)R * C * 32);  // [NS][32][SA]
+  float *stageB = stageA + (size_t)NS * 32 * SA;          // [NS][32][SB]
+  cf *tile = (cf *)(stageB + (size_t)NS * 32 * SB);       // [2][C][TL]   carried state, bins of lane 0's S5 stage
+  long long nv = sd.nBlocks - slot0; if (nv > nSlots) nv = nSlots;
+  if (nv <= 0) return;
+  const int nValid = (int)nv;
+  cf *stOut = st.outSpec + (size_t)s * C * B;
+  const size_t CB = (size_t)C * B;
+
+  for (int p0 = 0; p0 < nValid; p0 += 32) {
+    const int slot = p0 + lane;
+    const bool active = slot < nValid;
+    const int lastLane = min(31, nValid - 1 - p0);
+    const bool isNew = active && (blocks[sd.blockBase + slot0 + slot].flags & kNew);
+    const size_t blk = (size_t)s * nSlots + (active ? slot : p0);
+    const float *ra = st.recA + blk * B * NA, *rb = st.recB + blk * B * NB;
+    cf *so = specOut + blk * CB;
+    const int tBeg = 1 - OA, tEnd = (B - 1 + ls) + lastLane * D;
+
+    // request the records of step t (this lane: chain bin t - lane*D - ls, S5 bin t - lane*D + OA)
+    auto request = [&](int t) {
+      const int tau = t - lane * D, k = tau - ls, q = tau + OA, sl = ((t % NS) + NS) % NS;
+      if (active && k >= 0 && k < B) {
+        const float *src = ra + (size_t)k * NA; float *dst = stageA + ((size_t)sl * 32 + lane) * SA;
+#pragma unroll
+        for (int i = 0; i < NA; i += 4) cp_async16(dst + i, src + i);
+      }
+      if (active && q >= 1 && q < B) {
+        const float *src = rb + (size_t)q * NB; float *dst = stageB + ((size_t)sl * 32 + lane) * SB;
+#pragma unroll
+        for (int i = 0; i < NB; i += 4) cp_async16(dst + i, src + i);
+      }
+    };
+    // stage tile `ti` of the carried state (bins [ti*TL, ti*TL+TL) of every channel), all lanes, 16 bytes each
+    auto request_tile = [&](int ti) {
+      const int b0 = ti * TL;
+      if (b0 >= B) return;
+      cf *dst = tile + (size_t)(ti & 1) * C * TL;
+      for (int i = lane; i < C * (TL / 2); i += 32) {
+        const int c = i / (TL / 2), j = (i - c * (TL / 2)) * 2;
+        if (b0 + j < B) cp_async16(dst + (size_t)c * TL + j, stOut + (size_t)c * B + b0 + j);   // B is even
+      }
+    };
+    request_tile(0); request_tile(1);
+    for (int t = tBeg; t < tBeg + PF; ++t) { request(t); cp_async_commit(); }
+
+    cf last[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) last[c].re = last[c].im = 0.f;
+
+    for (int t = tBeg; t <= tEnd; ++t) {
+      request(t + PF);
+      const int q0 = t + OA;                               // lane 0's S5 bin
+      if (q0 > 0 && (q0 % TL) == 0) request_tile(q0 / TL + 1);
+      cp_async_commit();
+      cp_async_wait<PF>();
+      __syncwarp();
+      const int tau = t - lane * D, q = tau + OA, k = tau - ls, sl = ((t % NS) + NS) % NS;
+      cf up[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        up[c].re = __shfl_up_sync(0xffffffffu, last[c].re, 1);
+        up[c].im = __shfl_up_sync(0xffffffffu, last[c].im, 1);
+      }
+      if (active && q >= 1 && q < B) {
+        const cf r = T.specRot[q];
+        const float *b = stageB + ((size_t)sl * 32 + lane) * SB;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          cf o = up[c];
+          if (lane == 0) o = tile[((size_t)((q / TL) & 1) * C + c) * TL + (q % TL)];
+          ringN[((size_t)(q & RM) * C + c) * 32 + lane] = s5_bin(o, isNew, r, b[3 * c], b[3 * c + 1], b[3 * c + 2]);
+        }
+      }
+      if (active && k >= 0 && k < B) {
+        float rec[NA];
+        const float4 *a4 = (const float4 *)(stageA + ((size_t)sl * 32 + lane) * SA);
+#pragma unroll
+        for (int i = 0; i < NA / 4; ++i) { const float4 v = a4[i]; rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w; }
+        const int mc = __float_as_int(rec[8]);
+        cf oPrev = last[0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) if (c == mc) oPrev = last[c];
+        cf z; z.re = z.im = 0.f;
+        const cf oLong = (k >= ls) ? ringO[((size_t)((k - ls) & RM) * C + mc) * 32 + lane] : z;
+        const cf n1 = (k < B - 1) ? ringN[((size_t)((k + 1) & RM) * C + mc) * 32 + lane] : z;
+        const cf nL = (k < B - ls) ? ringN[((size_t)((k + ls) & RM) * C + mc) * 32 + lane] : z;
+        cf out[C];
+        chain_bin<C>(rec, mc, k, B, ls, oPrev, oLong, n1, nL, out);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          ringO[((size_t)(k & RM) * C + c) * 32 + lane] = out[c];
+          so[(size_t)c * B + k] = out[c];
+          if (lane == lastLane) stOut[(size_t)c * B + k] = out[c];
+          last[c] = out[c];
+        }
+      }
+      __syncwarp();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
   }
   // carry the input spectrum into the next chunk if its first block reuses it (no new spectrum there)
-  if (mLast >= 0 && (g.incremental || (mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew)))) {
+  const long long mLast = slot0 + nValid - 1;
+  if (g.incremental || (mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew))) {
     const BlockRec2 r2 = blocks2[sd.blockBase + mLast];
     if (r2.lastNew >= slot0) {
       const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput);
       cf *dst = st.lastInput + (size_t)s * CB;
-      for (int i = threadIdx.x; i < (int)CB; i += blockDim.x) dst[i] = src[i];
+      for (int i = lane; i < (int)CB; i += 32) dst[i] = src[i];
     }
   }
 }
 
-__global__ void __launch_bounds__(256) spectral_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                       const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut,
-                                                       StateDev st) {
-  extern __shared__ float4 sm4[];
-  float *sm = (float *)sm4;
-  if (g.C == 2) spectral_stream<2>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, sm);
-  else if (g.C == 1) spectral_stream<1>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, sm);
-  else spectral_stream<0>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, sm);
+template <int C>
+static void launch_chain(int S, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
+                         const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st) {
+  chain_kernel<C><<<S, 32, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st);
+}
+typedef void (*chain_launch_fn)(int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
+                                long long, int, const cf *, cf *, const StateDev &);
+static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>, launch_chain<3>, launch_chain<4>,
+                                                launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
+template <int C> static cudaError_t chain_attr(size_t smem) {
+  return cudaFuncSetAttribute(chain_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+static cudaError_t chain_set_smem(int C, size_t smem) {
+  switch (C) {
+    case 1: return chain_attr<1>(smem); case 2: return chain_attr<2>(smem); case 3: return chain_attr<3>(smem); case 4: return chain_attr<4>(smem);
+    case 5: return chain_attr<5>(smem); case 6: return chain_attr<6>(smem); case 7: return chain_attr<7>(smem); default: return chain_attr<8>(smem);
+  }
 }
 
 __global__ void __launch_bounds__(256) synthesis_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
@@ -202,18 +374,14 @@ static void reset_state(bsb_engine *e, stream_t q) {
   const int S = (int)e->hs.size();
   const size_t CB = (size_t)g.C * g.B;
   StateDev &st = e->st;
-  // reset(): zero phase state, rings, maps; seed the RNGs
-  dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE, S * CB * sizeof(float), q);
+  // reset(): zero phase state, rings, maps (the RNG is re-derived from the per-stream seed and the block table)
+  dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE[0], S * CB * sizeof(float), q); dzero(st.predE[1], S * CB * sizeof(float), q);
   dzero(st.lastInput, S * CB * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
   dzero(st.ring, (size_t)S * g.C * g.L * sizeof(float), q);
-#ifdef BS_HOSTEMU
-  std::memcpy(st.rng, e->dSeeds, S * sizeof(uint32_t));
-#else
-  cudaMemcpyAsync(st.rng, e->dSeeds, S * sizeof(uint32_t), cudaMemcpyDeviceToDevice, q);
-#endif
+  st.parity = 0;
 }
 
-// one time-chunk: stages bit0 = analysis + premap + spectral, bit1 = synthesis (with `synthMode`)
+// one time-chunk: stages bit0 = analysis + map + terms + chain, bit1 = synthesis (with `synthMode`)
 static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, int stages, int synthMode) {
   const Geometry &g = e->g;
   const int S = (int)e->hs.size();
@@ -221,88 +389,135 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
   StateDev &st = e->st;
   const int nt = 256;
   (void)nt; (void)q;
-#ifdef BS_HOSTEMU
-  std::vector<f4> smv((spectral_smem_floats(g.B, g.C) + 4 * (size_t)g.M + g.L + 64) / 4 + 1);
-  float *sm = (float *)smv.data();
-  auto mapFn = g.C == 2 ? map_stage<2> : (g.C == 1 ? map_stage<1> : map_stage<0>);
-  auto specFn = g.C == 2 ? spectral_block<2> : (g.C == 1 ? spectral_block<1> : spectral_block<0>);
+  // units: analyses (window x channel) actually computed; channel-blocks for the other stages
+  long long nNew = 0, nBlk = 0; bool anyAuto = false;
+  for (int s = 0; s < S; ++s) {
+    const long long n = std::min<long long>(nSlots, e->hs[s].nBlocks - slot0);
+    if (n > 0) nBlk += n;
+  }
   if (stages & 1) {
-  for (int s = 0; s < S; ++s) {   // analysis_kernel
-    const StreamDev &sd = e->hs[s];
-    for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
-      long long m = slot0 + t;
-      if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
-      for (int which = 0; which < 2; ++which)
-        for (int c = 0; c < g.C; ++c)
-          analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
-                         e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1);
-    }
+    if (e->dg.incremental) { nNew = (e->hostBlocks[0].flags & kNew) ? 1 : 0; anyAuto = fm_auto(e->hostBlocks[0]); }
+    else for (int s = 0; s < S; ++s)
+      for (long long m = slot0; m < slot0 + nSlots && m < e->hs[s].nBlocks; ++m) {
+        const BlockRec &r = e->hostBlocks[e->hs[s].blockBase + m];
+        nNew += (r.flags & kNew) ? 1 : 0; anyAuto = anyAuto || fm_auto(r);
+      }
   }
-  for (int s = 0; s < S; ++s) {   // premap_kernel
-    const StreamDev &sd = e->hs[s];
-    for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
-      long long m = slot0 + t;
-      const BlockRec rec = e->dBlocks[sd.blockBase + m];
-      if (needs_inline_map(rec)) continue;
-      const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
-      mapFn(e->dg, e->dt, rec, rec2, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput), nullptr,
-            st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, sm, 0, 1);
-    }
-  }
-  for (int s = 0; s < S; ++s) {   // spectral_kernel
-    const StreamDev &sd = e->hs[s];
-    long long mLast = -1;
-    for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
-      long long m = slot0 + t; mLast = m;
-      const BlockRec rec = e->dBlocks[sd.blockBase + m];
-      const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
-      const cf *inp = block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput);
-      const cf *prev = (rec.flags & kNew) ? e->specIn + (((size_t)s * nSlots + t) * 2 + 1) * CB : nullptr;
-      specFn(e->dg, e->dt, rec, rec2, inp, prev, st.outSpec + s * CB, st.predE + s * CB, st.rng + s, st.freqEst + 2 * s,
-             st.inEnergy + ((size_t)s * nSlots + t) * CB, st.map + ((size_t)s * nSlots + t) * g.B * 2, st.predIn + s * CB,
-             st.terms + (size_t)s * g.B * nterms(g.C), e->specOut + ((size_t)s * nSlots + t) * CB, needs_inline_map(rec), sm, 0, 1);
-    }
-    if (mLast >= 0 && (e->dg.incremental || (mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew)))) {
-      const BlockRec2 r2 = e->dBlocks2[sd.blockBase + mLast];
-      if (r2.lastNew >= slot0)
-        std::memcpy(st.lastInput + (size_t)s * CB, block_input(e->dg, r2, s, slot0, nSlots, e->specIn, st.lastInput), CB * sizeof(cf));
-    }
-  }
-  }
-  if (stages & 2)
-  for (int s = 0; s < S; ++s)     // synthesis_kernel
-    for (int c = 0; c < g.C; ++c)
-      synth_stream(e->dg, e->dt, e->hs[s], c, slot0, nSlots, synthMode, e->specOut + (size_t)s * nSlots * CB,
-                   st.ring + ((size_t)s * g.C + c) * g.L, sm, sm + 4 * (size_t)g.M, 0, 1);
-  e->launches += ((stages & 1) ? 3 : 0) + ((stages & 2) ? 1 : 0);
-#else
-  const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
-  const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float), smM = map_smem_floats(g.B) * sizeof(float);
-  auto span = [&](const char *name, long long units, auto &&launch) {
+  auto account = [&](const char *name, long long units) {
     const int k = e->kidx(name);
     e->kstat[k].launches += 1; e->kstat[k].units += units; e->launches += 1;
+    return k;
+  };
+#ifdef BS_HOSTEMU
+  std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)g.M + g.L + 64) / 4 + 1);
+  float *sm = (float *)smv.data();
+  const int NA = na_floats(g.C), NB = nb_floats(g.C);
+  auto mapA = g.C == 2 ? map_stage_a<2> : (g.C == 1 ? map_stage_a<1> : map_stage_a<0>);
+  auto mapB = g.C == 2 ? map_stage_b<2> : (g.C == 1 ? map_stage_b<1> : map_stage_b<0>);
+  auto termFn = g.C == 2 ? preterms_block<2> : (g.C == 1 ? preterms_block<1> : preterms_block<0>);
+  if (stages & 1) {
+    account("analysis_kernel", nNew * 2 * g.C);
+    for (int s = 0; s < S; ++s) {
+      const StreamDev &sd = e->hs[s];
+      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+        long long m = slot0 + t;
+        if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
+        for (int which = 0; which < 2; ++which)
+          for (int c = 0; c < g.C; ++c)
+            analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
+                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1);
+      }
+    }
+    account("premap_kernel", nBlk * g.C);
+    if (anyAuto) { account("freqest_kernel", nBlk); account("premap_kernel", 0); }
+    for (int s = 0; s < S; ++s) {   // premap (phase 0), freqest, premap (phase 1): per stream in block order
+      const StreamDev &sd = e->hs[s];
+      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+        long long m = slot0 + t; const size_t slot = (size_t)s * nSlots + t;
+        const BlockRec rec = e->dBlocks[sd.blockBase + m];
+        const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
+        float *inE = st.inEnergy + slot * CB;
+        mapA(e->dg, e->dt, rec, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput), inE, st.map + slot * g.B * 2,
+             st.fmAuto + 2 * slot, sm, 0, 1);
+        float base = 0.f;
+        if (fm_auto(rec)) base = st.fmBase[slot] = freqest_step(st.freqEst + 2 * s, st.fmAuto + 2 * slot);
+        mapB(e->dg, rec, rec2, base, inE, sm, 0, 1);
+      }
+    }
+    account("preterms_kernel", nBlk * g.C);
+    for (int s = 0; s < S; ++s) {
+      const StreamDev &sd = e->hs[s];
+      for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
+        long long m = slot0 + t; const size_t slot = (size_t)s * nSlots + t;
+        const BlockRec rec = e->dBlocks[sd.blockBase + m];
+        const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
+        const float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
+        const bool last = (m + 1 == sd.nBlocks) || (t + 1 == nSlots);
+        const uint32_t rng0 = minstd_jump(st.seeds[s], (uint32_t)(((unsigned long long)rec2.rngSkip * (unsigned long long)(2 * g.B - 2)) % 2147483646ull));
+        termFn(e->dg, e->dt, rec, rng0, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput),
+               (rec.flags & kNew) ? e->specIn + (slot * 2 + 1) * CB : nullptr, inE, mp, t > 0 ? inE - CB : nullptr,
+               t > 0 ? mp - (size_t)g.B * 2 : nullptr, st.predE[st.parity] + (size_t)s * CB,
+               last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr, st.recA + slot * g.B * NA, st.recB + slot * g.B * NB, 0, 1);
+      }
+    }
+    account("chain_kernel", nBlk * g.C);
+    for (int s = 0; s < S; ++s) {
+      const StreamDev &sd = e->hs[s];
+      long long nv = std::min<long long>(nSlots, sd.nBlocks - slot0);
+      if (nv <= 0) continue;
+      const size_t slot = (size_t)s * nSlots;
+      const BlockRec *bl = e->dBlocks + sd.blockBase + slot0;
+      const float *ra = st.recA + slot * g.B * NA, *rb = st.recB + slot * g.B * NB;
+      cf *so = e->specOut + slot * CB, *state = st.outSpec + (size_t)s * CB;
+      switch (g.C) {
+        case 1: chain_host<1>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; case 2: chain_host<2>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
+        case 3: chain_host<3>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; case 4: chain_host<4>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
+        case 5: chain_host<5>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; case 6: chain_host<6>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
+        case 7: chain_host<7>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; default: chain_host<8>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
+      }
+      const long long mLast = slot0 + nv - 1;
+      if (e->dg.incremental || (mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew))) {
+        const BlockRec2 r2 = e->dBlocks2[sd.blockBase + mLast];
+        if (r2.lastNew >= slot0)
+          std::memcpy(st.lastInput + (size_t)s * CB, block_input(e->dg, r2, s, slot0, nSlots, e->specIn, st.lastInput), CB * sizeof(cf));
+      }
+    }
+    st.parity ^= 1;
+  }
+  if (stages & 2) {
+    account("synthesis_kernel", nBlk * g.C);
+    for (int s = 0; s < S; ++s)
+      for (int c = 0; c < g.C; ++c)
+        synth_stream(e->dg, e->dt, e->hs[s], c, slot0, nSlots, synthMode, e->specOut + (size_t)s * nSlots * CB,
+                     st.ring + ((size_t)s * g.C + c) * g.L, sm, sm + 4 * (size_t)g.M, 0, 1);
+  }
+#else
+  const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
+  const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep);
+  auto span = [&](const char *name, long long units, auto &&launch) {
+    const int k = account(name, units);
     if (e->profiling) {
       cudaEvent_t a = e->get_event(), b = e->get_event();
       cudaEventRecord(a, q); launch(); cudaEventRecord(b, q);
       e->spans.push_back({k, a, b});
     } else launch();
   };
-  // units: analyses (window x channel) actually computed; channel-blocks for the other stages
-  long long nNew = 0, nBlk = 0;
-  for (int s = 0; s < S; ++s) {
-    const long long n = std::min<long long>(nSlots, e->hs[s].nBlocks - slot0);
-    if (n > 0) nBlk += n;
-  }
   if (stages & 1) {
-    if (e->dg.incremental) nNew = 1;
-    else for (int s = 0; s < S; ++s)
-      for (long long m = slot0; m < slot0 + nSlots && m < e->hs[s].nBlocks; ++m) nNew += (e->hostBlocks[e->hs[s].blockBase + m].flags & kNew) ? 1 : 0;
+    const unsigned nCta = (unsigned)((size_t)S * nSlots);
     span("analysis_kernel", nNew * 2 * g.C, [&] {
-      analysis_kernel<<<(unsigned)((size_t)S * nSlots * 2 * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
+      analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
     span("premap_kernel", nBlk * g.C, [&] {
-      premap_kernel<<<(unsigned)((size_t)S * nSlots), 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
-    span("spectral_kernel", nBlk * g.C, [&] {
-      spectral_kernel<<<S, nt, smS, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
+      premap_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st, 0); });
+    if (anyAuto) {
+      span("freqest_kernel", nBlk, [&] { freqest_kernel<<<(S + 63) / 64, 64, 0, q>>>(S, e->dStreams, e->dBlocks, slot0, nSlots, st); });
+      span("premap_kernel", 0, [&] {
+        premap_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st, 1); });
+    }
+    span("preterms_kernel", nBlk * g.C, [&] {
+      preterms_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
+    span("chain_kernel", nBlk * g.C, [&] {
+      kChainLaunch[g.C - 1](S, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
+    st.parity ^= 1;
   }
   if (stages & 2)
     span("synthesis_kernel", nBlk * g.C, [&] {
@@ -333,12 +548,11 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   e->dt.wpStart = upload(e, e->T.wpStart, e->owned); e->dt.wpSteady = upload(e, e->T.wpSteady, e->owned);
 #ifndef BS_HOSTEMU
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
-  const size_t smS = spectral_smem_floats(g.B, g.C) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY) != cudaSuccess ||
-      cudaFuncSetAttribute(spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smS) != cudaSuccess ||
+      chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep)) != cudaSuccess ||
       cudaFuncSetAttribute(premap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
-    std::fprintf(stderr, "bauklank_stretch: block size %d needs more shared memory than one SM has\n", block);
+    std::fprintf(stderr, "bauklank_stretch: block %d / interval %d needs more shared memory than one SM has\n", block, interval);
     bsb_destroy(e); return nullptr;
   }
 #endif
@@ -471,9 +685,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->hostBlocks = blocks;
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
-  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8);   // specIn (cur+prev) + specOut + inEnergy + map
+  // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
+  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (size_t)g.B * 4 * (na_floats(g.C) + nb_floats(g.C)));
   if (chunkBlocks <= 0) {
-    const size_t budget = (size_t)6 << 30;
+    const size_t budget = (size_t)12 << 30;
     chunkBlocks = (int)std::min<size_t>(64, std::max<size_t>(1, budget / perSlot));
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
@@ -484,13 +699,17 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->specIn = dalloc<cf>((size_t)S * chunkBlocks * 2 * CB, own);
   e->specOut = dalloc<cf>((size_t)S * chunkBlocks * CB, own);
   StateDev &st = e->st;
-  st.outSpec = dalloc<cf>(S * CB, own); st.predE = dalloc<float>(S * CB, own); st.lastInput = dalloc<cf>(S * CB, own);
-  st.rng = dalloc<uint32_t>(S, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
+  const size_t nSlotTot = (size_t)S * chunkBlocks;
+  st.outSpec = dalloc<cf>(S * CB, own); st.predE[0] = dalloc<float>(S * CB, own); st.predE[1] = dalloc<float>(S * CB, own);
+  st.lastInput = dalloc<cf>(S * CB, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
   st.ring = dalloc<float>((size_t)S * g.C * g.L, own);
-  st.inEnergy = dalloc<float>((size_t)S * chunkBlocks * CB, own); st.map = dalloc<float>((size_t)S * chunkBlocks * g.B * 2, own);
-  st.predIn = dalloc<cf>(S * CB, own); st.terms = dalloc<float>((size_t)S * g.B * nterms(g.C), own);
+  st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
+  st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
+  st.recA = dalloc<float>(nSlotTot * g.B * na_floats(g.C), own); st.recB = dalloc<float>(nSlotTot * g.B * nb_floats(g.C), own);
+  st.seeds = e->dSeeds; st.parity = 0;
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
-      !st.predE || !st.lastInput || !st.rng || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.predIn || !st.terms) {
+      !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase ||
+      !st.recA || !st.recB) {
     free_batch(e);
     return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);
   }
@@ -546,7 +765,7 @@ struct Compat {
   Geometry g{};
   std::unique_ptr<Control> ctl;
   Params p;
-  uint32_t seed = 1;
+  uint32_t seed = 1, rngState = 1;
   std::vector<float> io; int ioCh = 0, ioLen = 0;
   std::vector<float> ring; int ringPos = 0, inLen = 0;   // stft input ring [C][L+H+1]
   std::vector<float> lastCur, stage, pending;            // [C][L], [C][2L], [C][H]
@@ -609,13 +828,18 @@ void compat_configure(int ch, int L, int H, int split) {
 void compat_launch(Compat *c, long long m, const BlockRec &rec, BlockRec2 rec2, const Window *win, int stages, int mode) {
   bsb_engine *e = c->e;
   rec2.lastNew = (rec.flags & kNew) ? (int)m : -1;
+  rec2.rngSkip = 0;   // the shim tracks the generator state itself (it outlives configure(), like the reference's)
   e->hs[0].blockBase = -m; e->hs[0].outBase = m * c->g.H;
   h2d(e->dStreams, &e->hs[0], sizeof(StreamDev), 0);
   if (stages & 1) {
+    e->hostBlocks.assign(1, rec);
     h2d(e->dBlocks, &rec, sizeof(BlockRec), 0); h2d(e->dBlocks2, &rec2, sizeof(BlockRec2), 0);
     h2d(e->dWindows, win, 2 * sizeof(Window), 0);
+    h2d(e->dSeeds, &c->rngState, sizeof(uint32_t), 0);
   }
   if (launch_chunk(e, m, 1, 0, stages, mode)) bs::die(e->err.c_str());
+  if ((stages & 1) && !((rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor) <= 2.0f) && c->g.B >= 2)
+    c->rngState = minstd_jump(c->rngState, (uint32_t)(2 * c->g.B - 2));
 }
 
 // W#24 copyInput(toIndex)
@@ -757,13 +981,7 @@ void flush(int) { bs::die("flush() is exported by the reference but never called
 int stretch_main(int, char **) { return 0; }
 void stretch_set_seed(uint32_t seed) {
   Compat *c = cc(); c->seed = seed;
-  if (c->e) {   // W#26: minstd_rand(seed): state = seed % (2^31-1), 0 and 1 map to 1
-    uint32_t sd = seed % 2147483647u; sd = sd <= 1u ? 1u : sd;
-    h2d(c->e->dSeeds, &sd, sizeof sd, 0); h2d(c->e->st.rng, &sd, sizeof sd, 0);
-  }
+  uint32_t sd = seed % 2147483647u;   // W#26: minstd_rand(seed): state = seed % (2^31-1), 0 and 1 map to 1
+  c->rngState = sd <= 1u ? 1u : sd;
 }
 }
-
-#if defined(BS_PHASE_TIMING) && !defined(BS_HOSTEMU)
-extern "C" void bs_debug_phase_cycles(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16); }
-#endif

@@ -1,8 +1,9 @@
-// Device code of the stretch engine: three kernels per time-chunk of blocks
+// Device code of the stretch engine: five kernels per time-chunk of blocks
 //
 //   analysis_kernel   (stream, block, {cur,prev}, channel)  window -> half-bin-shifted real FFT -> spectrum in HBM
-//   spectral_kernel   one persistent CTA per stream, walks the chunk's blocks in order; phase state
-//                     (Band.output, Prediction.energy, RNG, formant estimates) stays resident per stream
+//   premap_kernel     (stream, block)  energies, smoothing, peaks, frequency map, formant envelope
+//   preterms_kernel   (stream, block)  per-bin coefficient records of the phase prediction (everything state-free)
+//   chain_kernel      one warp per stream: the bin-to-bin / block-to-block phase recurrence as a 32-block wavefront
 //   synthesis_kernel  one persistent CTA per (stream, channel): inverse FFT -> window -> overlap-add ring in shared
 //                     memory -> normalised output samples
 //
@@ -34,15 +35,6 @@ inline float __int_as_float_hd(int i) { float f; std::memcpy(&f, &i, 4); return 
 #define __int_as_float_hd(x) __int_as_float(x)
 #endif
 
-#if defined(BS_PHASE_TIMING) && !defined(BS_HOSTEMU)
-__device__ unsigned long long g_phase_cycles[16];
-#define BS_MARK(i) do { if (tid == 0 && blockIdx.x == 0) { unsigned long long t_ = clock64(); atomicAdd(&g_phase_cycles[i], t_ - t_mark_); t_mark_ = t_; } } while (0)
-#define BS_MARK_INIT() unsigned long long t_mark_ = clock64()
-#else
-#define BS_MARK(i) ((void)0)
-#define BS_MARK_INIT() ((void)0)
-#endif
-
 namespace bs {
 
 struct DevGeom {
@@ -65,25 +57,25 @@ struct StreamDev {
   long long outBase;      // output sample n is stored at out[c*outStride + n - outBase]
   long long nBlocks;
 };
-// persistent per-stream state + scratch (all device pointers, stream-major)
+// persistent per-stream state + per-chunk scratch (all device pointers, stream-major)
 struct StateDev {
-  cf *outSpec;        // [S][C][B]   Band.output
-  float *predE;       // [S][C][B]   Prediction.energy
-  cf *lastInput;      // [S][C][B]   last analysed spectrum (only used by blocks without a new spectrum)
-  uint32_t *rng;      // [S]
-  float *freqEst;     // [S][2]      freqEstimateWeighted, freqEstimateWeight
-  float *ring;        // [S][C][L]   overlap-add ring between chunks
-  // per chunk slot, written by the premap kernel
+  cf *outSpec;        // [S][C][B]     Band.output carried between wavefront passes and chunks
+  float *predE[2];    // [S][C][B] x2  Prediction.energy of a chunk's last block (read [parity], write [parity^1])
+  cf *lastInput;      // [S][C][B]     last analysed spectrum (only used by blocks without a new spectrum)
+  float *freqEst;     // [S][2]        freqEstimateWeighted, freqEstimateWeight
+  float *ring;        // [S][C][L]     overlap-add ring between chunks
+  // per chunk slot
   float *inEnergy;    // [S][T][C][B]
-  float *map;         // [S][T][B][2]   {inputBin, freqGrad}
-  // scratch
-  cf *predIn;         // [S][C][B]
-  float *terms;       // [S][B][NT]
+  float *map;         // [S][T][B][2]  {inputBin, freqGrad}
+  float *fmAuto;      // [S][T][2]     formant auto-detect: spectral peak (top, index)
+  float *fmBase;      // [S][T]        formant base bin after the leaky averages
+  float *recA, *recB; // [S][T][B][NA], [S][T][B][NB]  term records
+  const uint32_t *seeds;  // [S]       minstd_rand state at the start of the stream
+  int parity;
 };
 
 BS_HD int trunc_i32(float x) { return fabsf(x) < 2147483648.0f ? (int)x : INT32_MIN; }
 struct alignas(16) f4 { float x, y, z, w; };
-BS_HHD int nterms(int C) { return (16 + 3 * C + 3) & ~3; }
 
 // ------------------------------------------------------------------------------------------------------------
 // radix-4 DIT passes on split arrays (W#21/W#34 forward, W#20/W#33 inverse), `outer` sub-transforms of length
@@ -326,7 +318,7 @@ BS_HD float lerp_f(const float *a, int B, int low, float fr) {
   return ((hi - lo) * fr) + lo;
 }
 // minstd_rand: state after n steps from x (x_{k+1} = 48271 x_k mod 2^31-1), by square-and-multiply
-BS_HD uint32_t minstd_jump(uint32_t x, uint32_t n) {
+BS_HHD uint32_t minstd_jump(uint32_t x, uint32_t n) {
   unsigned long long a = 48271ull, r = 1ull; const unsigned long long m = 2147483647ull;
   while (n) { if (n & 1u) r = (r * a) % m; a = (a * a) % m; n >>= 1; }
   return (uint32_t)((r * (unsigned long long)x) % m);
@@ -339,29 +331,38 @@ BS_HD void make_output(float energy, cf fallback, float re, float im, float &ore
   oim = s * im; ore = s * re;
 }
 
-// State-independent part of the spectral stage of one block: input energies, energy smoothing, peak picking,
-// the output frequency map and the formant envelope (W#48 8238-9312).  It depends only on the block's input spectrum
-// and parameters (except the formant auto-detect, which carries freqEst across blocks), so the premap kernel runs it
-// for all blocks of a chunk in parallel.  Sequential recurrences run on tid 0.
-// smem (floats): energy[B+2] | smoothed[B] | cpk[B/2+2] ints | peaks[B] | misc[16]
+// ------------------------------------------------------------------------------------------------------------
+// Spectral stage.  Split by what depends on the carried phase state (Band.output):
+//
+//   map stage      (premap_kernel)    input energies, energy smoothing, peak picking, output frequency map, formant
+//                                     envelope (W#48 8238-9312).  State-free except the formant auto-detect, whose two
+//                                     leaky averages are advanced by freqest_kernel between phase A and phase B.
+//   term stage     (preterms_kernel)  every coefficient of the preliminary prediction (S5) and of the vertical chain
+//                                     (S6) that does not involve Band.output: one record per (block, bin).
+//   chain stage    (chain_kernel)     the recurrence itself: bin k of block m needs bins k-1, k-longStep of block m and
+//                                     bins k+1, k+longStep of block m-1, so consecutive blocks of one stream run as a
+//                                     wavefront -- lane j of a warp walks block m0+j, `lag` bins behind lane j-1.
+//
+// smem of the map stage (floats): energy[B+2] | smoothed[B] | cpk[B/2+2] ints | peaks[B] | misc[16]
 BS_HHD size_t map_smem_floats(int B) { return (((size_t)(B + 2) + B + (B / 2 + 2) + B + 16) + 3) & ~(size_t)3; }
+BS_HHD bool fm_auto(const BlockRec &rec) { return (rec.flags & kFormants) && !(rec.fmBaseFreq > 0.f); }
+
+// phase A: energies, map; for auto-detect formant blocks also the spectral-peak pick feeding the base estimate
 template <int CT>
-BS_HD void map_stage(const DevGeom &g, const DevTables &T, const BlockRec rec, const BlockRec2 rec2, const cf *inp,
-                     float *freqEst, float *inEnergy, float *mapv, float *sm, int tid, int nt) {
+BS_HD void map_stage_a(const DevGeom &g, const DevTables &T, const BlockRec rec, const cf *inp, float *inEnergy, float *mapv,
+                       float *fmAuto /* [2]: top, i1 (int bits) */, float *sm, int tid, int nt) {
   const int C = CT > 0 ? CT : g.C, B = g.B;
-  const bool mapped = rec.flags & kMapped, formants = rec.flags & kFormants;
+  const bool mapped = rec.flags & kMapped;
   const float fN = (float)(uint32_t)g.N, fH = (float)(uint32_t)g.H, ratio = fN / fH;
   float *energy = sm, *smoothed = sm + (B + 2);
   int *cpk = (int *)(smoothed + B);
   float *peaksG = (float *)(cpk + (B / 2 + 2));
-  int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] monotone flag, [2] formant base bin
-  BS_MARK_INIT();
+  int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] monotone flag
   for (int idx = tid; idx < C * B; idx += nt) {
     cf v = inp[idx];
     inEnergy[idx] = (v.im * v.im) + (v.re * v.re);
   }
   BS_SYNC();
-  BS_MARK(0);
   if (mapped) {
     for (int k = tid; k < B; k += nt) {
       float e = 0.f;
@@ -372,10 +373,8 @@ BS_HD void map_stage(const DevGeom &g, const DevTables &T, const BlockRec rec, c
     if (tid == 0) {
       // smoothEnergy steps 1,2 (one-pole, carry kept across both) then findPeaks
       float slew = 1.0f / ((ratio * 0.5f) + 1.0f), carry = 0.f;
-      BS_MARK(1);
       carry = smooth_pass(smoothed, B, slew, carry);
       carry = smooth_pass(smoothed, B, slew, carry);
-      BS_MARK(2);
       int nP = 0, k = 0, mono = 1, prevC = INT32_MIN;
       while (k < B) {
         if (!(energy[k] <= smoothed[k])) {
@@ -397,7 +396,6 @@ BS_HD void map_stage(const DevGeom &g, const DevTables &T, const BlockRec rec, c
         ++k;
       }
       misc[0] = nP; misc[1] = mono;
-      BS_MARK(3);
     }
     BS_SYNC();
     // updateOutputMap: every bin finds the LAST section (in the reference's write order) that covers it
@@ -441,8 +439,7 @@ BS_HD void map_stage(const DevGeom &g, const DevTables &T, const BlockRec rec, c
     for (int k = tid; k < B; k += nt) { mapv[2 * k] = (float)(uint32_t)k; mapv[2 * k + 1] = 1.0f; }
   }
   BS_SYNC();
-  BS_MARK(4);
-  if (formants) {
+  if (fm_auto(rec)) {
     float *fm = energy;  // [B+2]
     for (int k = tid; k < B + 2; k += nt) {
       float e = 0.f;
@@ -451,294 +448,217 @@ BS_HD void map_stage(const DevGeom &g, const DevTables &T, const BlockRec rec, c
     }
     BS_SYNC();
     if (tid == 0) {
-      float base = rec.fmBaseFreq, baseBin = (base * fN) + -0.5f;
-      if (!(base > 0.f)) {
-        int i1 = 0, i2 = 0, i3 = 0;
-        for (int i = 1; i <= B - 2; ++i) {
-          float v = fm[i];
-          if (v < fm[i - 1]) continue;
-          if (v <= fm[i + 1]) continue;
-          if (v <= fm[i3]) continue;
-          if (fm[i2] >= v) { i3 = i; continue; }
-          if (fm[i1] < v) { i3 = i2; i2 = i1; i1 = i; continue; }
-          i3 = i2; i2 = i;
-        }
-        float top = fm[i1]; double dtop = (double)top;
-        if ((double)fm[i2] > (dtop * 0.1)) {
-          int d = i1 - i2; if (d < 0) d = -d;
+      int i1 = 0, i2 = 0, i3 = 0;
+      for (int i = 1; i <= B - 2; ++i) {
+        float v = fm[i];
+        if (v < fm[i - 1]) continue;
+        if (v <= fm[i + 1]) continue;
+        if (v <= fm[i3]) continue;
+        if (fm[i2] >= v) { i3 = i; continue; }
+        if (fm[i1] < v) { i3 = i2; i2 = i1; i1 = i; continue; }
+        i3 = i2; i2 = i;
+      }
+      float top = fm[i1]; double dtop = (double)top;
+      if ((double)fm[i2] > (dtop * 0.1)) {
+        int d = i1 - i2; if (d < 0) d = -d;
+        if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
+        if (!((double)fm[i3] <= (dtop * 0.01))) {
+          d = i1 - i3; if (d < 0) d = -d;
           if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
-          if (!((double)fm[i3] <= (dtop * 0.01))) {
-            d = i1 - i3; if (d < 0) d = -d;
-            if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
-          }
         }
-        float w = freqEst[1];
-        float nw = (float)(((double)(top - w) * 0.25) + (double)w);
-        freqEst[1] = nw;
-        float ww = freqEst[0];
-        ww = (float)(((double)((top * (float)i1) - ww) * 0.25) + (double)ww);
-        freqEst[0] = ww;
-        baseBin = ww / (nw + 1e-30f);
       }
-      misc[2] = __float_as_int_hd(baseBin);
-    }
-    BS_SYNC();
-    for (int k = tid; k < B; k += nt) fm[k] = sqrtf(fm[k]);
-    BS_SYNC();
-    if (tid == 0) {
-      float baseBin = __int_as_float_hd(misc[2]);
-      float slew = (float)(1.0 / (((double)baseBin * 0.5) + 1.0));
-      float st = smooth_pass(fm, B, slew, 0.f);
-      smooth_pass(fm, B, slew, st);
-    }
-    BS_SYNC();
-    const bool comp = rec.flags & kFormantComp;
-    for (int k = tid; k < B; k += nt) {
-      float f = ((float)k + 0.5f) / fN;
-      if (comp) f = map_freq(f, rec.fmFreqMult, rec2.fmLimit);
-      float metric = fm[k], lim = rec2.fmLimit;
-      float gq = rec.fmInv * f;
-      float fi = (gq > lim) ? (((1.0f - rec.fmMult) * lim) + f) : gq;
-      float pos = (fi * fN) + -0.5f, env = 0.f;
-      if (!(pos < 0.f)) {
-        float fB = (float)B, x = (fB < pos) ? fB : pos, fl = floorf(x), fr = x - fl;
-        int idx = trunc_i32(fl);
-        float lo = fm[idx];
-        env = (fr * (fm[idx + 1] - lo)) + lo;
-      }
-      float g2 = env / (metric + 1e-30f); g2 = g2 * g2;
-      for (int c = 0; c < C; ++c) { size_t o = (size_t)c * B + k; inEnergy[o] = g2 * inEnergy[o]; }
+      fmAuto[0] = top; fmAuto[1] = __int_as_float_hd(i1);
     }
     BS_SYNC();
   }
 }
 
-// smem of the spectral kernel (floats): [map_stage area] | term tiles [2][32][NT] | chain rings
-BS_HHD size_t spectral_smem_head(int B) { return map_smem_floats(B); }
-BS_HHD size_t spectral_smem_floats(int B, int C) { return spectral_smem_head(B) + 64 * (size_t)nterms(C) + 192 + 128 * (size_t)C + 16; }
+// the two leaky averages of the formant base estimate, one block (W#48 8900-8960); returns the base bin
+BS_HD float freqest_step(float *freqEst, const float *fmAuto) {
+  const float top = fmAuto[0]; const int i1 = __float_as_int_hd(fmAuto[1]);
+  float w = freqEst[1];
+  float nw = (float)(((double)(top - w) * 0.25) + (double)w);
+  freqEst[1] = nw;
+  float ww = freqEst[0];
+  ww = (float)(((double)((top * (float)i1) - ww) * 0.25) + (double)ww);
+  freqEst[0] = ww;
+  return ww / (nw + 1e-30f);
+}
 
-// State-dependent part of one block of one stream (W#48 8193-8229 rotate, 9314-9455 preliminary prediction,
-// 9458-9873 vertical prediction chain).  `doMap`: the block's map stage was not precomputed (formant auto-detect).
+// phase B: formant envelope applied to the input energies (needs the base bin)
 template <int CT>
-BS_HD void spectral_block(const DevGeom &g, const DevTables &T, const BlockRec rec, const BlockRec2 rec2,
-                          const cf *inp, const cf *inPrev /* [C][B] each; inPrev == nullptr: no new spectrum */, cf *outSpec,
-                          float *predE, uint32_t *rngp, float *freqEst, float *inEnergy, float *mapv, cf *predIn,
-                          float *terms, cf *specOut, bool doMap, float *sm, int tid, int nt) {
-  const int C = CT > 0 ? CT : g.C, B = g.B, NT = nterms(C);
+BS_HD void map_stage_b(const DevGeom &g, const BlockRec rec, const BlockRec2 rec2, float baseBinAuto, float *inEnergy, float *sm, int tid, int nt) {
+  const int C = CT > 0 ? CT : g.C, B = g.B;
+  if (!(rec.flags & kFormants)) return;
+  const float fN = (float)(uint32_t)g.N;
+  float *fm = sm;  // [B+2]
+  for (int k = tid; k < B + 2; k += nt) {
+    float e = 0.f;
+    if (k < B) for (int c = 0; c < C; ++c) e = e + inEnergy[(size_t)c * B + k];
+    fm[k] = sqrtf(e);
+  }
+  BS_SYNC();
+  if (tid == 0) {
+    const float base = rec.fmBaseFreq;
+    const float baseBin = (base > 0.f) ? ((base * fN) + -0.5f) : baseBinAuto;
+    float slew = (float)(1.0 / (((double)baseBin * 0.5) + 1.0));
+    float st = smooth_pass(fm, B, slew, 0.f);
+    smooth_pass(fm, B, slew, st);
+  }
+  BS_SYNC();
+  const bool comp = rec.flags & kFormantComp;
+  for (int k = tid; k < B; k += nt) {
+    float f = ((float)k + 0.5f) / fN;
+    if (comp) f = map_freq(f, rec.fmFreqMult, rec2.fmLimit);
+    float metric = fm[k], lim = rec2.fmLimit;
+    float gq = rec.fmInv * f;
+    float fi = (gq > lim) ? (((1.0f - rec.fmMult) * lim) + f) : gq;
+    float pos = (fi * fN) + -0.5f, env = 0.f;
+    if (!(pos < 0.f)) {
+      float fB = (float)B, x = (fB < pos) ? fB : pos, fl = floorf(x), fr = x - fl;
+      int idx = trunc_i32(fl);
+      float lo = fm[idx];
+      env = (fr * (fm[idx + 1] - lo)) + lo;
+    }
+    float g2 = env / (metric + 1e-30f); g2 = g2 * g2;
+    for (int c = 0; c < C; ++c) { size_t o = (size_t)c * B + k; inEnergy[o] = g2 * inEnergy[o]; }
+  }
+  BS_SYNC();
+}
+
+// ---- term stage: per-(block, bin) records
+// recA[k] (chain, NA floats): 0..3 up1.re up1.im upLong.re upLong.im | 4..7 down1.re down1.im downLong.re downLong.im |
+//                             8 maxChannel (int bits) | 12+5c: energy, predIn.re, predIn.im, chanTwist.re, chanTwist.im
+// recB[k] (S5, NB floats):    3c: twist.re twist.im divisor
+BS_HHD int na_floats(int C) { return (12 + 5 * C + 3) & ~3; }
+BS_HHD int nb_floats(int C) { return (3 * C + 3) & ~3; }
+
+template <int CT>
+BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec rec, uint32_t rng0, const cf *inp,
+                          const cf *inPrev /* [C][B]; nullptr: no new spectrum */, const float *inEnergy, const float *mapv,
+                          const float *prevInE, const float *prevMap /* previous block of this stream in the chunk, or nullptr */,
+                          const float *prevEState /* Prediction.energy carried from the previous chunk */,
+                          float *predEOut /* nullptr unless this is the stream's last block of the chunk */,
+                          float *recA, float *recB, int tid, int nt) {
+  const int C = CT > 0 ? CT : g.C, B = g.B, NA = na_floats(C), NB = nb_floats(C);
   const bool isNew = rec.flags & kNew;
-  float *tileT = sm + spectral_smem_head(B);            // [2][32][NT] two 32-bin term tiles (16-byte aligned)
-  float *tileO = tileT + 64 * (size_t)NT;               // chain output rings: [64] cf, [64] int, [64][C] cf
   const cf *prv = isNew ? inPrev : inp;
   const cf *prvRot = isNew ? T.specRot : nullptr;
-  BS_MARK_INIT();
-  // S1 rotate Band.output (prevInput is rotated on the fly when read)
-  if (isNew) {
-    for (int idx = tid; idx < C * B; idx += nt) {
-      int k = idx % B;
-      cf o = outSpec[idx], r = T.specRot[k], n;
-      n.im = (o.im * r.re) + (o.re * r.im); n.re = (o.re * r.re) - (o.im * r.im);
-      outSpec[idx] = n;
-    }
-  }
-  if (doMap) map_stage<CT>(g, T, rec, rec2, inp, freqEst, inEnergy, mapv, sm, tid, nt);
-  BS_SYNC();
-  BS_MARK(5);
-  // S5 preliminary prediction, all (channel, bin) in parallel
-  for (int idx = tid; idx < C * B; idx += nt) {
-    int c = idx / B, k = idx - c * B;
-    const cf *ic = inp + (size_t)c * B, *pc = prv + (size_t)c * B;
-    float ib = mapv[2 * k], fl = floorf(ib);
-    int low = trunc_i32(fl); float fr = ib - fl;
-    float prevE = predE[idx], grad = mapv[2 * k + 1];
-    float en = lerp_f(inEnergy + (size_t)c * B, B, low, fr) * (grad > 0.f ? grad : 0.f);
-    predE[idx] = en;
-    cf in = lerp_c(ic, B, low, fr); predIn[idx] = in;
-    cf pv = lerp_prev(pc, prvRot, B, low, fr);
-    float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
-    cf o = outSpec[idx];
-    float div = ((en > prevE) ? en : prevE) + 1e-15f;
-    cf n;
-    n.im = ((tIm * o.re) + (tRe * o.im)) / div;
-    n.re = ((tRe * o.re) - (tIm * o.im)) / div;
-    outSpec[idx] = n;
-  }
-  BS_SYNC();
-  BS_MARK(6);
-  // S6 part 1: everything that does not depend on the chain, per bin, in parallel -> terms[k][NT]
   const int longStep = g.longStep;
   const float tf = rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor;
   const float rlo = ((tf > 2.0f) ? 4.0f : 0.0f) - tf, rscale = (tf - rlo) * 0x1p-31f, fLong = (float)longStep;
   const bool randomTF = !(tf <= 2.0f);
-  const uint32_t rng0 = *rngp;
   for (int k = tid; k < B; k += nt) {
-    float *tt = terms + (size_t)k * NT;
-    int mc = 0; float me = predE[k];
-    for (int c = 1; c < C; ++c) { float en = predE[(size_t)c * B + k]; if (en > me) { me = en; mc = c; } }
-    const cf *ic = inp + (size_t)mc * B; const cf *pi = predIn + (size_t)mc * B; const cf *oc = outSpec + (size_t)mc * B;
-    float pRe = pi[k].re, pIm = pi[k].im;
-    tt[11] = __int_as_float_hd(mc);
+    float *ra = recA + (size_t)k * NA, *rb = recB + (size_t)k * NB;
+    const float ib = mapv[2 * k], fl = floorf(ib), grad = mapv[2 * k + 1];
+    const int low = trunc_i32(fl); const float fr = ib - fl;
+    const float gpos = grad > 0.f ? grad : 0.f;
+    int lowP = 0; float frP = 0.f, gP = 0.f;
+    if (prevMap) {
+      const float ibP = prevMap[2 * k], flP = floorf(ibP), grP = prevMap[2 * k + 1];
+      lowP = trunc_i32(flP); frP = ibP - flP; gP = grP > 0.f ? grP : 0.f;
+    }
+    // S5 coefficients (W#48 9314-9455) and the maximum-energy channel
+    int mc = 0; float me = 0.f, pRe = 0.f, pIm = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float en = lerp_f(inEnergy + (size_t)c * B, B, low, fr) * gpos;
+      const cf in = lerp_c(inp + (size_t)c * B, B, low, fr);
+      const cf pv = lerp_prev(prv + (size_t)c * B, prvRot, B, low, fr);
+      const float prevE = prevMap ? (lerp_f(prevInE + (size_t)c * B, B, lowP, frP) * gP) : prevEState[(size_t)c * B + k];
+      if (predEOut) predEOut[(size_t)c * B + k] = en;
+      const float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
+      rb[3 * c] = tRe; rb[3 * c + 1] = tIm; rb[3 * c + 2] = ((en > prevE) ? en : prevE) + 1e-15f;
+      ra[12 + 5 * c] = en; ra[12 + 5 * c + 1] = in.re; ra[12 + 5 * c + 2] = in.im;
+      if (c == 0 || en > me) { me = en; mc = c; pRe = in.re; pIm = in.im; }
+    }
+    for (int c = 0; c < C; ++c) {   // channel twists: predIn[c] * conj(predIn[mc])
+      const float cRe = ra[12 + 5 * c + 1], cIm = ra[12 + 5 * c + 2];
+      ra[12 + 5 * c + 3] = (pIm * cIm) + (pRe * cRe);
+      ra[12 + 5 * c + 4] = (pRe * cIm) - (pIm * cRe);
+    }
+    ra[8] = __int_as_float_hd(mc); ra[9] = 0.f; ra[10] = 0.f; ra[11] = 0.f;
+    const cf *ic = inp + (size_t)mc * B;
+    // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep ...
+    float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
     if (k > 0) {
-      float ib = mapv[2 * k], btf = tf;
+      float btf = tf;
       if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
-      float x = ib - btf; int low = trunc_i32(floorf(x)); float fr = x - (float)low;
-      cf d = lerp_c(ic, B, low, fr);
-      tt[1] = (d.re * pIm) - (d.im * pRe); tt[0] = (d.im * pIm) + (d.re * pRe);
+      float x = ib - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
+      cf d = lerp_c(ic, B, lo2, fr2);
+      u1 = (d.re * pIm) - (d.im * pRe); u0 = (d.im * pIm) + (d.re * pRe);
       if (k >= longStep) {
-        x = ib - (btf * fLong); low = trunc_i32(floorf(x)); fr = x - (float)low;
-        d = lerp_c(ic, B, low, fr);
-        tt[2] = (d.im * pIm) + (d.re * pRe); tt[3] = (d.re * pIm) - (d.im * pRe);
+        x = ib - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
+        d = lerp_c(ic, B, lo2, fr2);
+        u2 = (d.im * pIm) + (d.re * pRe); u3 = (d.re * pIm) - (d.im * pRe);
       }
     }
+    // ... and downward neighbours k+1, k+longStep (their predIn is re-interpolated here for channel mc)
     if (k < B - 1) {
       float btf = tf;
       if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k + 1)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
-      float x = mapv[2 * (k + 1)] - btf; int low = trunc_i32(floorf(x)); float fr = x - (float)low;
-      cf d = lerp_c(ic, B, low, fr);
-      float uIm = pi[k + 1].im, uRe = pi[k + 1].re;
-      float tRe = (d.im * uIm) + (d.re * uRe), tIm = (d.re * uIm) - (d.im * uRe);
-      float oIm = oc[k + 1].im, oRe = oc[k + 1].re;
-      tt[4] = tRe * oRe; tt[5] = tIm * oIm;                 // phRe = ((tt4 + phRe) + tt5)
-      tt[8] = (tRe * oIm) - (tIm * oRe);                    // phIm = tt8 + phIm
+      const float ib1 = mapv[2 * (k + 1)], fl1 = floorf(ib1);
+      const cf u = lerp_c(ic, B, trunc_i32(fl1), ib1 - fl1);
+      float x = ib1 - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
+      cf d = lerp_c(ic, B, lo2, fr2);
+      d0 = (d.im * u.im) + (d.re * u.re); d1 = (d.re * u.im) - (d.im * u.re);
       if (k < B - longStep) {
-        int kk = k + longStep;
-        x = mapv[2 * kk] - (btf * fLong); low = trunc_i32(floorf(x)); fr = x - (float)low;
-        d = lerp_c(ic, B, low, fr);
-        uIm = pi[kk].im; uRe = pi[kk].re;
-        tRe = (d.im * uIm) + (d.re * uRe); tIm = (d.re * uIm) - (d.im * uRe);
-        oIm = oc[kk].im; oRe = oc[kk].re;
-        tt[6] = tRe * oRe; tt[7] = tIm * oIm;               // phRe = ((tt6 + phRe) + tt7)
-        tt[9] = tRe * oIm; tt[10] = oRe * tIm;              // phIm = ((tt9 + phIm) - tt10)
+        const int kk = k + longStep;
+        const float ibL = mapv[2 * kk], flL = floorf(ibL);
+        const cf uL = lerp_c(ic, B, trunc_i32(flL), ibL - flL);
+        x = ibL - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
+        d = lerp_c(ic, B, lo2, fr2);
+        d2 = (d.im * uL.im) + (d.re * uL.re); d3 = (d.re * uL.im) - (d.im * uL.re);
       }
     }
-    tt[12] = me; tt[13] = pRe; tt[14] = pIm;                   // energy and fallback input of the max channel
-    for (int c = 0; c < C; ++c) {
-      tt[16 + c] = predE[(size_t)c * B + k];
-      cf cp = predIn[(size_t)c * B + k];
-      tt[16 + C + 2 * c] = (pIm * cp.im) + (pRe * cp.re);      // channel twist re
-      tt[16 + C + 2 * c + 1] = (pRe * cp.im) - (pIm * cp.re);  // channel twist im
+    ra[0] = u0; ra[1] = u1; ra[2] = u2; ra[3] = u3; ra[4] = d0; ra[5] = d1; ra[6] = d2; ra[7] = d3;
+  }
+}
+
+// ---- chain stage arithmetic (shared by the CUDA wavefront kernel and the serial test emulation)
+// S1 rotate + S5: Band.output of the previous block at one bin -> the preliminary prediction of this block
+BS_HD cf s5_bin(cf o, bool isNew, cf r, float tRe, float tIm, float div) {
+  if (isNew) { cf n; n.im = (o.im * r.re) + (o.re * r.im); n.re = (o.re * r.re) - (o.im * r.im); o = n; }
+  cf n;
+  n.im = ((tIm * o.re) + (tRe * o.im)) / div;
+  n.re = ((tRe * o.re) - (tIm * o.im)) / div;
+  return n;
+}
+// S6 at bin k.  ra: the bin's recA record.  oPrev/oLong: this block's new output of channel mc at k-1 / k-longStep;
+// n1/nL: this block's S5 prediction of channel mc at k+1 / k+longStep.
+template <int C>
+BS_HD void chain_bin(const float *ra, int mc, int k, int B, int ls, cf oPrev, cf oLong, cf n1, cf nL, cf *out) {
+  float phRe = 0.f, phIm = 0.f;
+  if (k > 0) {
+    phIm = (ra[1] * oPrev.re) + (ra[0] * oPrev.im); phRe = (ra[0] * oPrev.re) - (ra[1] * oPrev.im);
+    if (k >= ls) {
+      phIm = ((ra[2] * oLong.im) + phIm) + (ra[3] * oLong.re);
+      phRe = ((ra[2] * oLong.re) + phRe) - (oLong.im * ra[3]);
     }
   }
-  BS_SYNC();
-  BS_MARK(7);
-  // S6 part 2: the bin-to-bin chain (first warp only).  32-bin tiles of terms are staged through shared memory.
-  // Lane 0 walks the bins computing only the maximum-energy channel (the one the recurrence runs through); the other
-  // channels ("followers": out[c] = makeOutput(out[mc] * channelTwist[c])) do not feed the recurrence unless the
-  // maximum channel changes, so they are filled in for a whole tile at once by all lanes afterwards, and computed on
-  // demand by lane 0 in the rare bins where it needs one early.
-#ifdef BS_HOSTEMU
-  const int lanes = 1, lane = 0; const bool inChain = true;
-#else
-  const int lanes = 32, lane = tid & 31; const bool inChain = tid < 32;
-#endif
-  if (inChain) {
-    cf *ringMc = (cf *)tileO;                  // [64] output of the max channel per bin
-    int *ringIdx = (int *)(tileO + 128);       // [64] which channel that was
-    cf *ringFull = (cf *)(tileO + 192);        // [64][C] all channels (complete for finished tiles)
-    const int nTiles = (B + 31) / 32;
-    for (int i = lane; i < 32 * NT && i < B * NT; i += lanes) tileT[i] = terms[i];
-    BS_WARPSYNC();
-    float pr = 0.f, pi_ = 0.f; int mcPrev = -1;
-    for (int tIdx = 0; tIdx < nTiles; ++tIdx) {
-      const int k0 = tIdx * 32, k1 = (k0 + 32 < B) ? k0 + 32 : B;
-      float *cur = tileT + (size_t)(tIdx & 1) * 32 * NT, *nxt = tileT + (size_t)((tIdx + 1) & 1) * 32 * NT;
-      if (tIdx + 1 < nTiles) {  // prefetch next tile while lane 0 works
-        int nEl = ((k1 + 32 < B) ? 32 : (B - k1)) * NT;
-        const float *src = terms + (size_t)k1 * NT;
-        for (int i = lane; i < nEl; i += lanes) nxt[i] = src[i];
-      }
-      // out[c][j] for a channel c that was not the maximum at bin j
-      auto follower = [&](int j, int c, float &re, float &im) {
-        if (j < k0) { cf v = ringFull[(size_t)(j & 63) * C + c]; re = v.re; im = v.im; return; }
-        const float *tj = cur + (size_t)(j - k0) * NT;
-        cf om = ringMc[j & 63];
-        float tRe = tj[16 + C + 2 * c], tIm = tj[16 + C + 2 * c + 1];
-        float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
-        float n2 = (qIm * qIm) + (qRe * qRe);
-        cf fb = {0.f, 0.f};
-        if (!(n2 > 1e-15f)) fb = predIn[(size_t)c * B + j];
-        make_output(tj[16 + c], fb, qRe, qIm, re, im);
-      };
-      if (lane == 0) {
-        if (k0 >= longStep && k1 <= B - longStep && longStep >= 2) {
-          // interior tile: no edge cases; next bin's terms and long-step history are fetched one bin ahead
-          const float *tt = cur;
-          f4 ta = *(const f4 *)tt, tb = *(const f4 *)(tt + 4), tc = *(const f4 *)(tt + 8), td = *(const f4 *)(tt + 12);
-          cf oL = ringMc[(k0 - longStep) & 63]; int iL = ringIdx[(k0 - longStep) & 63];
-          for (int k = k0; k < k1; ++k) {
-            const float *tn = tt + NT;
-            const f4 na = *(const f4 *)tn, nb = *(const f4 *)(tn + 4), nc = *(const f4 *)(tn + 8), nd = *(const f4 *)(tn + 12);
-            const cf noL = ringMc[(k + 1 - longStep) & 63]; const int niL = ringIdx[(k + 1 - longStep) & 63];
-            const int mc = __float_as_int_hd(tc.w);
-            float oRe = pr, oIm = pi_, lRe = oL.re, lIm = oL.im;
-            if ((mc != mcPrev) | (iL != mc)) {
-              if (mc != mcPrev) follower(k - 1, mc, oRe, oIm);
-              if (iL != mc) follower(k - longStep, mc, lRe, lIm);
-            }
-            float phIm = (ta.y * oRe) + (ta.x * oIm), phRe = (ta.x * oRe) - (ta.y * oIm);
-            phIm = ((ta.z * lIm) + phIm) + (ta.w * lRe);
-            phRe = ((ta.z * lRe) + phRe) - (lIm * ta.w);
-            phIm = tc.x + phIm; phRe = (tb.x + phRe) + tb.y;
-            phIm = (tc.y + phIm) - tc.z; phRe = (tb.z + phRe) + tb.w;
-            const float n2 = (phIm * phIm) + (phRe * phRe);
-            float div = n2;
-            if (!(n2 > 1e-15f)) { phRe = td.y; phIm = td.z; div = ((phRe * phRe) + 1e-15f) + (phIm * phIm); }
-            const float sc = sqrtf(td.x / div);
-            pi_ = sc * phIm; pr = sc * phRe; mcPrev = mc;
-            cf o; o.re = pr; o.im = pi_;
-            ringMc[k & 63] = o; ringIdx[k & 63] = mc;
-            ta = na; tb = nb; tc = nc; td = nd; oL = noL; iL = niL; tt = tn;
-          }
-        } else {
-          for (int k = k0; k < k1; ++k) {
-            const float *tt = cur + (size_t)(k - k0) * NT;
-            const f4 ta = *(const f4 *)tt, tb = *(const f4 *)(tt + 4), tc = *(const f4 *)(tt + 8), td = *(const f4 *)(tt + 12);
-            const int mc = __float_as_int_hd(tc.w);
-            float phRe = 0.f, phIm = 0.f, oRe, oIm;
-            if (k > 0) {
-              if (mc == mcPrev) { oRe = pr; oIm = pi_; } else follower(k - 1, mc, oRe, oIm);
-              phIm = (ta.y * oRe) + (ta.x * oIm); phRe = (ta.x * oRe) - (ta.y * oIm);
-              if (k >= longStep) {
-                const int j = k - longStep;
-                if (ringIdx[j & 63] == mc) { cf v = ringMc[j & 63]; oRe = v.re; oIm = v.im; } else follower(j, mc, oRe, oIm);
-                phIm = ((ta.z * oIm) + phIm) + (ta.w * oRe);
-                phRe = ((ta.z * oRe) + phRe) - (oIm * ta.w);
-              }
-            }
-            if (k < B - 1) {
-              phIm = tc.x + phIm;
-              phRe = (tb.x + phRe) + tb.y;
-              if (k < B - longStep) {
-                phIm = (tc.y + phIm) - tc.z;
-                phRe = (tb.z + phRe) + tb.w;
-              }
-            }
-            cf fb; fb.re = td.y; fb.im = td.z;
-            make_output(td.x, fb, phRe, phIm, oRe, oIm);
-            pr = oRe; pi_ = oIm; mcPrev = mc;
-            cf o; o.re = oRe; o.im = oIm;
-            ringMc[k & 63] = o; ringIdx[k & 63] = mc;
-          }
-        }
-      }
-      BS_WARPSYNC();
-      for (int j = lane; j < k1 - k0; j += lanes) {   // followers of this tile + coalesced write-back
-        const int kk = k0 + j;
-        const int mc = ringIdx[kk & 63];
-        const cf om = ringMc[kk & 63];
-        for (int c = 0; c < C; ++c) {
-          cf o = om;
-          if (c != mc) follower(kk, c, o.re, o.im);
-          ringFull[(size_t)(kk & 63) * C + c] = o;
-          outSpec[(size_t)c * B + kk] = o;
-          specOut[(size_t)c * B + kk] = o;
-        }
-      }
-      BS_WARPSYNC();
+  if (k < B - 1) {
+    const float t4 = ra[4] * n1.re, t5 = ra[5] * n1.im, t8 = (ra[4] * n1.im) - (ra[5] * n1.re);
+    phIm = t8 + phIm; phRe = (t4 + phRe) + t5;
+    if (k < B - ls) {
+      const float t6 = ra[6] * nL.re, t7 = ra[7] * nL.im, t9 = ra[6] * nL.im, t10 = nL.re * ra[7];
+      phIm = (t9 + phIm) - t10; phRe = (t6 + phRe) + t7;
     }
-    if (lane == 0 && randomTF && B >= 2) *rngp = minstd_jump(rng0, (uint32_t)(2 * B - 2));
   }
-  BS_SYNC();
-  BS_MARK(8);
+  float eMc = 0.f; cf fbMc = {0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < C; ++c) if (c == mc) { eMc = ra[12 + 5 * c]; fbMc.re = ra[12 + 5 * c + 1]; fbMc.im = ra[12 + 5 * c + 2]; }
+  cf om;
+  make_output(eMc, fbMc, phRe, phIm, om.re, om.im);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    cf o = om;
+    if (c != mc) {
+      const float tRe = ra[12 + 5 * c + 3], tIm = ra[12 + 5 * c + 4];
+      const float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
+      cf fb; fb.re = ra[12 + 5 * c + 1]; fb.im = ra[12 + 5 * c + 2];
+      make_output(ra[12 + 5 * c], fb, qRe, qIm, o.re, o.im);
+    }
+    out[c] = o;
+  }
 }
 
 // input spectrum of block m: the "current" analysis of the most recent block that had a new spectrum
@@ -748,7 +668,33 @@ BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, long l
   if (r2.lastNew >= slot0) return specIn + (((size_t)s * nSlots + (r2.lastNew - slot0)) * 2 + 0) * CB;
   return lastInput + (size_t)s * CB;
 }
-BS_HD bool needs_inline_map(const BlockRec &rec) { return (rec.flags & kFormants) && !(rec.fmBaseFreq > 0.f); }
 
+#ifdef BS_HOSTEMU
+// serial emulation of the chain stage for the blocks [0, nValid) of one stream's chunk: same per-bin functions, one
+// block after the other (the wavefront order of the CUDA kernel computes exactly the same values)
+template <int C>
+inline void chain_host(const DevGeom &g, const DevTables &T, const BlockRec *blocks /* of this stream, at slot0 */, int nValid,
+                       const float *recA, const float *recB /* [slot][B][N*] */, cf *specOut /* [slot][C][B] */, cf *stateOut /* [C][B] */) {
+  const int B = g.B, ls = g.longStep, NA = na_floats(C), NB = nb_floats(C);
+  std::vector<cf> o5((size_t)C * B);
+  for (int t = 0; t < nValid; ++t) {
+    const bool isNew = blocks[t].flags & kNew;
+    const float *ra = recA + (size_t)t * B * NA, *rb = recB + (size_t)t * B * NB;
+    cf *so = specOut + (size_t)t * C * B;
+    for (int q = 1; q < B; ++q)
+      for (int c = 0; c < C; ++c)
+        o5[(size_t)c * B + q] = s5_bin(stateOut[(size_t)c * B + q], isNew, T.specRot[q], rb[(size_t)q * NB + 3 * c], rb[(size_t)q * NB + 3 * c + 1], rb[(size_t)q * NB + 3 * c + 2]);
+    for (int k = 0; k < B; ++k) {
+      const float *r = ra + (size_t)k * NA;
+      const int mc = __float_as_int_hd(r[8]);
+      cf z = {0.f, 0.f}, out[C];
+      chain_bin<C>(r, mc, k, B, ls, k > 0 ? so[(size_t)mc * B + k - 1] : z, k >= ls ? so[(size_t)mc * B + k - ls] : z,
+                   k < B - 1 ? o5[(size_t)mc * B + k + 1] : z, k < B - ls ? o5[(size_t)mc * B + k + ls] : z, out);
+      for (int c = 0; c < C; ++c) so[(size_t)c * B + k] = out[c];
+    }
+    for (size_t i = 0; i < (size_t)C * B; ++i) stateOut[i] = so[i];
+  }
+}
+#endif
 
 }  // namespace bs

@@ -164,8 +164,9 @@ def stage_bytes(name, g):
     L, H, B = g["L"], g["H"], g["B"]
     table = {
         "analysis_kernel": 4 * L + 8 * B,          # per (window, channel): L samples in, B complex bins out
-        "premap_kernel": 8 * B + 4 * B + 8 * B,    # per channel-block: spectrum in, input energy out, (map / C) out
-        "spectral_kernel": 8 * B * 2 + 24 * B,     # per channel-block: cur+prev spectra in, phase state in/out, output spectrum out
+        "premap_kernel": 8 * B + 4 * B + 4 * B,    # per channel-block: spectrum in, input energy out, map (8B per block, 2 channels) out
+        "preterms_kernel": 16 * B + 8 * B + 64 * B,  # per channel-block: cur+prev spectra, energy+map in, 32-float record / 2 channels out
+        "chain_kernel": 64 * B + 8 * B,            # per channel-block: record in, output spectrum out (state stays on chip within a pass)
         "synthesis_kernel": 8 * B + 8 * L + 4 * H, # per channel-block: spectrum in, OLA ring read+write, H samples out
     }
     return table.get(name)
