@@ -115,14 +115,14 @@ __global__ void __launch_bounds__(256) preterms_kernel(DevGeom g, DevTables T, c
   const float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
   const bool last = (m + 1 == sd.nBlocks) || (t + 1 == nSlots);
   const uint32_t rng0 = minstd_jump(st.seeds[s], (uint32_t)(((unsigned long long)rec2.rngSkip * (unsigned long long)(2 * g.B - 2)) % 2147483646ull));
-  float *ra = st.recA + slot * g.B * na_floats(g.C), *rb = st.recB + slot * g.B * nb_floats(g.C);
+  float *rr = st.rec + slot * rec_rows(g.B, g.longStep) * nr_floats(g.C);
   const float *pE = st.predE[st.parity] + (size_t)s * CB;
   float *pEo = last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr;
   const float *pInE = t > 0 ? inE - CB : nullptr, *pMap = t > 0 ? mp - (size_t)g.B * 2 : nullptr;
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (g.C == 2) preterms_block<2>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, ra, rb, tid, nt);
-  else if (g.C == 1) preterms_block<1>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, ra, rb, tid, nt);
-  else preterms_block<0>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, ra, rb, tid, nt);
+  if (g.C == 2) preterms_block<2>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, tid, nt);
+  else if (g.C == 1) preterms_block<1>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, tid, nt);
+  else preterms_block<0>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, tid, nt);
 }
 
 // ---- chain: one warp per stream.  Lane j walks block p0+j of the chunk, `D` bins behind lane j-1, so that the
@@ -136,108 +136,112 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-constexpr int kChainPF = 4;       // records are requested this many steps before they are consumed
+constexpr int kChainPF = 3;       // records are requested this many steps before they are consumed
 constexpr int kChainTile = 64;    // bins per staged tile of the carried state
+constexpr int kChainWarps = 4;    // warps per CTA: 128 consecutive blocks of one stream in flight
 BS_HHD int chain_stride(int n) { return ((n / 4) | 1) * 4; }   // odd number of 16-byte units: conflict-free LDS.128
 BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
-BS_HHD size_t chain_smem_bytes(int C, int longStep) {
+BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
   const size_t R = chain_ring(longStep);
-  return 2 * R * C * 32 * sizeof(cf) + (size_t)(kChainPF + 1) * 32 * (chain_stride(na_floats(C)) + chain_stride(nb_floats(C))) * sizeof(float) +
-         2 * (size_t)kChainTile * C * sizeof(cf);
+  return (size_t)warps * (2 * R * C * 32 * sizeof(cf) + (size_t)(kChainPF + 1) * 32 * chain_stride(nr_floats(C)) * sizeof(float)) +
+         2 * (size_t)kChainTile * C * sizeof(cf) + 2 * (size_t)warps * C * sizeof(cf);
 }
 
 template <int C>
-__global__ void __launch_bounds__(32) chain_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                   const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut,
-                                                   StateDev st) {
+__global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                                 const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
+                                                                 cf *specOut, StateDev st) {
   extern __shared__ float4 sm4[];
-  constexpr int NA = (12 + 5 * C + 3) & ~3, NB = (3 * C + 3) & ~3, SA = ((NA / 4) | 1) * 4, SB = ((NB / 4) | 1) * 4;
+  constexpr int NR = (9 + 8 * C + 3) & ~3, SR = ((NR / 4) | 1) * 4, SO = 9 + 5 * C;
   constexpr int PF = kChainPF, NS = PF + 1, TL = kChainTile;
-  const int s = blockIdx.x, lane = threadIdx.x;
+  const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = blockDim.x >> 5, j = threadIdx.x;
   const StreamDev sd = streams[s];
   const int B = g.B, ls = g.longStep, D = ls + 2, OA = 1, R = chain_ring(ls), RM = R - 1;
-  cf *ringN = (cf *)sm4;                                  // [R][C][32]  S5 prediction of this lane's block
-  cf *ringO = ringN + (size_t)R * C * 32;                 // [R][C][32]  new output of this lane's block
-  float *stageA = (float *)(ringO + (size_t)R * C * 32);  // [NS][32][SA]
-  float *stageB = stageA + (size_t)NS * 32 * SA;          // [NS][32][SB]
-  cf *tile = (cf *)(stageB + (size_t)NS * 32 * SB);       // [2][C][TL]   carried state, bins of lane 0's S5 stage
+  const size_t rows = rec_rows(B, ls);
+  // per warp: ringN [R][C][32] (S5 prediction of the lane's block), ringO [R][C][32] (its new output), stage [NS][32][SR]
+  const size_t warpFloats = 2 * (size_t)R * C * 32 * 2 + (size_t)NS * 32 * SR;
+  float *wbase = (float *)sm4 + warpFloats * warp;
+  cf *ringN = (cf *)wbase, *ringO = ringN + (size_t)R * C * 32;
+  float *stage = (float *)(ringO + (size_t)R * C * 32);
+  cf *tile = (cf *)((float *)sm4 + warpFloats * nW);       // [2][C][TL]  carried state, the bins ahead of slot 0's S5 stage
+  cf *hand = tile + 2 * (size_t)C * TL;                    // [2][nW][C]  last lane of a warp -> lane 0 of the next
   long long nv = sd.nBlocks - slot0; if (nv > nSlots) nv = nSlots;
   if (nv <= 0) return;
-  const int nValid = (int)nv;
+  const int nValid = (int)nv, perPass = 32 * nW;
   cf *stOut = st.outSpec + (size_t)s * C * B;
   const size_t CB = (size_t)C * B;
 
-  for (int p0 = 0; p0 < nValid; p0 += 32) {
-    const int slot = p0 + lane;
+  for (int p0 = 0; p0 < nValid; p0 += perPass) {
+    const int slot = p0 + j;
     const bool active = slot < nValid;
-    const int lastLane = min(31, nValid - 1 - p0);
+    const int lastJ = min(perPass - 1, nValid - 1 - p0);
     const bool isNew = active && (blocks[sd.blockBase + slot0 + slot].flags & kNew);
     const size_t blk = (size_t)s * nSlots + (active ? slot : p0);
-    const float *ra = st.recA + blk * B * NA, *rb = st.recB + blk * B * NB;
+    const float *rec = st.rec + blk * rows * NR;
     cf *so = specOut + blk * CB;
-    const int tBeg = 1 - OA, tEnd = (B - 1 + ls) + lastLane * D;
+    const int tEnd = (B - 1 + ls) + lastJ * D;
 
-    // request the records of step t (this lane: chain bin t - lane*D - ls, S5 bin t - lane*D + OA)
-    auto request = [&](int t) {
-      const int tau = t - lane * D, k = tau - ls, q = tau + OA, sl = ((t % NS) + NS) % NS;
-      if (active && k >= 0 && k < B) {
-        const float *src = ra + (size_t)k * NA; float *dst = stageA + ((size_t)sl * 32 + lane) * SA;
+    // request the record row of step t (row = local time + OA: chain bin row-ls-1, S5 bin row)
+    auto request = [&](int t, int sl) {
+      const int r = t - j * D + OA;
+      if (active && r >= 1 && r < (int)rows) {
+        const float *src = rec + (size_t)r * NR; float *dst = stage + ((size_t)sl * 32 + lane) * SR;
 #pragma unroll
-        for (int i = 0; i < NA; i += 4) cp_async16(dst + i, src + i);
-      }
-      if (active && q >= 1 && q < B) {
-        const float *src = rb + (size_t)q * NB; float *dst = stageB + ((size_t)sl * 32 + lane) * SB;
-#pragma unroll
-        for (int i = 0; i < NB; i += 4) cp_async16(dst + i, src + i);
+        for (int i = 0; i < NR; i += 4) cp_async16(dst + i, src + i);
       }
     };
-    // stage tile `ti` of the carried state (bins [ti*TL, ti*TL+TL) of every channel), all lanes, 16 bytes each
+    // stage tile `ti` of the carried state (bins [ti*TL, ti*TL+TL) of every channel), whole CTA, 16 bytes per thread
     auto request_tile = [&](int ti) {
       const int b0 = ti * TL;
       if (b0 >= B) return;
       cf *dst = tile + (size_t)(ti & 1) * C * TL;
-      for (int i = lane; i < C * (TL / 2); i += 32) {
-        const int c = i / (TL / 2), j = (i - c * (TL / 2)) * 2;
-        if (b0 + j < B) cp_async16(dst + (size_t)c * TL + j, stOut + (size_t)c * B + b0 + j);   // B is even
+      for (int i = j; i < C * (TL / 2); i += perPass) {
+        const int c = i / (TL / 2), jj = (i - c * (TL / 2)) * 2;
+        if (b0 + jj < B) cp_async16(dst + (size_t)c * TL + jj, stOut + (size_t)c * B + b0 + jj);   // B is even
       }
     };
     request_tile(0); request_tile(1);
-    for (int t = tBeg; t < tBeg + PF; ++t) { request(t); cp_async_commit(); }
+    for (int t = 0; t < PF; ++t) { request(t, t); cp_async_commit(); }
 
     cf last[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) last[c].re = last[c].im = 0.f;
+    cf rot = T.specRot[1];                                  // rotation of the next S5 bin, fetched one step ahead
+    int sl = 0, slReq = PF;                                 // stage slots of step t and of step t+PF (mod NS)
 
-    for (int t = tBeg; t <= tEnd; ++t) {
-      request(t + PF);
-      const int q0 = t + OA;                               // lane 0's S5 bin
+    for (int t = 0; t <= tEnd; ++t) {
+      request(t + PF, slReq);
+      const int q0 = t + OA;                                // slot 0's S5 bin
       if (q0 > 0 && (q0 % TL) == 0) request_tile(q0 / TL + 1);
       cp_async_commit();
       cp_async_wait<PF>();
-      __syncwarp();
-      const int tau = t - lane * D, q = tau + OA, k = tau - ls, sl = ((t % NS) + NS) % NS;
+      __syncthreads();
+      const int tau = t - j * D, q = tau + OA, k = tau - ls;
       cf up[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         up[c].re = __shfl_up_sync(0xffffffffu, last[c].re, 1);
         up[c].im = __shfl_up_sync(0xffffffffu, last[c].im, 1);
       }
+      float row[NR];                                        // this step's record (chain part of bin k, S5 part of bin q)
+      if (active && q >= 1 && q < (int)rows) {
+        const float4 *r4 = (const float4 *)(stage + ((size_t)sl * 32 + lane) * SR);
+#pragma unroll
+        for (int i = 0; i < NR / 4; ++i) { const float4 v = r4[i]; row[4 * i] = v.x; row[4 * i + 1] = v.y; row[4 * i + 2] = v.z; row[4 * i + 3] = v.w; }
+      }
       if (active && q >= 1 && q < B) {
-        const cf r = T.specRot[q];
-        const float *b = stageB + ((size_t)sl * 32 + lane) * SB;
+        const cf r = rot;
+        if (q + 1 < B) rot = T.specRot[q + 1];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           cf o = up[c];
-          if (lane == 0) o = tile[((size_t)((q / TL) & 1) * C + c) * TL + (q % TL)];
-          ringN[((size_t)(q & RM) * C + c) * 32 + lane] = s5_bin(o, isNew, r, b[3 * c], b[3 * c + 1], b[3 * c + 2]);
+          if (lane == 0) o = (warp == 0) ? tile[((size_t)((q / TL) & 1) * C + c) * TL + (q % TL)] : hand[((size_t)((t & 1) ^ 1) * nW + warp - 1) * C + c];
+          ringN[((size_t)(q & RM) * C + c) * 32 + lane] = s5_bin(o, isNew, r, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2]);
         }
       }
       if (active && k >= 0 && k < B) {
-        float rec[NA];
-        const float4 *a4 = (const float4 *)(stageA + ((size_t)sl * 32 + lane) * SA);
-#pragma unroll
-        for (int i = 0; i < NA / 4; ++i) { const float4 v = a4[i]; rec[4 * i] = v.x; rec[4 * i + 1] = v.y; rec[4 * i + 2] = v.z; rec[4 * i + 3] = v.w; }
-        const int mc = __float_as_int(rec[8]);
+        const float *ra = row;
+        const int mc = __float_as_int(ra[8]);
         cf oPrev = last[0];
 #pragma unroll
         for (int c = 1; c < C; ++c) if (c == mc) oPrev = last[c];
@@ -246,19 +250,20 @@ __global__ void __launch_bounds__(32) chain_kernel(DevGeom g, DevTables T, const
         const cf n1 = (k < B - 1) ? ringN[((size_t)((k + 1) & RM) * C + mc) * 32 + lane] : z;
         const cf nL = (k < B - ls) ? ringN[((size_t)((k + ls) & RM) * C + mc) * 32 + lane] : z;
         cf out[C];
-        chain_bin<C>(rec, mc, k, B, ls, oPrev, oLong, n1, nL, out);
+        chain_bin<C>(ra, mc, k, B, ls, oPrev, oLong, n1, nL, out);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           ringO[((size_t)(k & RM) * C + c) * 32 + lane] = out[c];
           so[(size_t)c * B + k] = out[c];
-          if (lane == lastLane) stOut[(size_t)c * B + k] = out[c];
+          if (j == lastJ) stOut[(size_t)c * B + k] = out[c];
+          if (lane == 31) hand[((size_t)(t & 1) * nW + warp) * C + c] = out[c];
           last[c] = out[c];
         }
       }
-      __syncwarp();
+      sl = (sl + 1 == NS) ? 0 : sl + 1; slReq = (slReq + 1 == NS) ? 0 : slReq + 1;
     }
     cp_async_wait<0>();
-    __syncwarp();
+    __syncthreads();
   }
   // carry the input spectrum into the next chunk if its first block reuses it (no new spectrum there)
   const long long mLast = slot0 + nValid - 1;
@@ -267,17 +272,24 @@ __global__ void __launch_bounds__(32) chain_kernel(DevGeom g, DevTables T, const
     if (r2.lastNew >= slot0) {
       const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput);
       cf *dst = st.lastInput + (size_t)s * CB;
-      for (int i = lane; i < (int)CB; i += 32) dst[i] = src[i];
+      for (int i = j; i < (int)CB; i += perPass) dst[i] = src[i];
     }
   }
 }
 
-template <int C>
-static void launch_chain(int S, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
-                         const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st) {
-  chain_kernel<C><<<S, 32, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st);
+// warps per chain CTA: as many as the chunk can use, the kernel was compiled for, and shared memory holds
+static int chain_warps(int C, int longStep, int nSlots) {
+  int w = std::max(1, std::min(kChainWarps, (nSlots + 31) / 32));
+  while (w > 1 && chain_smem_bytes(C, longStep, w) > (size_t)200 * 1024) --w;
+  return w;
 }
-typedef void (*chain_launch_fn)(int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
+
+template <int C>
+static void launch_chain(int S, int warps, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
+                         const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st) {
+  chain_kernel<C><<<S, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st);
+}
+typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
                                 long long, int, const cf *, cf *, const StateDev &);
 static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>, launch_chain<3>, launch_chain<4>,
                                                 launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
@@ -411,7 +423,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
 #ifdef BS_HOSTEMU
   std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)g.M + g.L + 64) / 4 + 1);
   float *sm = (float *)smv.data();
-  const int NA = na_floats(g.C), NB = nb_floats(g.C);
+  const size_t recPerSlot = (size_t)rec_rows(g.B, g.longStep) * nr_floats(g.C);
   auto mapA = g.C == 2 ? map_stage_a<2> : (g.C == 1 ? map_stage_a<1> : map_stage_a<0>);
   auto mapB = g.C == 2 ? map_stage_b<2> : (g.C == 1 ? map_stage_b<1> : map_stage_b<0>);
   auto termFn = g.C == 2 ? preterms_block<2> : (g.C == 1 ? preterms_block<1> : preterms_block<0>);
@@ -457,7 +469,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
         termFn(e->dg, e->dt, rec, rng0, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput),
                (rec.flags & kNew) ? e->specIn + (slot * 2 + 1) * CB : nullptr, inE, mp, t > 0 ? inE - CB : nullptr,
                t > 0 ? mp - (size_t)g.B * 2 : nullptr, st.predE[st.parity] + (size_t)s * CB,
-               last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr, st.recA + slot * g.B * NA, st.recB + slot * g.B * NB, 0, 1);
+               last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr, st.rec + slot * recPerSlot, 0, 1);
       }
     }
     account("chain_kernel", nBlk * g.C);
@@ -467,13 +479,13 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
       if (nv <= 0) continue;
       const size_t slot = (size_t)s * nSlots;
       const BlockRec *bl = e->dBlocks + sd.blockBase + slot0;
-      const float *ra = st.recA + slot * g.B * NA, *rb = st.recB + slot * g.B * NB;
+      const float *rr = st.rec + slot * recPerSlot;
       cf *so = e->specOut + slot * CB, *state = st.outSpec + (size_t)s * CB;
       switch (g.C) {
-        case 1: chain_host<1>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; case 2: chain_host<2>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
-        case 3: chain_host<3>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; case 4: chain_host<4>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
-        case 5: chain_host<5>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; case 6: chain_host<6>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
-        case 7: chain_host<7>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break; default: chain_host<8>(e->dg, e->dt, bl, (int)nv, ra, rb, so, state); break;
+        case 1: chain_host<1>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; case 2: chain_host<2>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
+        case 3: chain_host<3>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; case 4: chain_host<4>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
+        case 5: chain_host<5>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; case 6: chain_host<6>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
+        case 7: chain_host<7>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; default: chain_host<8>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
       }
       const long long mLast = slot0 + nv - 1;
       if (e->dg.incremental || (mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew))) {
@@ -493,7 +505,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
   }
 #else
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
-  const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep);
+  const int chainWarps = chain_warps(g.C, g.longStep, nSlots);
+  const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
   auto span = [&](const char *name, long long units, auto &&launch) {
     const int k = account(name, units);
     if (e->profiling) {
@@ -516,7 +529,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
     span("preterms_kernel", nBlk * g.C, [&] {
       preterms_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     span("chain_kernel", nBlk * g.C, [&] {
-      kChainLaunch[g.C - 1](S, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
+      kChainLaunch[g.C - 1](S, chainWarps, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
     st.parity ^= 1;
   }
   if (stages & 2)
@@ -550,7 +563,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY) != cudaSuccess ||
-      chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep)) != cudaSuccess ||
+      chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep, chain_warps(g.C, g.longStep, 1 << 20))) != cudaSuccess ||
       cudaFuncSetAttribute(premap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
     std::fprintf(stderr, "bauklank_stretch: block %d / interval %d needs more shared memory than one SM has\n", block, interval);
     bsb_destroy(e); return nullptr;
@@ -686,10 +699,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
-  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (size_t)g.B * 4 * (na_floats(g.C) + nb_floats(g.C)));
+  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (size_t)rec_rows(g.B, g.longStep) * 4 * nr_floats(g.C));
   if (chunkBlocks <= 0) {
-    const size_t budget = (size_t)12 << 30;
-    chunkBlocks = (int)std::min<size_t>(64, std::max<size_t>(1, budget / perSlot));
+    const size_t budget = (size_t)24 << 30;
+    chunkBlocks = (int)std::min<size_t>(128, std::max<size_t>(1, budget / perSlot));
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
   e->chunk = chunkBlocks;
@@ -705,11 +718,11 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.ring = dalloc<float>((size_t)S * g.C * g.L, own);
   st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
-  st.recA = dalloc<float>(nSlotTot * g.B * na_floats(g.C), own); st.recB = dalloc<float>(nSlotTot * g.B * nb_floats(g.C), own);
+  st.rec = dalloc<float>(nSlotTot * rec_rows(g.B, g.longStep) * nr_floats(g.C), own);
   st.seeds = e->dSeeds; st.parity = 0;
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
       !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase ||
-      !st.recA || !st.recB) {
+      !st.rec) {
     free_batch(e);
     return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);
   }

@@ -69,7 +69,7 @@ struct StateDev {
   float *map;         // [S][T][B][2]  {inputBin, freqGrad}
   float *fmAuto;      // [S][T][2]     formant auto-detect: spectral peak (top, index)
   float *fmBase;      // [S][T]        formant base bin after the leaky averages
-  float *recA, *recB; // [S][T][B][NA], [S][T][B][NB]  term records
+  float *rec;         // [S][T][B+longStep+1][NR]  term records (one row per wavefront step)
   const uint32_t *seeds;  // [S]       minstd_rand state at the start of the stream
   int parity;
 };
@@ -526,12 +526,14 @@ BS_HD void map_stage_b(const DevGeom &g, const BlockRec rec, const BlockRec2 rec
   BS_SYNC();
 }
 
-// ---- term stage: per-(block, bin) records
-// recA[k] (chain, NA floats): 0..3 up1.re up1.im upLong.re upLong.im | 4..7 down1.re down1.im downLong.re downLong.im |
-//                             8 maxChannel (int bits) | 12+5c: energy, predIn.re, predIn.im, chanTwist.re, chanTwist.im
-// recB[k] (S5, NB floats):    3c: twist.re twist.im divisor
-BS_HHD int na_floats(int C) { return (12 + 5 * C + 3) & ~3; }
-BS_HHD int nb_floats(int C) { return (3 * C + 3) & ~3; }
+// ---- term stage: per-(block, bin) records.  One row of NR floats per wavefront step of a block: row r holds the chain
+// coefficients of bin k = r - R0 (R0 = longStep + 1) and the S5 coefficients of bin q = r, because that is the pair of
+// bins a lane of the chain kernel works on in the same step.  Rows 0 .. B-1+R0.
+//   0..3 up1.re up1.im upLong.re upLong.im | 4..7 down1.re down1.im downLong.re downLong.im | 8 maxChannel (int bits)
+//   9+5c: energy, predIn.re, predIn.im, chanTwist.re, chanTwist.im            (bin k)
+//   9+5C+3c: S5 twist.re, twist.im, divisor                                   (bin q)
+BS_HHD int nr_floats(int C) { return (9 + 8 * C + 3) & ~3; }
+BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
 
 template <int CT>
 BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec rec, uint32_t rng0, const cf *inp,
@@ -539,8 +541,8 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
                           const float *prevInE, const float *prevMap /* previous block of this stream in the chunk, or nullptr */,
                           const float *prevEState /* Prediction.energy carried from the previous chunk */,
                           float *predEOut /* nullptr unless this is the stream's last block of the chunk */,
-                          float *recA, float *recB, int tid, int nt) {
-  const int C = CT > 0 ? CT : g.C, B = g.B, NA = na_floats(C), NB = nb_floats(C);
+                          float *recRows, int tid, int nt) {
+  const int C = CT > 0 ? CT : g.C, B = g.B, NR = nr_floats(C), R0 = g.longStep + 1, SO = 9 + 5 * C;
   const bool isNew = rec.flags & kNew;
   const cf *prv = isNew ? inPrev : inp;
   const cf *prvRot = isNew ? T.specRot : nullptr;
@@ -549,7 +551,7 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
   const float rlo = ((tf > 2.0f) ? 4.0f : 0.0f) - tf, rscale = (tf - rlo) * 0x1p-31f, fLong = (float)longStep;
   const bool randomTF = !(tf <= 2.0f);
   for (int k = tid; k < B; k += nt) {
-    float *ra = recA + (size_t)k * NA, *rb = recB + (size_t)k * NB;
+    float *ra = recRows + (size_t)(k + R0) * NR, *rb = recRows + (size_t)k * NR + SO;
     const float ib = mapv[2 * k], fl = floorf(ib), grad = mapv[2 * k + 1];
     const int low = trunc_i32(fl); const float fr = ib - fl;
     const float gpos = grad > 0.f ? grad : 0.f;
@@ -568,15 +570,15 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
       if (predEOut) predEOut[(size_t)c * B + k] = en;
       const float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
       rb[3 * c] = tRe; rb[3 * c + 1] = tIm; rb[3 * c + 2] = ((en > prevE) ? en : prevE) + 1e-15f;
-      ra[12 + 5 * c] = en; ra[12 + 5 * c + 1] = in.re; ra[12 + 5 * c + 2] = in.im;
+      ra[9 + 5 * c] = en; ra[9 + 5 * c + 1] = in.re; ra[9 + 5 * c + 2] = in.im;
       if (c == 0 || en > me) { me = en; mc = c; pRe = in.re; pIm = in.im; }
     }
     for (int c = 0; c < C; ++c) {   // channel twists: predIn[c] * conj(predIn[mc])
-      const float cRe = ra[12 + 5 * c + 1], cIm = ra[12 + 5 * c + 2];
-      ra[12 + 5 * c + 3] = (pIm * cIm) + (pRe * cRe);
-      ra[12 + 5 * c + 4] = (pRe * cIm) - (pIm * cRe);
+      const float cRe = ra[9 + 5 * c + 1], cIm = ra[9 + 5 * c + 2];
+      ra[9 + 5 * c + 3] = (pIm * cIm) + (pRe * cRe);
+      ra[9 + 5 * c + 4] = (pRe * cIm) - (pIm * cRe);
     }
-    ra[8] = __int_as_float_hd(mc); ra[9] = 0.f; ra[10] = 0.f; ra[11] = 0.f;
+    ra[8] = __int_as_float_hd(mc);
     const cf *ic = inp + (size_t)mc * B;
     // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep ...
     float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
@@ -645,17 +647,17 @@ BS_HD void chain_bin(const float *ra, int mc, int k, int B, int ls, cf oPrev, cf
   }
   float eMc = 0.f; cf fbMc = {0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < C; ++c) if (c == mc) { eMc = ra[12 + 5 * c]; fbMc.re = ra[12 + 5 * c + 1]; fbMc.im = ra[12 + 5 * c + 2]; }
+  for (int c = 0; c < C; ++c) if (c == mc) { eMc = ra[9 + 5 * c]; fbMc.re = ra[9 + 5 * c + 1]; fbMc.im = ra[9 + 5 * c + 2]; }
   cf om;
   make_output(eMc, fbMc, phRe, phIm, om.re, om.im);
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     cf o = om;
     if (c != mc) {
-      const float tRe = ra[12 + 5 * c + 3], tIm = ra[12 + 5 * c + 4];
+      const float tRe = ra[9 + 5 * c + 3], tIm = ra[9 + 5 * c + 4];
       const float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
-      cf fb; fb.re = ra[12 + 5 * c + 1]; fb.im = ra[12 + 5 * c + 2];
-      make_output(ra[12 + 5 * c], fb, qRe, qIm, o.re, o.im);
+      cf fb; fb.re = ra[9 + 5 * c + 1]; fb.im = ra[9 + 5 * c + 2];
+      make_output(ra[9 + 5 * c], fb, qRe, qIm, o.re, o.im);
     }
     out[c] = o;
   }
@@ -674,18 +676,21 @@ BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, long l
 // block after the other (the wavefront order of the CUDA kernel computes exactly the same values)
 template <int C>
 inline void chain_host(const DevGeom &g, const DevTables &T, const BlockRec *blocks /* of this stream, at slot0 */, int nValid,
-                       const float *recA, const float *recB /* [slot][B][N*] */, cf *specOut /* [slot][C][B] */, cf *stateOut /* [C][B] */) {
-  const int B = g.B, ls = g.longStep, NA = na_floats(C), NB = nb_floats(C);
+                       const float *rec /* [slot][rows][NR] */, cf *specOut /* [slot][C][B] */, cf *stateOut /* [C][B] */) {
+  const int B = g.B, ls = g.longStep, NR = nr_floats(C), R0 = ls + 1, SO = 9 + 5 * C;
+  const size_t rows = rec_rows(B, ls);
   std::vector<cf> o5((size_t)C * B);
   for (int t = 0; t < nValid; ++t) {
     const bool isNew = blocks[t].flags & kNew;
-    const float *ra = recA + (size_t)t * B * NA, *rb = recB + (size_t)t * B * NB;
+    const float *rr = rec + (size_t)t * rows * NR;
     cf *so = specOut + (size_t)t * C * B;
     for (int q = 1; q < B; ++q)
-      for (int c = 0; c < C; ++c)
-        o5[(size_t)c * B + q] = s5_bin(stateOut[(size_t)c * B + q], isNew, T.specRot[q], rb[(size_t)q * NB + 3 * c], rb[(size_t)q * NB + 3 * c + 1], rb[(size_t)q * NB + 3 * c + 2]);
+      for (int c = 0; c < C; ++c) {
+        const float *b = rr + (size_t)q * NR + SO + 3 * c;
+        o5[(size_t)c * B + q] = s5_bin(stateOut[(size_t)c * B + q], isNew, T.specRot[q], b[0], b[1], b[2]);
+      }
     for (int k = 0; k < B; ++k) {
-      const float *r = ra + (size_t)k * NA;
+      const float *r = rr + (size_t)(k + R0) * NR;
       const int mc = __float_as_int_hd(r[8]);
       cf z = {0.f, 0.f}, out[C];
       chain_bin<C>(r, mc, k, B, ls, k > 0 ? so[(size_t)mc * B + k - 1] : z, k >= ls ? so[(size_t)mc * B + k - ls] : z,
