@@ -120,9 +120,11 @@ __global__ void __launch_bounds__(256) preterms_kernel(DevGeom g, DevTables T, c
   float *pEo = last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr;
   const float *pInE = t > 0 ? inE - CB : nullptr, *pMap = t > 0 ? mp - (size_t)g.B * 2 : nullptr;
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (g.C == 2) preterms_block<2>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, tid, nt);
-  else if (g.C == 1) preterms_block<1>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, tid, nt);
-  else preterms_block<0>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, tid, nt);
+  extern __shared__ float4 sm4[];
+  float *sm = (float *)sm4;
+  if (g.C == 2) preterms_block<2>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, sm, tid, nt);
+  else if (g.C == 1) preterms_block<1>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, sm, tid, nt);
+  else preterms_block<0>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, sm, tid, nt);
 }
 
 // ---- chain: one warp per stream.  Lane j walks block p0+j of the chunk, `D` bins behind lane j-1, so that the
@@ -211,8 +213,11 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
 
     for (int t = 0; t <= tEnd; ++t) {
       request(t + PF, slReq);
-      const int q0 = t + OA;                                // slot 0's S5 bin
-      if (q0 > 0 && (q0 % TL) == 0) request_tile(q0 / TL + 1);
+      // slot 0's S5 stage reads bin t+OA this step.  The buffer of tile i-1 was last read one step BEFORE the step with
+      // (t+OA) % TL == 0; threads that are ahead may only overwrite it once everybody has passed the barrier after that
+      // read, i.e. from the step with (t+OA) % TL == 1 on.
+      const int q0 = t + OA;
+      if (q0 > TL && (q0 % TL) == 1) request_tile(q0 / TL + 1);
       cp_async_commit();
       cp_async_wait<PF>();
       __syncthreads();
@@ -421,7 +426,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
     return k;
   };
 #ifdef BS_HOSTEMU
-  std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)g.M + g.L + 64) / 4 + 1);
+  std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)g.M + g.L + preterms_smem_floats(g.C, g.longStep) + 64) / 4 + 1);
   float *sm = (float *)smv.data();
   const size_t recPerSlot = (size_t)rec_rows(g.B, g.longStep) * nr_floats(g.C);
   auto mapA = g.C == 2 ? map_stage_a<2> : (g.C == 1 ? map_stage_a<1> : map_stage_a<0>);
@@ -469,7 +474,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
         termFn(e->dg, e->dt, rec, rng0, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput),
                (rec.flags & kNew) ? e->specIn + (slot * 2 + 1) * CB : nullptr, inE, mp, t > 0 ? inE - CB : nullptr,
                t > 0 ? mp - (size_t)g.B * 2 : nullptr, st.predE[st.parity] + (size_t)s * CB,
-               last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr, st.rec + slot * recPerSlot, 0, 1);
+               last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr, st.rec + slot * recPerSlot, sm, 0, 1);
       }
     }
     account("chain_kernel", nBlk * g.C);
@@ -506,6 +511,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
 #else
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
   const int chainWarps = chain_warps(g.C, g.longStep, nSlots);
+  const size_t smT = preterms_smem_floats(g.C, g.longStep) * sizeof(float);
   const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
   auto span = [&](const char *name, long long units, auto &&launch) {
     const int k = account(name, units);
@@ -527,7 +533,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
         premap_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st, 1); });
     }
     span("preterms_kernel", nBlk * g.C, [&] {
-      preterms_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
+      preterms_kernel<<<nCta, nt, smT, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     span("chain_kernel", nBlk * g.C, [&] {
       kChainLaunch[g.C - 1](S, chainWarps, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
     st.parity ^= 1;
@@ -563,6 +569,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY) != cudaSuccess ||
+      cudaFuncSetAttribute(preterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
       chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep, chain_warps(g.C, g.longStep, 1 << 20))) != cudaSuccess ||
       cudaFuncSetAttribute(premap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
     std::fprintf(stderr, "bauklank_stretch: block %d / interval %d needs more shared memory than one SM has\n", block, interval);

@@ -293,9 +293,32 @@ BS_HD float map_freq(float f, float mult, float limit) {
   if (!(f <= limit)) return ((mult + -1.0f) * limit) + f;
   return mult * f;
 }
-BS_HD float smooth_pass(float *v, int n, float slew, float s) {  // backward then forward one-pole pass
-  for (int i = n - 1; i >= 0; --i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
-  for (int i = 0; i < n; ++i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
+// One-pole smoother, backward then forward (W#48 8420-8520); the recurrence s <- s + (v[i]-s)*slew is strictly serial, so
+// the loop keeps 16 samples in registers at a time: 16 independent loads, 16 dependent updates, 16 stores.
+BS_HD float smooth_pass(float *v, int n, float slew, float s) {
+  constexpr int U = 16;
+  int i = n;
+  for (; i >= U; i -= U) {
+    float x[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) x[j] = v[i - U + j];
+#pragma unroll
+    for (int j = U - 1; j >= 0; --j) { s = ((x[j] - s) * slew) + s; x[j] = s; }
+#pragma unroll
+    for (int j = 0; j < U; ++j) v[i - U + j] = x[j];
+  }
+  for (--i; i >= 0; --i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
+  i = 0;
+  for (; i + U <= n; i += U) {
+    float x[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) x[j] = v[i + j];
+#pragma unroll
+    for (int j = 0; j < U; ++j) { s = ((x[j] - s) * slew) + s; x[j] = s; }
+#pragma unroll
+    for (int j = 0; j < U; ++j) v[i + j] = x[j];
+  }
+  for (; i < n; ++i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
   return s;
 }
 BS_HD cf lerp_c(const cf *a, int B, int low, float fr) {
@@ -323,11 +346,17 @@ BS_HHD uint32_t minstd_jump(uint32_t x, uint32_t n) {
   while (n) { if (n & 1u) r = (r * a) % m; a = (a * a) % m; n >>= 1; }
   return (uint32_t)((r * (unsigned long long)x) % m);
 }
+// x / d and sqrt(x) where d is a positive normal number.  A zero x passes through unchanged, which is what IEEE division
+// and square root give (+-0 / d = +-0, sqrt(+-0) = +-0); it is singled out only so that the hardware divide / sqrt
+// sequences never see a zero operand, which would send the whole warp through their slow path.  Silent bins (pitched
+// down above the input's Nyquist, or digital silence) are full of such zeros.
+BS_HD float div_pos(float x, float d) { const bool z = (x == 0.f); const float q = (z ? 1.0f : x) / d; return z ? x : q; }
+BS_HD float sqrt_z(float x) { const bool z = (x == 0.f); const float q = sqrtf(z ? 1.0f : x); return z ? x : q; }
 BS_HD void make_output(float energy, cf fallback, float re, float im, float &ore, float &oim) {
   float n2 = (im * im) + (re * re), div;
   if (n2 > 1e-15f) div = n2;
   else { re = fallback.re; im = fallback.im; div = ((re * re) + 1e-15f) + (im * im); }
-  float s = sqrtf(energy / div);
+  float s = sqrt_z(div_pos(energy, div));
   oim = s * im; ore = s * re;
 }
 
@@ -343,8 +372,8 @@ BS_HD void make_output(float energy, cf fallback, float re, float im, float &ore
 //                                     bins k+1, k+longStep of block m-1, so consecutive blocks of one stream run as a
 //                                     wavefront -- lane j of a warp walks block m0+j, `lag` bins behind lane j-1.
 //
-// smem of the map stage (floats): energy[B+2] | smoothed[B] | cpk[B/2+2] ints | peaks[B] | misc[16]
-BS_HHD size_t map_smem_floats(int B) { return (((size_t)(B + 2) + B + (B / 2 + 2) + B + 16) + 3) & ~(size_t)3; }
+// smem of the map stage (floats): energy[B+2] | smoothed[B] | cpk[B/2+2] ints | peaks[B] | misc[16] | segCnt[256]
+BS_HHD size_t map_smem_floats(int B) { return (((size_t)(B + 2) + B + (B / 2 + 2) + B + 16 + 256) + 3) & ~(size_t)3; }
 BS_HHD bool fm_auto(const BlockRec &rec) { return (rec.flags & kFormants) && !(rec.fmBaseFreq > 0.f); }
 
 // phase A: energies, map; for auto-detect formant blocks also the spectral-peak pick feeding the base estimate
@@ -358,6 +387,7 @@ BS_HD void map_stage_a(const DevGeom &g, const DevTables &T, const BlockRec rec,
   int *cpk = (int *)(smoothed + B);
   float *peaksG = (float *)(cpk + (B / 2 + 2));
   int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] monotone flag
+  int *segCnt = misc + 16;           // [nt] run starts per thread segment
   for (int idx = tid; idx < C * B; idx += nt) {
     cf v = inp[idx];
     inEnergy[idx] = (v.im * v.im) + (v.re * v.re);
@@ -371,31 +401,43 @@ BS_HD void map_stage_a(const DevGeom &g, const DevTables &T, const BlockRec rec,
     }
     BS_SYNC();
     if (tid == 0) {
-      // smoothEnergy steps 1,2 (one-pole, carry kept across both) then findPeaks
+      // smoothEnergy steps 1,2 (one-pole, carry kept across both)
       float slew = 1.0f / ((ratio * 0.5f) + 1.0f), carry = 0.f;
       carry = smooth_pass(smoothed, B, slew, carry);
       carry = smooth_pass(smoothed, B, slew, carry);
-      int nP = 0, k = 0, mono = 1, prevC = INT32_MIN;
-      while (k < B) {
-        if (!(energy[k] <= smoothed[k])) {
-          float sum = 0.f, wsum = 0.f;
-          while (k < B) {
-            float en = energy[k];
-            if (en <= smoothed[k]) break;
-            sum = en + sum; wsum = (en * (float)k) + wsum; ++k;
-          }
-          float avg = wsum / sum;
-          float f = (avg + 0.5f) / fN;
-          float o = (map_freq(f, rec.pkMult, rec.pkLimit) * fN) + -0.5f;
-          peaksG[2 * nP] = avg; peaksG[2 * nP + 1] = o;
-          int cc = trunc_i32(ceilf(o));
-          if (cc < prevC) mono = 0;
-          prevC = cc; cpk[nP] = cc;
-          ++nP;
+    }
+    BS_SYNC();
+    // findPeaks (W#48 8560-8700): a peak = a maximal run of bins with energy > smoothed.  Runs are independent, so every
+    // thread takes the runs that START in its segment of bins (and follows them past the segment end); the peak index is
+    // the number of run starts before it (counted per segment, then prefix-summed).
+    {
+      const int seg = (B + nt - 1) / nt, k0 = tid * seg, k1 = (k0 + seg < B) ? k0 + seg : B;
+      int cnt = 0;
+      for (int k = k0; k < k1; ++k)
+        if (!(energy[k] <= smoothed[k]) && (k == 0 || energy[k - 1] <= smoothed[k - 1])) ++cnt;
+      segCnt[tid] = cnt;
+      BS_SYNC();
+      if (tid == 0) { int acc = 0; for (int i = 0; i < nt; ++i) { int c = segCnt[i]; segCnt[i] = acc; acc += c; } misc[0] = acc; misc[1] = 1; }
+      BS_SYNC();
+      int nP = segCnt[tid];
+      for (int k = k0; k < k1; ++k) {
+        if (!(!(energy[k] <= smoothed[k]) && (k == 0 || energy[k - 1] <= smoothed[k - 1]))) continue;
+        float sum = 0.f, wsum = 0.f;
+        for (int kk = k; kk < B; ++kk) {
+          float en = energy[kk];
+          if (en <= smoothed[kk]) break;
+          sum = en + sum; wsum = (en * (float)kk) + wsum;
         }
-        ++k;
+        float avg = wsum / sum;
+        float f = (avg + 0.5f) / fN;
+        float o = (map_freq(f, rec.pkMult, rec.pkLimit) * fN) + -0.5f;
+        peaksG[2 * nP] = avg; peaksG[2 * nP + 1] = o;
+        cpk[nP] = trunc_i32(ceilf(o));
+        ++nP;
       }
-      misc[0] = nP; misc[1] = mono;
+      BS_SYNC();
+      const int nAll = misc[0];
+      for (int i = tid + 1; i < nAll; i += nt) if (cpk[i] < cpk[i - 1]) misc[1] = 0;   // benign race: every writer stores 0
     }
     BS_SYNC();
     // updateOutputMap: every bin finds the LAST section (in the reference's write order) that covers it
@@ -535,14 +577,19 @@ BS_HD void map_stage_b(const DevGeom &g, const BlockRec rec, const BlockRec2 rec
 BS_HHD int nr_floats(int C) { return (9 + 8 * C + 3) & ~3; }
 BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
 
+// Rows are produced in tiles of kTermTile bins staged in shared memory, so that every record row leaves the SM as part
+// of one contiguous, 16-byte-vectorised burst (a row mixes two bins R0 apart, hence the R0 rows carried tile to tile).
+constexpr int kTermTile = 256;
+BS_HHD size_t preterms_smem_floats(int C, int longStep) { return (size_t)(kTermTile + longStep + 1) * nr_floats(C); }
+
 template <int CT>
 BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec rec, uint32_t rng0, const cf *inp,
                           const cf *inPrev /* [C][B]; nullptr: no new spectrum */, const float *inEnergy, const float *mapv,
                           const float *prevInE, const float *prevMap /* previous block of this stream in the chunk, or nullptr */,
                           const float *prevEState /* Prediction.energy carried from the previous chunk */,
                           float *predEOut /* nullptr unless this is the stream's last block of the chunk */,
-                          float *recRows, int tid, int nt) {
-  const int C = CT > 0 ? CT : g.C, B = g.B, NR = nr_floats(C), R0 = g.longStep + 1, SO = 9 + 5 * C;
+                          float *recRows, float *sm, int tid, int nt) {
+  const int C = CT > 0 ? CT : g.C, B = g.B, NR = nr_floats(C), R0 = g.longStep + 1, SO = 9 + 5 * C, TB = kTermTile;
   const bool isNew = rec.flags & kNew;
   const cf *prv = isNew ? inPrev : inp;
   const cf *prvRot = isNew ? T.specRot : nullptr;
@@ -550,69 +597,85 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
   const float tf = rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor;
   const float rlo = ((tf > 2.0f) ? 4.0f : 0.0f) - tf, rscale = (tf - rlo) * 0x1p-31f, fLong = (float)longStep;
   const bool randomTF = !(tf <= 2.0f);
-  for (int k = tid; k < B; k += nt) {
-    float *ra = recRows + (size_t)(k + R0) * NR, *rb = recRows + (size_t)k * NR + SO;
-    const float ib = mapv[2 * k], fl = floorf(ib), grad = mapv[2 * k + 1];
-    const int low = trunc_i32(fl); const float fr = ib - fl;
-    const float gpos = grad > 0.f ? grad : 0.f;
-    int lowP = 0; float frP = 0.f, gP = 0.f;
-    if (prevMap) {
-      const float ibP = prevMap[2 * k], flP = floorf(ibP), grP = prevMap[2 * k + 1];
-      lowP = trunc_i32(flP); frP = ibP - flP; gP = grP > 0.f ? grP : 0.f;
-    }
-    // S5 coefficients (W#48 9314-9455) and the maximum-energy channel
-    int mc = 0; float me = 0.f, pRe = 0.f, pIm = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float en = lerp_f(inEnergy + (size_t)c * B, B, low, fr) * gpos;
-      const cf in = lerp_c(inp + (size_t)c * B, B, low, fr);
-      const cf pv = lerp_prev(prv + (size_t)c * B, prvRot, B, low, fr);
-      const float prevE = prevMap ? (lerp_f(prevInE + (size_t)c * B, B, lowP, frP) * gP) : prevEState[(size_t)c * B + k];
-      if (predEOut) predEOut[(size_t)c * B + k] = en;
-      const float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
-      rb[3 * c] = tRe; rb[3 * c + 1] = tIm; rb[3 * c + 2] = ((en > prevE) ? en : prevE) + 1e-15f;
-      ra[9 + 5 * c] = en; ra[9 + 5 * c + 1] = in.re; ra[9 + 5 * c + 2] = in.im;
-      if (c == 0 || en > me) { me = en; mc = c; pRe = in.re; pIm = in.im; }
-    }
-    for (int c = 0; c < C; ++c) {   // channel twists: predIn[c] * conj(predIn[mc])
-      const float cRe = ra[9 + 5 * c + 1], cIm = ra[9 + 5 * c + 2];
-      ra[9 + 5 * c + 3] = (pIm * cIm) + (pRe * cRe);
-      ra[9 + 5 * c + 4] = (pRe * cIm) - (pIm * cRe);
-    }
-    ra[8] = __int_as_float_hd(mc);
-    const cf *ic = inp + (size_t)mc * B;
-    // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep ...
-    float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    if (k > 0) {
-      float btf = tf;
-      if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
-      float x = ib - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
-      cf d = lerp_c(ic, B, lo2, fr2);
-      u1 = (d.re * pIm) - (d.im * pRe); u0 = (d.im * pIm) + (d.re * pRe);
-      if (k >= longStep) {
-        x = ib - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
-        d = lerp_c(ic, B, lo2, fr2);
-        u2 = (d.im * pIm) + (d.re * pRe); u3 = (d.re * pIm) - (d.im * pRe);
+  for (int k0 = 0; k0 < B; k0 += TB) {
+    const int nb = (B - k0 < TB) ? B - k0 : TB;
+    for (int i = tid; i < nb; i += nt) {
+      const int k = k0 + i;
+      float *ra = sm + (size_t)(i + R0) * NR, *rb = sm + (size_t)i * NR + SO;   // local rows: chain part R0 rows further down
+      const float ib = mapv[2 * k], fl = floorf(ib), grad = mapv[2 * k + 1];
+      const int low = trunc_i32(fl); const float fr = ib - fl;
+      const float gpos = grad > 0.f ? grad : 0.f;
+      int lowP = 0; float frP = 0.f, gP = 0.f;
+      if (prevMap) {
+        const float ibP = prevMap[2 * k], flP = floorf(ibP), grP = prevMap[2 * k + 1];
+        lowP = trunc_i32(flP); frP = ibP - flP; gP = grP > 0.f ? grP : 0.f;
       }
-    }
-    // ... and downward neighbours k+1, k+longStep (their predIn is re-interpolated here for channel mc)
-    if (k < B - 1) {
-      float btf = tf;
-      if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k + 1)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
-      const float ib1 = mapv[2 * (k + 1)], fl1 = floorf(ib1);
-      const cf u = lerp_c(ic, B, trunc_i32(fl1), ib1 - fl1);
-      float x = ib1 - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
-      cf d = lerp_c(ic, B, lo2, fr2);
-      d0 = (d.im * u.im) + (d.re * u.re); d1 = (d.re * u.im) - (d.im * u.re);
-      if (k < B - longStep) {
-        const int kk = k + longStep;
-        const float ibL = mapv[2 * kk], flL = floorf(ibL);
-        const cf uL = lerp_c(ic, B, trunc_i32(flL), ibL - flL);
-        x = ibL - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
-        d = lerp_c(ic, B, lo2, fr2);
-        d2 = (d.im * uL.im) + (d.re * uL.re); d3 = (d.re * uL.im) - (d.im * uL.re);
+      // S5 coefficients (W#48 9314-9455) and the maximum-energy channel
+      int mc = 0; float me = 0.f, pRe = 0.f, pIm = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float en = lerp_f(inEnergy + (size_t)c * B, B, low, fr) * gpos;
+        const cf in = lerp_c(inp + (size_t)c * B, B, low, fr);
+        const cf pv = lerp_prev(prv + (size_t)c * B, prvRot, B, low, fr);
+        const float prevE = prevMap ? (lerp_f(prevInE + (size_t)c * B, B, lowP, frP) * gP) : prevEState[(size_t)c * B + k];
+        if (predEOut) predEOut[(size_t)c * B + k] = en;
+        const float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
+        rb[3 * c] = tRe; rb[3 * c + 1] = tIm; rb[3 * c + 2] = ((en > prevE) ? en : prevE) + 1e-15f;
+        ra[9 + 5 * c] = en; ra[9 + 5 * c + 1] = in.re; ra[9 + 5 * c + 2] = in.im;
+        if (c == 0 || en > me) { me = en; mc = c; pRe = in.re; pIm = in.im; }
       }
+      for (int c = 0; c < C; ++c) {   // channel twists: predIn[c] * conj(predIn[mc])
+        const float cRe = ra[9 + 5 * c + 1], cIm = ra[9 + 5 * c + 2];
+        ra[9 + 5 * c + 3] = (pIm * cIm) + (pRe * cRe);
+        ra[9 + 5 * c + 4] = (pRe * cIm) - (pIm * cRe);
+      }
+      ra[8] = __int_as_float_hd(mc);
+      const cf *ic = inp + (size_t)mc * B;
+      // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep ...
+      float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      if (k > 0) {
+        float btf = tf;
+        if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
+        float x = ib - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
+        cf d = lerp_c(ic, B, lo2, fr2);
+        u1 = (d.re * pIm) - (d.im * pRe); u0 = (d.im * pIm) + (d.re * pRe);
+        if (k >= longStep) {
+          x = ib - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
+          d = lerp_c(ic, B, lo2, fr2);
+          u2 = (d.im * pIm) + (d.re * pRe); u3 = (d.re * pIm) - (d.im * pRe);
+        }
+      }
+      // ... and downward neighbours k+1, k+longStep (their predIn is re-interpolated here for channel mc)
+      if (k < B - 1) {
+        float btf = tf;
+        if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k + 1)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
+        const float ib1 = mapv[2 * (k + 1)], fl1 = floorf(ib1);
+        const cf u = lerp_c(ic, B, trunc_i32(fl1), ib1 - fl1);
+        float x = ib1 - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
+        cf d = lerp_c(ic, B, lo2, fr2);
+        d0 = (d.im * u.im) + (d.re * u.re); d1 = (d.re * u.im) - (d.im * u.re);
+        if (k < B - longStep) {
+          const int kk = k + longStep;
+          const float ibL = mapv[2 * kk], flL = floorf(ibL);
+          const cf uL = lerp_c(ic, B, trunc_i32(flL), ibL - flL);
+          x = ibL - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
+          d = lerp_c(ic, B, lo2, fr2);
+          d2 = (d.im * uL.im) + (d.re * uL.re); d3 = (d.re * uL.im) - (d.im * uL.re);
+        }
+      }
+      ra[0] = u0; ra[1] = u1; ra[2] = u2; ra[3] = u3; ra[4] = d0; ra[5] = d1; ra[6] = d2; ra[7] = d3;
     }
-    ra[0] = u0; ra[1] = u1; ra[2] = u2; ra[3] = u3; ra[4] = d0; ra[5] = d1; ra[6] = d2; ra[7] = d3;
+    BS_SYNC();
+    // local rows [0, nOut) are complete: global rows k0 .. k0+nOut-1 (the last tile also flushes the R0 trailing rows)
+    const bool lastTile = k0 + TB >= B;
+    const int nOut = lastTile ? nb + R0 : TB;
+    {
+      const f4 *src = (const f4 *)sm; f4 *dst = (f4 *)(recRows + (size_t)k0 * NR);
+      for (int i = tid; i < nOut * (NR / 4); i += nt) dst[i] = src[i];
+    }
+    BS_SYNC();
+    if (!lastTile)   // chain parts of this tile's last R0 bins belong to the first R0 rows of the next tile
+      for (int i = tid; i < R0 * SO; i += nt) { const int r = i / SO, f = i - r * SO; sm[(size_t)r * NR + f] = sm[(size_t)(TB + r) * NR + f]; }
+    BS_SYNC();
   }
 }
 
@@ -621,8 +684,8 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
 BS_HD cf s5_bin(cf o, bool isNew, cf r, float tRe, float tIm, float div) {
   if (isNew) { cf n; n.im = (o.im * r.re) + (o.re * r.im); n.re = (o.re * r.re) - (o.im * r.im); o = n; }
   cf n;
-  n.im = ((tIm * o.re) + (tRe * o.im)) / div;
-  n.re = ((tRe * o.re) - (tIm * o.im)) / div;
+  n.im = div_pos((tIm * o.re) + (tRe * o.im), div);
+  n.re = div_pos((tRe * o.re) - (tIm * o.im), div);
   return n;
 }
 // S6 at bin k.  ra: the bin's recA record.  oPrev/oLong: this block's new output of channel mc at k-1 / k-longStep;
