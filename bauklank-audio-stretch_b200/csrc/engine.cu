@@ -138,15 +138,12 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-constexpr int kChainPF = 3;       // records are requested this many steps before they are consumed
 constexpr int kChainTile = 64;    // bins per staged tile of the carried state
-constexpr int kChainWarps = 4;    // warps per CTA: 128 consecutive blocks of one stream in flight
-BS_HHD int chain_stride(int n) { return ((n / 4) | 1) * 4; }   // odd number of 16-byte units: conflict-free LDS.128
+constexpr int kChainWarps = 8;    // warps per CTA: up to 256 consecutive blocks of one stream in flight
 BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
 BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
   const size_t R = chain_ring(longStep);
-  return (size_t)warps * (2 * R * C * 32 * sizeof(cf) + (size_t)(kChainPF + 1) * 32 * chain_stride(nr_floats(C)) * sizeof(float)) +
-         2 * (size_t)kChainTile * C * sizeof(cf) + 2 * (size_t)warps * C * sizeof(cf);
+  return (size_t)warps * (2 * R * C * 32 * sizeof(cf)) + 2 * (size_t)kChainTile * C * sizeof(cf) + 2 * (size_t)warps * C * sizeof(cf);
 }
 
 template <int C>
@@ -154,24 +151,21 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
                                                                  const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
                                                                  cf *specOut, StateDev st) {
   extern __shared__ float4 sm4[];
-  constexpr int NR = (9 + 8 * C + 3) & ~3, SR = ((NR / 4) | 1) * 4, SO = 9 + 5 * C;
-  constexpr int PF = kChainPF, NS = PF + 1, TL = kChainTile;
+  constexpr int NR = (9 + 8 * C + 3) & ~3, SO = 9 + 5 * C, TL = kChainTile;
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = blockDim.x >> 5, j = threadIdx.x;
   const StreamDev sd = streams[s];
   const int B = g.B, ls = g.longStep, D = ls + 2, OA = 1, R = chain_ring(ls), RM = R - 1;
-  const size_t rows = rec_rows(B, ls);
-  // per warp: ringN [R][C][32] (S5 prediction of the lane's block), ringO [R][C][32] (its new output), stage [NS][32][SR]
-  const size_t warpFloats = 2 * (size_t)R * C * 32 * 2 + (size_t)NS * 32 * SR;
-  float *wbase = (float *)sm4 + warpFloats * warp;
-  cf *ringN = (cf *)wbase, *ringO = ringN + (size_t)R * C * 32;
-  float *stage = (float *)(ringO + (size_t)R * C * 32);
-  cf *tile = (cf *)((float *)sm4 + warpFloats * nW);       // [2][C][TL]  carried state, the bins ahead of slot 0's S5 stage
+  const int rows = rec_rows(B, ls);
+  // per warp: ringN [R][C][32] (S5 prediction of the lane's block), ringO [R][C][32] (its new output)
+  cf *ringN = (cf *)sm4 + (size_t)warp * 2 * R * C * 32, *ringO = ringN + (size_t)R * C * 32;
+  cf *tile = (cf *)sm4 + (size_t)nW * 2 * R * C * 32;      // [2][C][TL]  carried state, the bins ahead of slot 0's S5 stage
   cf *hand = tile + 2 * (size_t)C * TL;                    // [2][nW][C]  last lane of a warp -> lane 0 of the next
   long long nv = sd.nBlocks - slot0; if (nv > nSlots) nv = nSlots;
   if (nv <= 0) return;
   const int nValid = (int)nv, perPass = 32 * nW;
   cf *stOut = st.outSpec + (size_t)s * C * B;
   const size_t CB = (size_t)C * B;
+  const cf *specRot = T.specRot;
 
   for (int p0 = 0; p0 < nValid; p0 += perPass) {
     const int slot = p0 + j;
@@ -179,19 +173,10 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     const int lastJ = min(perPass - 1, nValid - 1 - p0);
     const bool isNew = active && (blocks[sd.blockBase + slot0 + slot].flags & kNew);
     const size_t blk = (size_t)s * nSlots + (active ? slot : p0);
-    const float *rec = st.rec + blk * rows * NR;
+    const float4 *rec4 = (const float4 *)(st.rec + blk * (size_t)rows * NR);
     cf *so = specOut + blk * CB;
     const int tEnd = (B - 1 + ls) + lastJ * D;
 
-    // request the record row of step t (row = local time + OA: chain bin row-ls-1, S5 bin row)
-    auto request = [&](int t, int sl) {
-      const int r = t - j * D + OA;
-      if (active && r >= 1 && r < (int)rows) {
-        const float *src = rec + (size_t)r * NR; float *dst = stage + ((size_t)sl * 32 + lane) * SR;
-#pragma unroll
-        for (int i = 0; i < NR; i += 4) cp_async16(dst + i, src + i);
-      }
-    };
     // stage tile `ti` of the carried state (bins [ti*TL, ti*TL+TL) of every channel), whole CTA, 16 bytes per thread
     auto request_tile = [&](int ti) {
       const int b0 = ti * TL;
@@ -203,23 +188,38 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
       }
     };
     request_tile(0); request_tile(1);
-    for (int t = 0; t < PF; ++t) { request(t, t); cp_async_commit(); }
+    cp_async_commit();
 
     cf last[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) last[c].re = last[c].im = 0.f;
-    cf rot = T.specRot[1];                                  // rotation of the next S5 bin, fetched one step ahead
-    int sl = 0, slReq = PF;                                 // stage slots of step t and of step t+PF (mod NS)
+    // The record row and the spectral rotation of a step are fetched into registers one step ahead: a step takes
+    // longer than a DRAM round trip, so the loads are complete when the next step starts.
+    float4 nxt[NR / 4];
+    cf rotNxt; rotNxt.re = rotNxt.im = 0.f;
+    auto fetch = [&](int t) {   // row = local time + OA: chain part of bin row-ls-1, S5 part of bin row
+      const int r = t - j * D + OA;
+      if (active && r >= 1 && r < rows) {
+        const float4 *src = rec4 + (size_t)r * (NR / 4);
+#pragma unroll
+        for (int i = 0; i < NR / 4; ++i) nxt[i] = __ldcs(src + i);
+        if (r < B) rotNxt = specRot[r];
+      }
+    };
+    fetch(0);
 
     for (int t = 0; t <= tEnd; ++t) {
-      request(t + PF, slReq);
+      float row[NR];
+#pragma unroll
+      for (int i = 0; i < NR / 4; ++i) { row[4 * i] = nxt[i].x; row[4 * i + 1] = nxt[i].y; row[4 * i + 2] = nxt[i].z; row[4 * i + 3] = nxt[i].w; }
+      const cf rot = rotNxt;
+      fetch(t + 1);
       // slot 0's S5 stage reads bin t+OA this step.  The buffer of tile i-1 was last read one step BEFORE the step with
       // (t+OA) % TL == 0; threads that are ahead may only overwrite it once everybody has passed the barrier after that
       // read, i.e. from the step with (t+OA) % TL == 1 on.
       const int q0 = t + OA;
-      if (q0 > TL && (q0 % TL) == 1) request_tile(q0 / TL + 1);
-      cp_async_commit();
-      cp_async_wait<PF>();
+      if (q0 > TL && (q0 % TL) == 1) { request_tile(q0 / TL + 1); cp_async_commit(); }
+      cp_async_wait<0>();     // (a tile requested this step is not needed for another TL-1 steps; waiting for it is cheap)
       __syncthreads();
       const int tau = t - j * D, q = tau + OA, k = tau - ls;
       cf up[C];
@@ -228,20 +228,12 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
         up[c].re = __shfl_up_sync(0xffffffffu, last[c].re, 1);
         up[c].im = __shfl_up_sync(0xffffffffu, last[c].im, 1);
       }
-      float row[NR];                                        // this step's record (chain part of bin k, S5 part of bin q)
-      if (active && q >= 1 && q < (int)rows) {
-        const float4 *r4 = (const float4 *)(stage + ((size_t)sl * 32 + lane) * SR);
-#pragma unroll
-        for (int i = 0; i < NR / 4; ++i) { const float4 v = r4[i]; row[4 * i] = v.x; row[4 * i + 1] = v.y; row[4 * i + 2] = v.z; row[4 * i + 3] = v.w; }
-      }
       if (active && q >= 1 && q < B) {
-        const cf r = rot;
-        if (q + 1 < B) rot = T.specRot[q + 1];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           cf o = up[c];
           if (lane == 0) o = (warp == 0) ? tile[((size_t)((q / TL) & 1) * C + c) * TL + (q % TL)] : hand[((size_t)((t & 1) ^ 1) * nW + warp - 1) * C + c];
-          ringN[((size_t)(q & RM) * C + c) * 32 + lane] = s5_bin(o, isNew, r, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2]);
+          ringN[((size_t)(q & RM) * C + c) * 32 + lane] = s5_bin(o, isNew, rot, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2]);
         }
       }
       if (active && k >= 0 && k < B) {
@@ -259,13 +251,12 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           ringO[((size_t)(k & RM) * C + c) * 32 + lane] = out[c];
-          so[(size_t)c * B + k] = out[c];
+          __stcs(reinterpret_cast<float2 *>(so + (size_t)c * B + k), make_float2(out[c].re, out[c].im));
           if (j == lastJ) stOut[(size_t)c * B + k] = out[c];
           if (lane == 31) hand[((size_t)(t & 1) * nW + warp) * C + c] = out[c];
           last[c] = out[c];
         }
       }
-      sl = (sl + 1 == NS) ? 0 : sl + 1; slReq = (slReq + 1 == NS) ? 0 : slReq + 1;
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -708,8 +699,8 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
   const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (size_t)rec_rows(g.B, g.longStep) * 4 * nr_floats(g.C));
   if (chunkBlocks <= 0) {
-    const size_t budget = (size_t)24 << 30;
-    chunkBlocks = (int)std::min<size_t>(128, std::max<size_t>(1, budget / perSlot));
+    const size_t budget = (size_t)40 << 30;
+    chunkBlocks = (int)std::min<size_t>(256, std::max<size_t>(1, budget / perSlot));
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
   e->chunk = chunkBlocks;

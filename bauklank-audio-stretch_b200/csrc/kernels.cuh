@@ -350,8 +350,13 @@ BS_HHD uint32_t minstd_jump(uint32_t x, uint32_t n) {
 // and square root give (+-0 / d = +-0, sqrt(+-0) = +-0); it is singled out only so that the hardware divide / sqrt
 // sequences never see a zero operand, which would send the whole warp through their slow path.  Silent bins (pitched
 // down above the input's Nyquist, or digital silence) are full of such zeros.
-BS_HD float div_pos(float x, float d) { const bool z = (x == 0.f); const float q = (z ? 1.0f : x) / d; return z ? x : q; }
-BS_HD float sqrt_z(float x) { const bool z = (x == 0.f); const float q = sqrtf(z ? 1.0f : x); return z ? x : q; }
+#ifdef BS_HOSTEMU
+#define BS_OPAQUE(v) ((void)0)
+#else
+#define BS_OPAQUE(v) asm volatile("" : "+f"(v))   // keeps the compiler from folding the substitute operand back in
+#endif
+BS_HD float div_pos(float x, float d) { const bool z = (x == 0.f); float xs = z ? 1.0f : x; BS_OPAQUE(xs); const float q = xs / d; return z ? x : q; }
+BS_HD float sqrt_z(float x) { const bool z = (x == 0.f); float xs = z ? 1.0f : x; BS_OPAQUE(xs); const float q = sqrtf(xs); return z ? x : q; }
 BS_HD void make_output(float energy, cf fallback, float re, float im, float &ore, float &oim) {
   float n2 = (im * im) + (re * re), div;
   if (n2 > 1e-15f) div = n2;

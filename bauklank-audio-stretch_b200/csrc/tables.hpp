@@ -17,7 +17,7 @@
 
 namespace bs {
 
-struct cf { float re, im; };
+struct alignas(8) cf { float re, im; };   // 8-byte aligned: one 64-bit load/store per complex value
 
 // ---- musl single-precision sin/cos kernels (polynomials evaluated in double, rounded once) ----
 inline float sindf_(double x) {
