@@ -146,6 +146,111 @@ BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
   return (size_t)warps * (2 * R * C * 32 * sizeof(cf)) + 2 * (size_t)kChainTile * C * sizeof(cf) + 2 * (size_t)warps * C * sizeof(cf);
 }
 
+// ---- branch-free IEEE division / square root for the chain's hot loop.
+// `x / d` and `sqrtf(x)` compile to a MUFU seed + FFMA refinement guarded by a range check that branches to a slow
+// subroutine; eight such guarded regions per step serialise the instruction stream of a loop that is latency bound to
+// begin with.  The helpers below run the SAME refinement sequences (they are what nvcc emits on the fast path, see
+// profiles/), without the branch, and report operands outside a conservative safe range in `slow`; the caller then
+// recomputes that step with the plain operators.  Within the safe range both give the correctly rounded result.
+__device__ __forceinline__ float mufu_rcp(float d) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
+__device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float div_fast(float x, float d, bool &slow) {   // zero numerator passes through, as in div_pos
+  const bool z = (x == 0.f);
+  const float xs = z ? 1.0f : x;
+  const int ex = (__float_as_int(xs) >> 23) & 0xff, ed = (__float_as_int(d) >> 23) & 0xff;   // biased exponents
+  slow |= (unsigned)(ex - 32) > 190u || (unsigned)(ed - 32) > 190u || (unsigned)(ex - ed + 90) > 180u || d < 0.f;
+  float r = mufu_rcp(d);
+  const float t = __fmaf_rn(-d, r, 1.0f);
+  r = __fmaf_rn(r, t, r);
+  float q = __fmaf_rn(xs, r, 0.0f);
+  const float e = __fmaf_rn(-d, q, xs);
+  q = __fmaf_rn(r, e, q);
+  return z ? x : q;
+}
+__device__ __forceinline__ float sqrt_fast(float x, bool &slow) {           // zero passes through, as in sqrt_z
+  const bool z = (x == 0.f);
+  const float xs = z ? 1.0f : x;
+  slow |= (unsigned)(__float_as_int(xs) - 0x0d000000) > 0x727fffffu;
+  const float y = mufu_rsq(xs);
+  float sq = __fmul_rn(xs, y);
+  const float h = __fmul_rn(y, 0.5f);
+  const float e = __fmaf_rn(-sq, sq, xs);
+  sq = __fmaf_rn(e, h, sq);
+  return z ? x : sq;
+}
+__device__ __forceinline__ cf s5_fast(cf o, bool isNew, cf r, float tRe, float tIm, float div, bool &slow) {
+  cf n; n.im = (o.im * r.re) + (o.re * r.im); n.re = (o.re * r.re) - (o.im * r.im);
+  if (isNew) o = n;
+  cf y;
+  y.im = div_fast((tIm * o.re) + (tRe * o.im), div, slow);
+  y.re = div_fast((tRe * o.re) - (tIm * o.im), div, slow);
+  return y;
+}
+__device__ __forceinline__ void make_output_fast(float energy, cf fb, float re, float im, cf &o, bool &slow) {
+  const float n2 = (im * im) + (re * re);
+  const bool big = n2 > 1e-15f;
+  const float divF = ((fb.re * fb.re) + 1e-15f) + (fb.im * fb.im);
+  const float re2 = big ? re : fb.re, im2 = big ? im : fb.im, div = big ? n2 : divF;
+  const float sc = sqrt_fast(div_fast(energy, div, slow), slow);
+  o.im = sc * im2; o.re = sc * re2;
+}
+// chain_bin (kernels.cuh) with selects instead of branches; same operations in the same order
+template <int C>
+__device__ __forceinline__ void chain_fast(const float *ra, int mc, int k, int B, int ls, cf oPrev, cf oLong, cf n1, cf nL, cf *out, bool &slow) {
+  float phIm = (ra[1] * oPrev.re) + (ra[0] * oPrev.im), phRe = (ra[0] * oPrev.re) - (ra[1] * oPrev.im);
+  if (!(k > 0)) { phIm = 0.f; phRe = 0.f; }
+  {
+    const float aIm = ((ra[2] * oLong.im) + phIm) + (ra[3] * oLong.re), aRe = ((ra[2] * oLong.re) + phRe) - (oLong.im * ra[3]);
+    if (k >= ls) { phIm = aIm; phRe = aRe; }
+  }
+  {
+    const float t4 = ra[4] * n1.re, t5 = ra[5] * n1.im, t8 = (ra[4] * n1.im) - (ra[5] * n1.re);
+    const float aIm = t8 + phIm, aRe = (t4 + phRe) + t5;
+    if (k < B - 1) { phIm = aIm; phRe = aRe; }
+  }
+  {
+    const float t6 = ra[6] * nL.re, t7 = ra[7] * nL.im, t9 = ra[6] * nL.im, t10 = nL.re * ra[7];
+    const float aIm = (t9 + phIm) - t10, aRe = (t6 + phRe) + t7;
+    if (k < B - ls) { phIm = aIm; phRe = aRe; }
+  }
+  float eMc = ra[9]; cf fbMc; fbMc.re = ra[10]; fbMc.im = ra[11];
+#pragma unroll
+  for (int c = 1; c < C; ++c) if (c == mc) { eMc = ra[9 + 5 * c]; fbMc.re = ra[9 + 5 * c + 1]; fbMc.im = ra[9 + 5 * c + 2]; }
+  cf om;
+  make_output_fast(eMc, fbMc, phRe, phIm, om, slow);
+  if (C == 2) {   // exactly one follower: pick its record fields by mc instead of computing both and discarding one
+    const bool m0 = (mc == 0);
+    const float tRe = m0 ? ra[9 + 5 + 3] : ra[9 + 3], tIm = m0 ? ra[9 + 5 + 4] : ra[9 + 4], eo = m0 ? ra[9 + 5] : ra[9];
+    cf fb; fb.re = m0 ? ra[9 + 5 + 1] : ra[9 + 1]; fb.im = m0 ? ra[9 + 5 + 2] : ra[9 + 2];
+    const float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
+    cf oo;
+    make_output_fast(eo, fb, qRe, qIm, oo, slow);
+    out[0] = m0 ? om : oo; out[C - 1] = m0 ? oo : om;
+    return;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float tRe = ra[9 + 5 * c + 3], tIm = ra[9 + 5 * c + 4];
+    const float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
+    cf fb; fb.re = ra[9 + 5 * c + 1]; fb.im = ra[9 + 5 * c + 2];
+    cf o;
+    bool slowF = false;
+    make_output_fast(ra[9 + 5 * c], fb, qRe, qIm, o, slowF);
+    if (c == mc) o = om; else slow |= slowF;
+    out[c] = o;
+  }
+}
+
+// self-test hook for the helpers above (tests/test_gpu_parity.py): q = x / d, r = sqrt(x), flags bit0/bit1 = slow
+__global__ void arith_selftest_kernel(const float *x, const float *d, float *q, float *r, int *flags, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool s1 = false, s2 = false;
+  q[i] = div_fast(x[i], d[i], s1);
+  r[i] = sqrt_fast(x[i], s2);
+  flags[i] = (s1 ? 1 : 0) | (s2 ? 2 : 0);
+}
+
 template <int C>
 __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
                                                                  const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
@@ -157,7 +262,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
   const int B = g.B, ls = g.longStep, D = ls + 2, OA = 1, R = chain_ring(ls), RM = R - 1;
   const int rows = rec_rows(B, ls);
   // per warp: ringN [R][C][32] (S5 prediction of the lane's block), ringO [R][C][32] (its new output)
-  cf *ringN = (cf *)sm4 + (size_t)warp * 2 * R * C * 32, *ringO = ringN + (size_t)R * C * 32;
+  cf *ringN = (cf *)sm4 + (size_t)warp * 2 * R * C * 32 + lane, *ringO = ringN + (size_t)R * C * 32;
   cf *tile = (cf *)sm4 + (size_t)nW * 2 * R * C * 32;      // [2][C][TL]  carried state, the bins ahead of slot 0's S5 stage
   cf *hand = tile + 2 * (size_t)C * TL;                    // [2][nW][C]  last lane of a warp -> lane 0 of the next
   long long nv = sd.nBlocks - slot0; if (nv > nSlots) nv = nSlots;
@@ -166,12 +271,18 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
   cf *stOut = st.outSpec + (size_t)s * C * B;
   const size_t CB = (size_t)C * B;
   const cf *specRot = T.specRot;
+  const int handSrc = warp > 0 ? warp - 1 : 0;
+  // uninitialised ring entries are read (and discarded) by the select-based arithmetic: give them a defined value
+  for (int i = j; i < nW * 2 * R * C * 32; i += perPass) { cf z; z.re = z.im = 0.f; ((cf *)sm4)[i] = z; }
+  for (int i = j; i < 2 * C * TL + 2 * nW * C; i += perPass) { cf z; z.re = z.im = 0.f; tile[i] = z; }
+  __syncthreads();
 
   for (int p0 = 0; p0 < nValid; p0 += perPass) {
     const int slot = p0 + j;
     const bool active = slot < nValid;
     const int lastJ = min(perPass - 1, nValid - 1 - p0);
     const bool isNew = active && (blocks[sd.blockBase + slot0 + slot].flags & kNew);
+    const bool isLast = (j == lastJ);
     const size_t blk = (size_t)s * nSlots + (active ? slot : p0);
     const float4 *rec4 = (const float4 *)(st.rec + blk * (size_t)rows * NR);
     cf *so = specOut + blk * CB;
@@ -189,73 +300,85 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     };
     request_tile(0); request_tile(1);
     cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
 
     cf last[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) last[c].re = last[c].im = 0.f;
-    // The record row and the spectral rotation of a step are fetched into registers one step ahead: a step takes
-    // longer than a DRAM round trip, so the loads are complete when the next step starts.
-    float4 nxt[NR / 4];
-    cf rotNxt; rotNxt.re = rotNxt.im = 0.f;
-    auto fetch = [&](int t) {   // row = local time + OA: chain part of bin row-ls-1, S5 part of bin row
+    // The record row and the spectral rotation of a step are fetched into registers one step ahead (two register sets,
+    // ping-pong): a step takes longer than a DRAM round trip, so the loads are complete when the next step starts.
+    float4 bufA[NR / 4], bufB[NR / 4];
+    cf rotA, rotB; rotA.re = rotA.im = rotB.re = rotB.im = 0.f;
+#pragma unroll
+    for (int i = 0; i < NR / 4; ++i) bufA[i] = bufB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int t, float4 *buf, cf &rot) {   // row = local time + OA: chain part of bin row-ls-1, S5 part of bin row
       const int r = t - j * D + OA;
       if (active && r >= 1 && r < rows) {
         const float4 *src = rec4 + (size_t)r * (NR / 4);
 #pragma unroll
-        for (int i = 0; i < NR / 4; ++i) nxt[i] = __ldcs(src + i);
-        if (r < B) rotNxt = specRot[r];
+        for (int i = 0; i < NR / 4; ++i) buf[i] = __ldcs(src + i);
+        rot = specRot[r < B ? r : 0];
       }
     };
-    fetch(0);
-
-    for (int t = 0; t <= tEnd; ++t) {
-      float row[NR];
-#pragma unroll
-      for (int i = 0; i < NR / 4; ++i) { row[4 * i] = nxt[i].x; row[4 * i + 1] = nxt[i].y; row[4 * i + 2] = nxt[i].z; row[4 * i + 3] = nxt[i].w; }
-      const cf rot = rotNxt;
-      fetch(t + 1);
+    auto step = [&](int t, const float4 *buf, const cf rot) {
       // slot 0's S5 stage reads bin t+OA this step.  The buffer of tile i-1 was last read one step BEFORE the step with
       // (t+OA) % TL == 0; threads that are ahead may only overwrite it once everybody has passed the barrier after that
-      // read, i.e. from the step with (t+OA) % TL == 1 on.
+      // read, i.e. from the step with (t+OA) % TL == 1 on.  The tile is complete long before it is needed; the wait
+      // only formalises that, one step ahead of its first use.
       const int q0 = t + OA;
       if (q0 > TL && (q0 % TL) == 1) { request_tile(q0 / TL + 1); cp_async_commit(); }
-      cp_async_wait<0>();     // (a tile requested this step is not needed for another TL-1 steps; waiting for it is cheap)
+      if ((q0 % TL) == TL - 1) cp_async_wait<0>();
       __syncthreads();
+      const float *row = (const float *)buf;
       const int tau = t - j * D, q = tau + OA, k = tau - ls;
-      cf up[C];
+      const bool validQ = active && q >= 1 && q < B, validK = active && k >= 0 && k < B;
+      const int qc = q & (2 * TL - 1);                      // position of bin q in the two-tile window (slot 0 only)
+      // S1 + S5 for bin q: previous block's output from the lane above (shuffle), the warp above (hand) or the state
+      cf n5[C];
+      bool slowQ = false;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        up[c].re = __shfl_up_sync(0xffffffffu, last[c].re, 1);
-        up[c].im = __shfl_up_sync(0xffffffffu, last[c].im, 1);
+        cf o;
+        o.re = __shfl_up_sync(0xffffffffu, last[c].re, 1);
+        o.im = __shfl_up_sync(0xffffffffu, last[c].im, 1);
+        const cf oT = tile[((size_t)(qc / TL) * C + c) * TL + (qc % TL)];
+        const cf oH = hand[((size_t)((t & 1) ^ 1) * nW + handSrc) * C + c];
+        if (lane == 0) o = (warp == 0) ? oT : oH;
+        n5[c] = s5_fast(o, isNew, rot, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2], slowQ);
+        if (validQ && slowQ) n5[c] = s5_bin(o, isNew, rot, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2]);
+        if (validQ) ringN[((size_t)(q & RM) * C + c) * 32] = n5[c];
       }
-      if (active && q >= 1 && q < B) {
+      // S6 for bin k
+      const int mc = validK ? __float_as_int(row[8]) : 0;
+      cf oPrev = last[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) if (c == mc) oPrev = last[c];
+      const cf oLong = ringO[((size_t)((k - ls) & RM) * C + mc) * 32];
+      const cf n1 = ringN[((size_t)((k + 1) & RM) * C + mc) * 32];
+      const cf nL = ringN[((size_t)((k + ls) & RM) * C + mc) * 32];
+      cf out[C];
+      bool slowK = false;
+      chain_fast<C>(row, mc, k, B, ls, oPrev, oLong, n1, nL, out, slowK);
+      if (validK && slowK) chain_bin<C>(row, mc, k, B, ls, oPrev, oLong, n1, nL, out);
+      if (validK) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          cf o = up[c];
-          if (lane == 0) o = (warp == 0) ? tile[((size_t)((q / TL) & 1) * C + c) * TL + (q % TL)] : hand[((size_t)((t & 1) ^ 1) * nW + warp - 1) * C + c];
-          ringN[((size_t)(q & RM) * C + c) * 32 + lane] = s5_bin(o, isNew, rot, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2]);
-        }
-      }
-      if (active && k >= 0 && k < B) {
-        const float *ra = row;
-        const int mc = __float_as_int(ra[8]);
-        cf oPrev = last[0];
-#pragma unroll
-        for (int c = 1; c < C; ++c) if (c == mc) oPrev = last[c];
-        cf z; z.re = z.im = 0.f;
-        const cf oLong = (k >= ls) ? ringO[((size_t)((k - ls) & RM) * C + mc) * 32 + lane] : z;
-        const cf n1 = (k < B - 1) ? ringN[((size_t)((k + 1) & RM) * C + mc) * 32 + lane] : z;
-        const cf nL = (k < B - ls) ? ringN[((size_t)((k + ls) & RM) * C + mc) * 32 + lane] : z;
-        cf out[C];
-        chain_bin<C>(ra, mc, k, B, ls, oPrev, oLong, n1, nL, out);
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          ringO[((size_t)(k & RM) * C + c) * 32 + lane] = out[c];
+          ringO[((size_t)(k & RM) * C + c) * 32] = out[c];
           __stcs(reinterpret_cast<float2 *>(so + (size_t)c * B + k), make_float2(out[c].re, out[c].im));
-          if (j == lastJ) stOut[(size_t)c * B + k] = out[c];
+          if (isLast) stOut[(size_t)c * B + k] = out[c];
           if (lane == 31) hand[((size_t)(t & 1) * nW + warp) * C + c] = out[c];
           last[c] = out[c];
         }
+      }
+    };
+    fetch(0, bufA, rotA);
+    for (int t = 0; t <= tEnd; t += 2) {
+      fetch(t + 1, bufB, rotB);
+      step(t, bufA, rotA);
+      if (t + 1 <= tEnd) {
+        fetch(t + 2, bufA, rotA);
+        step(t + 1, bufB, rotB);
       }
     }
     cp_async_wait<0>();
@@ -744,6 +867,16 @@ int bsb_run(bsb_engine *e, void *cudaStream) {
   for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk)
     if (launch_chunk(e, slot0, e->chunk, q, 3, kSynthEmit | kSynthAdd)) return -1;
   return 0;
+}
+
+int bsb_selftest_arith(const float *dX, const float *dD, float *dQ, float *dR, int *dFlags, int n) {
+#ifdef BS_HOSTEMU
+  for (int i = 0; i < n; ++i) { dQ[i] = div_pos(dX[i], dD[i]); dR[i] = sqrt_z(dX[i]); dFlags[i] = 0; }
+  return 0;
+#else
+  arith_selftest_kernel<<<(n + 255) / 256, 256>>>(dX, dD, dQ, dR, dFlags, n);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+#endif
 }
 
 int bsb_block_info(const bsb_engine *e, int s, long long b, long long out[8]) {

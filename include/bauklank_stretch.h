@@ -97,6 +97,11 @@ void bsb_set_profiling(bsb_engine *e, int on);
 int bsb_kernel_count(const bsb_engine *e);
 int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units);
 
+/* Self-test of the branch-free divide / square-root helpers of the chain kernel (device pointers, n elements):
+ * q = x / d, r = sqrt(x) for positive d; flags bit0/bit1 = the operand pair was outside the helpers' safe range (the
+ * kernel recomputes such steps with the plain IEEE operators).  Used by the GPU parity tests only. */
+int bsb_selftest_arith(const float *d_x, const float *d_d, float *d_q, float *d_r, int *d_flags, int n);
+
 #ifdef __cplusplus
 }
 #endif

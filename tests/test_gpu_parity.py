@@ -121,3 +121,29 @@ def test_properties_at_batch_scale(bs):
     for x, y in zip(sub, outs):
         assert float((x[:, 8000:-8000] - y[:, 8000:-8000]).abs().max()) <= 1e-6
     eng.close()
+
+
+def test_branch_free_div_sqrt_are_ieee(bs):
+    """The chain kernel's hot loop divides and takes square roots without the compiler's guarded slow path; inside the
+    helpers' safe range the results must be the correctly rounded IEEE ones (numpy float32), bit for bit."""
+    import torch
+    lib = bs.load_library()
+    n = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ex = torch.randint(-60, 40, (n,), device="cuda", generator=g).float()
+    x = (torch.rand(n, device="cuda", generator=g) + 1.0) * torch.exp2(ex) * torch.where(torch.rand(n, device="cuda", generator=g) < 0.5, -1.0, 1.0)
+    d = (torch.rand(n, device="cuda", generator=g) + 1.0) * torch.exp2(torch.randint(-50, 40, (n,), device="cuda", generator=g).float())
+    x[::1001] = 0.0; x[5::4001] = -0.0
+    x[7::5003] = 1e-44; d[11::6007] = 3e38       # outside the safe range: must be flagged
+    q = torch.empty_like(x); r = torch.empty_like(x); fl = torch.zeros(n, dtype=torch.int32, device="cuda")
+    assert lib.bsb_selftest_arith(x.data_ptr(), d.data_ptr(), q.data_ptr(), r.data_ptr(), fl.data_ptr(), n) == 0
+    xn, dn, qn, rn, fn = (t.cpu().numpy() for t in (x, d, q, r, fl))
+    with np.errstate(all="ignore"):
+        qe = (xn / dn).astype(np.float32)
+        re_ = np.sqrt(xn).astype(np.float32)
+    ok_d = (fn & 1) == 0
+    assert ok_d.mean() > 0.99 and bool((fn[7::5003] & 1).all()) and bool((fn[11::6007] & 1).all())
+    assert (qn.view(np.uint32)[ok_d] == qe.view(np.uint32)[ok_d]).all()
+    pos = (xn >= 0) & ((fn & 2) == 0)
+    assert pos.mean() > 0.45
+    assert (rn.view(np.uint32)[pos] == re_.view(np.uint32)[pos]).all()
