@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) preterms_kernel(DevGeom g, DevTables T, c
   const float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
   const bool last = (m + 1 == sd.nBlocks) || (t + 1 == nSlots);
   const uint32_t rng0 = minstd_jump(st.seeds[s], (uint32_t)(((unsigned long long)rec2.rngSkip * (unsigned long long)(2 * g.B - 2)) % 2147483646ull));
-  float *rr = st.rec + slot * rec_rows(g.B, g.longStep) * nr_floats(g.C);
+  float *rr = st.rec + (size_t)s * ((nSlots + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C) + rec_slot_offset(t, g.B, g.longStep, g.C);
   const float *pE = st.predE[st.parity] + (size_t)s * CB;
   float *pEo = last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr;
   const float *pInE = t > 0 ? inE - CB : nullptr, *pMap = t > 0 ? mp - (size_t)g.B * 2 : nullptr;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
                                                                  const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
                                                                  cf *specOut, StateDev st) {
   extern __shared__ float4 sm4[];
-  constexpr int NR = (9 + 8 * C + 3) & ~3, SO = 9 + 5 * C, TL = kChainTile;
+  constexpr int NR = (9 + 8 * C + 3) & ~3, NRP = (NR + 31) & ~31, SO = 9 + 5 * C, TL = kChainTile;
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = blockDim.x >> 5, j = threadIdx.x;
   const StreamDev sd = streams[s];
   const int B = g.B, ls = g.longStep, D = ls + 2, OA = 1, R = chain_ring(ls), RM = R - 1;
@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     const bool isNew = active && (blocks[sd.blockBase + slot0 + slot].flags & kNew);
     const bool isLast = (j == lastJ);
     const size_t blk = (size_t)s * nSlots + (active ? slot : p0);
-    const float4 *rec4 = (const float4 *)(st.rec + blk * (size_t)rows * NR);
+    // this warp's record group (wavefront-major, see kernels.cuh): diagonal u holds row u - lane*D of lane's block
+    const float4 *grp4 = (const float4 *)(st.rec + ((size_t)s * ((nSlots + 31) / 32) + (p0 >> 5) + warp) * rec_group_floats(B, ls, C)) + (size_t)lane * (NRP / 4);
     cf *so = specOut + blk * CB;
     const int tEnd = (B - 1 + ls) + lastJ * D;
 
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     auto fetch = [&](int t, float4 *buf, cf &rot) {   // row = local time + OA: chain part of bin row-ls-1, S5 part of bin row
       const int r = t - j * D + OA;
       if (active && r >= 1 && r < rows) {
-        const float4 *src = rec4 + (size_t)r * (NR / 4);
+        const float4 *src = grp4 + (size_t)(r + lane * D) * (32 * NRP / 4);
 #pragma unroll
         for (int i = 0; i < NR / 4; ++i) buf[i] = __ldcs(src + i);
         rot = specRot[r < B ? r : 0];
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
       const float *row = (const float *)buf;
       const int tau = t - j * D, q = tau + OA, k = tau - ls;
       const bool validQ = active && q >= 1 && q < B, validK = active && k >= 0 && k < B;
+      if (!__any_sync(0xffffffffu, validQ || validK)) return;   // the whole warp is before its first or past its last bin
       const int qc = q & (2 * TL - 1);                      // position of bin q in the two-tile window (slot 0 only)
       // S1 + S5 for bin q: previous block's output from the lane above (shuffle), the warp above (hand) or the state
       cf n5[C];
@@ -542,7 +544,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
 #ifdef BS_HOSTEMU
   std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)g.M + g.L + preterms_smem_floats(g.C, g.longStep) + 64) / 4 + 1);
   float *sm = (float *)smv.data();
-  const size_t recPerSlot = (size_t)rec_rows(g.B, g.longStep) * nr_floats(g.C);
+  const size_t recPerStream = (size_t)((nSlots + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
   auto mapA = g.C == 2 ? map_stage_a<2> : (g.C == 1 ? map_stage_a<1> : map_stage_a<0>);
   auto mapB = g.C == 2 ? map_stage_b<2> : (g.C == 1 ? map_stage_b<1> : map_stage_b<0>);
   auto termFn = g.C == 2 ? preterms_block<2> : (g.C == 1 ? preterms_block<1> : preterms_block<0>);
@@ -588,7 +590,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
         termFn(e->dg, e->dt, rec, rng0, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput),
                (rec.flags & kNew) ? e->specIn + (slot * 2 + 1) * CB : nullptr, inE, mp, t > 0 ? inE - CB : nullptr,
                t > 0 ? mp - (size_t)g.B * 2 : nullptr, st.predE[st.parity] + (size_t)s * CB,
-               last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr, st.rec + slot * recPerSlot, sm, 0, 1);
+               last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr,
+               st.rec + (size_t)s * recPerStream + rec_slot_offset(t, g.B, g.longStep, g.C), sm, 0, 1);
       }
     }
     account("chain_kernel", nBlk * g.C);
@@ -598,7 +601,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
       if (nv <= 0) continue;
       const size_t slot = (size_t)s * nSlots;
       const BlockRec *bl = e->dBlocks + sd.blockBase + slot0;
-      const float *rr = st.rec + slot * recPerSlot;
+      const float *rr = st.rec + (size_t)s * recPerStream;
       cf *so = e->specOut + slot * CB, *state = st.outSpec + (size_t)s * CB;
       switch (g.C) {
         case 1: chain_host<1>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; case 2: chain_host<2>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
@@ -820,10 +823,11 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
-  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (size_t)rec_rows(g.B, g.longStep) * 4 * nr_floats(g.C));
+  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
   if (chunkBlocks <= 0) {
-    const size_t budget = (size_t)40 << 30;
+    const size_t budget = (size_t)48 << 30;
     chunkBlocks = (int)std::min<size_t>(256, std::max<size_t>(1, budget / perSlot));
+    if (chunkBlocks > 32) chunkBlocks &= ~31;   // whole warps of the chain wavefront
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
   e->chunk = chunkBlocks;
@@ -839,7 +843,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.ring = dalloc<float>((size_t)S * g.C * g.L, own);
   st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
-  st.rec = dalloc<float>(nSlotTot * rec_rows(g.B, g.longStep) * nr_floats(g.C), own);
+  st.rec = dalloc<float>((size_t)S * ((chunkBlocks + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C), own);
   st.seeds = e->dSeeds; st.parity = 0;
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
       !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase ||

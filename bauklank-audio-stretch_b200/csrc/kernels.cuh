@@ -581,11 +581,24 @@ BS_HD void map_stage_b(const DevGeom &g, const BlockRec rec, const BlockRec2 rec
 //   9+5C+3c: S5 twist.re, twist.im, divisor                                   (bin q)
 BS_HHD int nr_floats(int C) { return (9 + 8 * C + 3) & ~3; }
 BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
+// Storage is "wavefront-major": the slots of a chunk are grouped by 32 (one warp of the chain kernel), and inside a
+// group the rows of the 32 blocks are interleaved along diagonals u = row + lane*lag, so that the 32 rows a warp
+// consumes in one step are ONE contiguous run (32 row pitches) instead of 32 cursors in 32 different blocks' records.
+// The row pitch is a whole number of 128-byte lines, so a row is always written and read as full lines.
+BS_HHD int nr_pitch(int C) { return (nr_floats(C) + 31) & ~31; }
+BS_HHD int chain_lag(int longStep) { return longStep + 2; }
+BS_HHD size_t rec_group_floats(int B, int longStep, int C) { return (size_t)(rec_rows(B, longStep) + 31 * chain_lag(longStep)) * 32 * nr_pitch(C); }
+BS_HHD size_t rec_row_stride(int C) { return (size_t)32 * nr_pitch(C); }
+// row 0 of chunk slot `slot` of a stream whose chunk records start at `base`; row r is rec_row_stride floats further per row
+BS_HHD size_t rec_slot_offset(int slot, int B, int longStep, int C) {
+  const int lane = slot & 31, grp = slot >> 5;
+  return (size_t)grp * rec_group_floats(B, longStep, C) + ((size_t)lane * chain_lag(longStep) * 32 + lane) * nr_pitch(C);
+}
 
 // Rows are produced in tiles of kTermTile bins staged in shared memory, so that every record row leaves the SM as part
 // of one contiguous, 16-byte-vectorised burst (a row mixes two bins R0 apart, hence the R0 rows carried tile to tile).
 constexpr int kTermTile = 256;
-BS_HHD size_t preterms_smem_floats(int C, int longStep) { return (size_t)(kTermTile + longStep + 1) * nr_floats(C); }
+BS_HHD size_t preterms_smem_floats(int C, int longStep) { return (size_t)(kTermTile + longStep + 1) * (nr_pitch(C) + 4); }
 
 template <int CT>
 BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec rec, uint32_t rng0, const cf *inp,
@@ -593,8 +606,10 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
                           const float *prevInE, const float *prevMap /* previous block of this stream in the chunk, or nullptr */,
                           const float *prevEState /* Prediction.energy carried from the previous chunk */,
                           float *predEOut /* nullptr unless this is the stream's last block of the chunk */,
-                          float *recRows, float *sm, int tid, int nt) {
-  const int C = CT > 0 ? CT : g.C, B = g.B, NR = nr_floats(C), R0 = g.longStep + 1, SO = 9 + 5 * C, TB = kTermTile;
+                          float *recRows /* row 0 of this block; rows are rec_row_stride apart */, float *sm, int tid, int nt) {
+  const int C = CT > 0 ? CT : g.C, B = g.B, R0 = g.longStep + 1, SO = 9 + 5 * C, TB = kTermTile;
+  const int NRP = nr_pitch(C), NR = NRP + 4;   // NR: row stride in shared memory (pitch + 4 floats against bank conflicts)
+  const size_t rowStride = rec_row_stride(C);
   const bool isNew = rec.flags & kNew;
   const cf *prv = isNew ? inPrev : inp;
   const cf *prvRot = isNew ? T.specRot : nullptr;
@@ -673,9 +688,9 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
     // local rows [0, nOut) are complete: global rows k0 .. k0+nOut-1 (the last tile also flushes the R0 trailing rows)
     const bool lastTile = k0 + TB >= B;
     const int nOut = lastTile ? nb + R0 : TB;
-    {
-      const f4 *src = (const f4 *)sm; f4 *dst = (f4 *)(recRows + (size_t)k0 * NR);
-      for (int i = tid; i < nOut * (NR / 4); i += nt) dst[i] = src[i];
+    for (int i = tid; i < nOut * (NRP / 4); i += nt) {   // whole 128-byte lines, 8 threads per line
+      const int r = i / (NRP / 4), f = i - r * (NRP / 4);
+      ((f4 *)(recRows + (size_t)(k0 + r) * rowStride))[f] = ((const f4 *)(sm + (size_t)r * NR))[f];
     }
     BS_SYNC();
     if (!lastTile)   // chain parts of this tile's last R0 bins belong to the first R0 rows of the next tile
@@ -744,13 +759,13 @@ BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, long l
 // block after the other (the wavefront order of the CUDA kernel computes exactly the same values)
 template <int C>
 inline void chain_host(const DevGeom &g, const DevTables &T, const BlockRec *blocks /* of this stream, at slot0 */, int nValid,
-                       const float *rec /* [slot][rows][NR] */, cf *specOut /* [slot][C][B] */, cf *stateOut /* [C][B] */) {
-  const int B = g.B, ls = g.longStep, NR = nr_floats(C), R0 = ls + 1, SO = 9 + 5 * C;
-  const size_t rows = rec_rows(B, ls);
+                       const float *rec /* the stream's chunk records */, cf *specOut /* [slot][C][B] */, cf *stateOut /* [C][B] */) {
+  const int B = g.B, ls = g.longStep, R0 = ls + 1, SO = 9 + 5 * C;
+  const size_t NR = rec_row_stride(C);
   std::vector<cf> o5((size_t)C * B);
   for (int t = 0; t < nValid; ++t) {
     const bool isNew = blocks[t].flags & kNew;
-    const float *rr = rec + (size_t)t * rows * NR;
+    const float *rr = rec + rec_slot_offset(t, B, ls, C);
     cf *so = specOut + (size_t)t * C * B;
     for (int q = 1; q < B; ++q)
       for (int c = 0; c < C; ++c) {
