@@ -154,6 +154,10 @@ class BatchStretch:
         """Bracket every kernel launch of the following runs with CUDA events (on the run's stream)."""
         self.lib.bsb_set_profiling(self.h, 1 if on else 0)
 
+    def set_overlap(self, on=True):
+        """Chunk pipelining on two internal CUDA streams (default on); off = strictly serial kernels."""
+        self.lib.bsb_set_overlap(self.h, 1 if on else 0)
+
     def kernel_stats(self):
         """{kernel name: dict(ms, launches, units)} of the last run; ``ms`` is 0 unless profiling was on."""
         out = {}

@@ -139,7 +139,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 constexpr int kChainTile = 64;    // bins per staged tile of the carried state
-constexpr int kChainWarps = 8;    // warps per CTA: up to 256 consecutive blocks of one stream in flight
+constexpr int kChainWarps = 4;    // warps per CTA: up to 128 consecutive blocks of one stream in flight
 BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
 BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
   const size_t R = chain_ring(longStep);
@@ -386,16 +386,24 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     cp_async_wait<0>();
     __syncthreads();
   }
-  // carry the input spectrum into the next chunk if its first block reuses it (no new spectrum there)
-  const long long mLast = slot0 + nValid - 1;
-  if (g.incremental || (mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew))) {
-    const BlockRec2 r2 = blocks2[sd.blockBase + mLast];
-    if (r2.lastNew >= slot0) {
-      const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput);
-      cf *dst = st.lastInput + (size_t)s * CB;
-      for (int i = j; i < (int)CB; i += perPass) dst[i] = src[i];
-    }
-  }
+}
+
+// carry: the last analysed spectrum of a stream survives the chunk if the next chunk starts with a block that has no
+// new spectrum of its own (streaming drive with inputInterval 0).  Runs after the term stage, in the same CUDA stream.
+__global__ void __launch_bounds__(256) carry_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
+                                                    long long slot0, int nSlots, const cf *specIn, StateDev st) {
+  const int s = blockIdx.x;
+  const StreamDev sd = streams[s];
+  long long nv = sd.nBlocks - slot0; if (nv > nSlots) nv = nSlots;
+  if (nv <= 0) return;
+  const long long mLast = slot0 + nv - 1;
+  if (!(g.incremental || (mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew)))) return;
+  const BlockRec2 r2 = blocks2[sd.blockBase + mLast];
+  if (r2.lastNew < slot0) return;
+  const size_t CB = (size_t)g.C * g.B;
+  const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput);
+  cf *dst = st.lastInput + (size_t)s * CB;
+  for (int i = threadIdx.x; i < (int)CB; i += blockDim.x) dst[i] = src[i];
 }
 
 // warps per chain CTA: as many as the chunk can use, the kernel was compiled for, and shared memory holds
@@ -463,7 +471,12 @@ struct bsb_engine {
   struct KStat { const char *name; double ms; long long launches, units; };
   std::vector<KStat> kstat;
   bool profiling = false;
+  bool overlap = true;             // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1
+  float *recBuf[2] = {nullptr, nullptr};
 #ifndef BS_HOSTEMU
+  cudaStream_t sFront = nullptr, sBack = nullptr;
+  cudaEvent_t evFront[2] = {nullptr, nullptr}, evBack[2] = {nullptr, nullptr}, evFork = nullptr, evJoin[2] = {nullptr, nullptr};
+  bool backUsed[2] = {false, false};
   struct Span { int k; cudaEvent_t a, b; };
   std::vector<Span> spans; std::vector<cudaEvent_t> evPool; size_t evUsed = 0;
   cudaEvent_t get_event() {
@@ -515,13 +528,16 @@ static void reset_state(bsb_engine *e, stream_t q) {
 }
 
 // one time-chunk: stages bit0 = analysis + map + terms + chain, bit1 = synthesis (with `synthMode`)
-static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, int stages, int synthMode) {
+// Front half (analysis, map, terms, carry) goes to qF, back half (chain, synthesis) to qB; with two different streams
+// the back half of chunk i runs beside the front half of chunk i+1, handing the term records over in buffer `buf`.
+static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF, stream_t qB, int buf, int stages, int synthMode) {
   const Geometry &g = e->g;
   const int S = (int)e->hs.size();
   const size_t CB = (size_t)g.C * g.B;
+  e->st.rec = e->recBuf[buf];
   StateDev &st = e->st;
   const int nt = 256;
-  (void)nt; (void)q;
+  (void)nt; (void)qF; (void)qB;
   // units: analyses (window x channel) actually computed; channel-blocks for the other stages
   long long nNew = 0, nBlk = 0; bool anyAuto = false;
   for (int s = 0; s < S; ++s) {
@@ -536,6 +552,13 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
         nNew += (r.flags & kNew) ? 1 : 0; anyAuto = anyAuto || fm_auto(r);
       }
   }
+  bool needCarry = e->dg.incremental != 0;
+  if ((stages & 1) && !needCarry)
+    for (int s = 0; s < S && !needCarry; ++s) {
+      const long long mNext = slot0 + nSlots;
+      if (mNext < e->hs[s].nBlocks && !(e->hostBlocks[e->hs[s].blockBase + mNext].flags & kNew)) needCarry = true;
+    }
+  (void)needCarry;
   auto account = [&](const char *name, long long units) {
     const int k = e->kidx(name);
     e->kstat[k].launches += 1; e->kstat[k].units += units; e->launches += 1;
@@ -630,6 +653,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
   const int chainWarps = chain_warps(g.C, g.longStep, nSlots);
   const size_t smT = preterms_smem_floats(g.C, g.longStep) * sizeof(float);
   const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
+  const bool twoStreams = (qF != qB);
+  stream_t q = qF;
   auto span = [&](const char *name, long long units, auto &&launch) {
     const int k = account(name, units);
     if (e->profiling) {
@@ -640,6 +665,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
   };
   if (stages & 1) {
     const unsigned nCta = (unsigned)((size_t)S * nSlots);
+    if (twoStreams && e->backUsed[buf]) cudaStreamWaitEvent(qF, e->evBack[buf], 0);   // the chain that read this record buffer is done
     span("analysis_kernel", nNew * 2 * g.C, [&] {
       analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
     span("premap_kernel", nBlk * g.C, [&] {
@@ -651,10 +677,16 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t q, 
     }
     span("preterms_kernel", nBlk * g.C, [&] {
       preterms_kernel<<<nCta, nt, smT, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
+    if (needCarry) span("carry_kernel", 0, [&] {
+      carry_kernel<<<S, 256, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
+    if (twoStreams) { cudaEventRecord(e->evFront[buf], qF); cudaStreamWaitEvent(qB, e->evFront[buf], 0); }
+    q = qB;
     span("chain_kernel", nBlk * g.C, [&] {
       kChainLaunch[g.C - 1](S, chainWarps, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
+    if (twoStreams) { cudaEventRecord(e->evBack[buf], qB); e->backUsed[buf] = true; }
     st.parity ^= 1;
   }
+  q = qB;
   if (stages & 2)
     span("synthesis_kernel", nBlk * g.C, [&] {
       synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, e->specOut, st); });
@@ -683,6 +715,12 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   e->dt.specRot = upload(e, e->T.specRot, e->owned);
   e->dt.wpStart = upload(e, e->T.wpStart, e->owned); e->dt.wpSteady = upload(e, e->T.wpSteady, e->owned);
 #ifndef BS_HOSTEMU
+  cudaStreamCreateWithFlags(&e->sFront, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&e->sBack, cudaStreamNonBlocking);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&e->evFront[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->evBack[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
   const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY) != cudaSuccess ||
@@ -709,6 +747,10 @@ void bsb_destroy(bsb_engine *e) {
   for (void *p : e->owned) dfree(p);
 #ifndef BS_HOSTEMU
   for (auto &ev : e->evPool) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) { if (e->evFront[i]) cudaEventDestroy(e->evFront[i]); if (e->evBack[i]) cudaEventDestroy(e->evBack[i]); if (e->evJoin[i]) cudaEventDestroy(e->evJoin[i]); }
+  if (e->evFork) cudaEventDestroy(e->evFork);
+  if (e->sFront) cudaStreamDestroy(e->sFront);
+  if (e->sBack) cudaStreamDestroy(e->sBack);
 #endif
   delete e;
 }
@@ -823,10 +865,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
-  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
+  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + 2 * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
   if (chunkBlocks <= 0) {
     const size_t budget = (size_t)48 << 30;
-    chunkBlocks = (int)std::min<size_t>(256, std::max<size_t>(1, budget / perSlot));
+    chunkBlocks = (int)std::min<size_t>(128, std::max<size_t>(1, budget / perSlot));
     if (chunkBlocks > 32) chunkBlocks &= ~31;   // whole warps of the chain wavefront
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
@@ -843,7 +885,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.ring = dalloc<float>((size_t)S * g.C * g.L, own);
   st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
-  st.rec = dalloc<float>((size_t)S * ((chunkBlocks + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C), own);
+  const size_t recFloats = (size_t)S * ((chunkBlocks + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
+  e->recBuf[0] = dalloc<float>(recFloats, own);
+  e->recBuf[1] = (e->maxBlocks > chunkBlocks) ? dalloc<float>(recFloats, own) : nullptr;   // second buffer only if there is a next chunk
+  st.rec = e->recBuf[0];
   st.seeds = e->dSeeds; st.parity = 0;
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
       !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase ||
@@ -868,10 +913,28 @@ int bsb_run(bsb_engine *e, void *cudaStream) {
 #ifndef BS_HOSTEMU
   e->spans.clear(); e->evUsed = 0;
 #endif
-  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk)
-    if (launch_chunk(e, slot0, e->chunk, q, 3, kSynthEmit | kSynthAdd)) return -1;
+#ifdef BS_HOSTEMU
+  for (long long slot0 = 0, i = 0; slot0 < e->maxBlocks; slot0 += e->chunk, ++i)
+    if (launch_chunk(e, slot0, e->chunk, q, q, 0, 3, kSynthEmit | kSynthAdd)) return -1;
+#else
+  const bool two = e->overlap && e->recBuf[1] != nullptr && e->maxBlocks > e->chunk;
+  if (two) {   // fork: both internal streams start after everything already queued on the caller's stream
+    cudaEventRecord(e->evFork, q);
+    cudaStreamWaitEvent(e->sFront, e->evFork, 0); cudaStreamWaitEvent(e->sBack, e->evFork, 0);
+    e->backUsed[0] = e->backUsed[1] = false;
+  }
+  long long i = 0;
+  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk, ++i)
+    if (launch_chunk(e, slot0, e->chunk, two ? e->sFront : q, two ? e->sBack : q, two ? (int)(i & 1) : 0, 3, kSynthEmit | kSynthAdd)) return -1;
+  if (two) {   // join
+    cudaEventRecord(e->evJoin[0], e->sFront); cudaEventRecord(e->evJoin[1], e->sBack);
+    cudaStreamWaitEvent(q, e->evJoin[0], 0); cudaStreamWaitEvent(q, e->evJoin[1], 0);
+  }
+#endif
   return 0;
 }
+
+void bsb_set_overlap(bsb_engine *e, int on) { e->overlap = on != 0; }
 
 int bsb_selftest_arith(const float *dX, const float *dD, float *dQ, float *dR, int *dFlags, int n) {
 #ifdef BS_HOSTEMU
@@ -985,7 +1048,7 @@ void compat_launch(Compat *c, long long m, const BlockRec &rec, BlockRec2 rec2, 
     h2d(e->dWindows, win, 2 * sizeof(Window), 0);
     h2d(e->dSeeds, &c->rngState, sizeof(uint32_t), 0);
   }
-  if (launch_chunk(e, m, 1, 0, stages, mode)) bs::die(e->err.c_str());
+  if (launch_chunk(e, m, 1, 0, 0, 0, stages, mode)) bs::die(e->err.c_str());
   if ((stages & 1) && !((rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor) <= 2.0f) && c->g.B >= 2)
     c->rngState = minstd_jump(c->rngState, (uint32_t)(2 * c->g.B - 2));
 }

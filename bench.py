@@ -234,7 +234,11 @@ def main_gpu(args):
     w1 = time.perf_counter()
     ms = a.elapsed_time(b)
     launches = eng.launch_count() * args.steps
-    stats = eng.kernel_stats()                            # of the last run
+    stats = eng.kernel_stats()                            # of the last timed run (kernels of adjacent chunks overlap)
+    eng.set_overlap(False)                                # one more, untimed, strictly serial run: kernels timed in isolation
+    eng.run(); torch.cuda.synchronize()
+    stats_iso = eng.kernel_stats()
+    eng.set_overlap(True)
     eng.set_profiling(False)
     clocks = sampler.stop(w0, w1) if sampler else None
     chk = float(outs_all[::4097].abs().sum().item())      # the result is read (and must be finite)
@@ -287,6 +291,11 @@ def main_gpu(args):
             kernels[k] = {"ms_per_step": round(v["ms"], 3), "launches": v["launches"], "units": v["units"], "bytes_per_unit": bpu,
                           "achieved_gbs": round(gbs, 1) if gbs else None, "frac": round(gbs / peak, 4) if gbs else None}
         d = kernels[dom]
+        iso = {}
+        for k, v in stats_iso.items():
+            bpu = stage_bytes(k, geom)
+            gbs = (bpu * v["units"] / (v["ms"] * 1e-3) / 1e9) if (bpu and v["ms"] > 0) else None
+            iso[k] = {"ms_per_step": round(v["ms"], 3), "achieved_gbs": round(gbs, 1) if gbs else None, "frac": round(gbs / peak, 4) if gbs else None}
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu --set full capture
         if os.path.exists(tp):
@@ -295,6 +304,8 @@ def main_gpu(args):
                     "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_launch": d["bytes_per_unit"] * d["units"] / max(1, d["launches"]) if d["bytes_per_unit"] else None,
                     "avg_launch_ms": d["ms_per_step"] / max(1, d["launches"]), "kernels": kernels,
+                    "kernels_isolated": iso, "note": "kernels = CUDA-event time inside the timed region, where the chain/synthesis kernels of one chunk "
+                    "share the GPU with the analysis/map/term kernels of the next; kernels_isolated = one extra untimed run with the overlap off",
                     "nominal_hbm_gbs": 7700.0}
         cb = None
         if world == 1 and not args.no_cpu_baseline:

@@ -94,6 +94,10 @@ int bsb_block_info(const bsb_engine *e, int stream, long long block, long long o
  * computed; other kernels: channel-blocks) are always counted; device milliseconds only while profiling is on (one
  * CUDA event pair per launch on the run's stream, read back when a stat is queried -- the run is not serialised). */
 void bsb_set_profiling(bsb_engine *e, int on);
+/* chunk pipelining (default on): the chain + synthesis kernels of time chunk i run on a second internal CUDA stream
+ * beside the analysis / map / term kernels of chunk i+1; off = every kernel in order on the caller's stream (used to
+ * time kernels in isolation).  Results are identical either way. */
+void bsb_set_overlap(bsb_engine *e, int on);
 int bsb_kernel_count(const bsb_engine *e);
 int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units);
 

@@ -147,3 +147,18 @@ def test_branch_free_div_sqrt_are_ieee(bs):
     pos = (xn >= 0) & ((fn & 2) == 0)
     assert pos.mean() > 0.45
     assert (rn.view(np.uint32)[pos] == re_.view(np.uint32)[pos]).all()
+
+
+def test_overlap_switch_does_not_change_results(bs, golden):
+    """Chunk pipelining on two CUDA streams vs strictly serial kernels: identical output."""
+    import torch
+    case = cases.CASES["KA6"]
+    clip = torch.from_numpy(cases.make_clip(case["clip"])).cuda()
+    for on in (True, False):
+        eng = cases.make_batch(bs, case, 2)
+        outs = eng.plan([clip], [cases.batch_drive(bs, case, clip.shape[1])], chunk_blocks=32)
+        eng.set_overlap(on)
+        eng.run(); eng.run()
+        torch.cuda.synchronize()
+        assert_matches_golden("KA6", outs[0].cpu().numpy(), golden)
+        eng.close()
