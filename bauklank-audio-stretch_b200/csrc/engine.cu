@@ -432,14 +432,32 @@ static cudaError_t chain_set_smem(int C, size_t smem) {
   }
 }
 
-__global__ void __launch_bounds__(256) synthesis_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
-                                                        int mode, const cf *specOut, StateDev st) {
+__global__ void __launch_bounds__(256) isynth_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
+                                                     const cf *specOut, StateDev st) {
   extern __shared__ float sm[];
-  const int s = blockIdx.x / g.C, c = blockIdx.x % g.C;
+  int idx = blockIdx.x;
+  const int c = idx % g.C; idx /= g.C;
+  const int slot = idx % nSlots; const int s = idx / nSlots;
   const StreamDev sd = streams[s];
-  float *ring = sm + 4 * (size_t)g.M;
-  synth_stream(g, T, sd, c, slot0, nSlots, mode, specOut + (size_t)s * nSlots * g.C * g.B, st.ring + ((size_t)s * g.C + c) * g.L, sm,
-               ring, threadIdx.x, blockDim.x);
+  if (slot0 + slot >= sd.nBlocks) return;
+  const size_t blk = (size_t)s * nSlots + slot;
+  synth_frame(g, T, specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, sm, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) ola_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots, int mode,
+                                                  StateDev st) {
+  const int s = blockIdx.y / g.C, c = blockIdx.y % g.C;
+  const StreamDev sd = streams[s];
+  long long nvl = sd.nBlocks - slot0; if (nvl > nSlots) nvl = nSlots;
+  if (nvl <= 0) return;
+  const int nv = (int)nvl;
+  const long long ringBase = ((mode & kSynthEmit) ? slot0 : slot0 + g.split) * (long long)g.H;
+  const long long nE1 = (mode & kSynthEmit) ? (slot0 + nv) * (long long)g.H : ringBase;
+  const long long n = ringBase + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nE1 + g.L) return;
+  const size_t rc = ((size_t)s * g.C + c) * g.L;
+  ola_sample(g, T, sd, c, n, ringBase, nE1, slot0, nv, (mode & kSynthAdd) != 0, st.frames + (size_t)s * nSlots * g.C * g.L,
+             st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
 }
 #endif
 
@@ -484,6 +502,11 @@ struct bsb_engine {
     return evPool[evUsed++];
   }
 #endif
+  long long maxBlocksOr1(long long slot0) const {   // blocks of the longest stream from slot0 on (at least 1)
+    long long n = 1;
+    for (const StreamDev &d : hs) n = std::max<long long>(n, d.nBlocks - slot0);
+    return n;
+  }
   int kidx(const char *name) {
     for (size_t i = 0; i < kstat.size(); ++i) if (!std::strcmp(kstat[i].name, name)) return (int)i;
     kstat.push_back(KStat{name, 0.0, 0, 0}); return (int)kstat.size() - 1;
@@ -523,7 +546,8 @@ static void reset_state(bsb_engine *e, stream_t q) {
   // reset(): zero phase state, rings, maps (the RNG is re-derived from the per-stream seed and the block table)
   dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE[0], S * CB * sizeof(float), q); dzero(st.predE[1], S * CB * sizeof(float), q);
   dzero(st.lastInput, S * CB * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
-  dzero(st.ring, (size_t)S * g.C * g.L * sizeof(float), q);
+  dzero(st.ring[0], (size_t)S * g.C * g.L * sizeof(float), q); dzero(st.ring[1], (size_t)S * g.C * g.L * sizeof(float), q);
+  st.ringPar = 0;
   st.parity = 0;
 }
 
@@ -642,14 +666,33 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
     st.parity ^= 1;
   }
   if (stages & 2) {
-    account("synthesis_kernel", nBlk * g.C);
-    for (int s = 0; s < S; ++s)
-      for (int c = 0; c < g.C; ++c)
-        synth_stream(e->dg, e->dt, e->hs[s], c, slot0, nSlots, synthMode, e->specOut + (size_t)s * nSlots * CB,
-                     st.ring + ((size_t)s * g.C + c) * g.L, sm, sm + 4 * (size_t)g.M, 0, 1);
+    if (synthMode & kSynthAdd) {
+      account("isynth_kernel", nBlk * g.C);
+      for (int s = 0; s < S; ++s)
+        for (int t = 0; t < nSlots && slot0 + t < e->hs[s].nBlocks; ++t)
+          for (int c = 0; c < g.C; ++c) {
+            const size_t blk = (size_t)s * nSlots + t;
+            synth_frame(e->dg, e->dt, e->specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, sm, 0, 1);
+          }
+    }
+    account("ola_kernel", nBlk * g.C);
+    for (int s = 0; s < S; ++s) {
+      const StreamDev &sd = e->hs[s];
+      long long nvl = std::min<long long>(nSlots, sd.nBlocks - slot0);
+      if (nvl <= 0) continue;
+      const long long ringBase = ((synthMode & kSynthEmit) ? slot0 : slot0 + g.split) * (long long)g.H;
+      const long long nE1 = (synthMode & kSynthEmit) ? (slot0 + nvl) * (long long)g.H : ringBase;
+      for (int c = 0; c < g.C; ++c) {
+        const size_t rc = ((size_t)s * g.C + c) * g.L;
+        for (long long n = ringBase; n < nE1 + g.L; ++n)
+          ola_sample(e->dg, e->dt, sd, c, n, ringBase, nE1, slot0, (int)nvl, (synthMode & kSynthAdd) != 0,
+                     st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+      }
+    }
+    st.ringPar ^= 1;
   }
 #else
-  const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
+  const size_t smA = 4 * (size_t)g.M * sizeof(float);
   const int chainWarps = chain_warps(g.C, g.longStep, nSlots);
   const size_t smT = preterms_smem_floats(g.C, g.longStep) * sizeof(float);
   const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
@@ -687,9 +730,15 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
     st.parity ^= 1;
   }
   q = qB;
-  if (stages & 2)
-    span("synthesis_kernel", nBlk * g.C, [&] {
-      synthesis_kernel<<<S * g.C, nt, smY, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, e->specOut, st); });
+  if (stages & 2) {
+    if (synthMode & kSynthAdd)
+      span("isynth_kernel", nBlk * g.C, [&] {
+        isynth_kernel<<<(unsigned)((size_t)S * nSlots * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, e->specOut, st); });
+    const long long span_n = (long long)std::min<long long>(nSlots, e->maxBlocksOr1(slot0)) * g.H + g.L;
+    span("ola_kernel", nBlk * g.C, [&] {
+      ola_kernel<<<dim3((unsigned)((span_n + 255) / 256), (unsigned)(S * g.C)), 256, 0, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, st); });
+    st.ringPar ^= 1;
+  }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
 #endif
@@ -721,9 +770,9 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
     cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
-  const size_t smA = 4 * (size_t)g.M * sizeof(float), smY = (4 * (size_t)g.M + g.L) * sizeof(float);
+  const size_t smA = 4 * (size_t)g.M * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
-      cudaFuncSetAttribute(synthesis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smY) != cudaSuccess ||
+      cudaFuncSetAttribute(isynth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(preterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
       chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep, chain_warps(g.C, g.longStep, 1 << 20))) != cudaSuccess ||
       cudaFuncSetAttribute(premap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
@@ -865,7 +914,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
-  const size_t perSlot = (size_t)S * (CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + 2 * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
+  const size_t perSlot = (size_t)S * ((size_t)g.C * g.L * 4 + CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + 2 * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
   if (chunkBlocks <= 0) {
     const size_t budget = (size_t)48 << 30;
     chunkBlocks = (int)std::min<size_t>(128, std::max<size_t>(1, budget / perSlot));
@@ -882,7 +931,8 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   const size_t nSlotTot = (size_t)S * chunkBlocks;
   st.outSpec = dalloc<cf>(S * CB, own); st.predE[0] = dalloc<float>(S * CB, own); st.predE[1] = dalloc<float>(S * CB, own);
   st.lastInput = dalloc<cf>(S * CB, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
-  st.ring = dalloc<float>((size_t)S * g.C * g.L, own);
+  st.ring[0] = dalloc<float>((size_t)S * g.C * g.L, own); st.ring[1] = dalloc<float>((size_t)S * g.C * g.L, own);
+  st.frames = dalloc<float>(nSlotTot * g.C * g.L, own); st.ringPar = 0;
   st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
   const size_t recFloats = (size_t)S * ((chunkBlocks + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
@@ -891,7 +941,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.rec = e->recBuf[0];
   st.seeds = e->dSeeds; st.parity = 0;
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
-      !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase ||
+      !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring[0] || !st.ring[1] || !st.frames || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase ||
       !st.rec) {
     free_batch(e);
     return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);

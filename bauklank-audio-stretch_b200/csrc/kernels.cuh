@@ -4,8 +4,8 @@
 //   premap_kernel     (stream, block)  energies, smoothing, peaks, frequency map, formant envelope
 //   preterms_kernel   (stream, block)  per-bin coefficient records of the phase prediction (everything state-free)
 //   chain_kernel      one warp per stream: the bin-to-bin / block-to-block phase recurrence as a 32-block wavefront
-//   synthesis_kernel  one persistent CTA per (stream, channel): inverse FFT -> window -> overlap-add ring in shared
-//                     memory -> normalised output samples
+//   isynth_kernel     (stream, block, channel)  inverse FFT -> synthesis window -> frame in HBM
+//   ola_kernel        (stream, channel, output sample)  overlap-add of the frames in block order -> normalised output
 //
 // All arithmetic is f32 in the reference's operation order (compile with -fmad=false; IEEE div/sqrt), see the
 // citations on each routine (W#n = wasm function n of the blob at app/SignalsmithStretch.mjs:265).
@@ -63,7 +63,9 @@ struct StateDev {
   float *predE[2];    // [S][C][B] x2  Prediction.energy of a chunk's last block (read [parity], write [parity^1])
   cf *lastInput;      // [S][C][B]     last analysed spectrum (only used by blocks without a new spectrum)
   float *freqEst;     // [S][2]        freqEstimateWeighted, freqEstimateWeight
-  float *ring;        // [S][C][L]     overlap-add ring between chunks
+  float *ring[2];     // [S][C][L] x2  overlap-add partial sums carried between chunks (read [ringPar], write [ringPar^1])
+  float *frames;      // [S][T][C][L]  windowed synthesis frames of the chunk
+  int ringPar;
   // per chunk slot
   float *inEnergy;    // [S][T][C][B]
   float *map;         // [S][T][B][2]  {inputBin, freqGrad}
@@ -221,9 +223,10 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
   BS_SYNC();
 }
 
-// inverse modified real FFT of one channel's output spectrum + windowed overlap-add into `ring` (smem, [L]) at `pos`
-// (W#48 9986-10932).  smem: 4*M floats.
-BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float *ring, int pos, float *sm, int tid, int nt) {
+// inverse modified real FFT of one channel's output spectrum, synthesis window applied: the block's contribution to
+// the output, frame[i] for output sample frameStart + i (W#48 9986-10932; the first half of the window carries the
+// half-bin shift's sign flip, `ring -= t*w` there = adding -(t*w)).  smem: 4*M floats.
+BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float *frame, float *sm, int tid, int nt) {
   const int M = g.M, N = g.N, L = g.L, off = g.off;
   float *ar = sm, *ai = sm + M, *br = sm + 2 * M, *bi = sm + 3 * M;
   const int half = M >> 1;
@@ -248,8 +251,8 @@ BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float 
     float tv[2] = {t0, t1};
     for (int e = 0; e < 2; ++e) {
       int n = 2 * j + e;
-      if (n < L - off) { int i = n + off; int p = pos + i; if (p >= L) p -= L; ring[p] = ring[p] + (tv[e] * T.win[i]); }
-      else if (n >= N - off) { int i = n - (N - off); int p = pos + i; if (p >= L) p -= L; ring[p] = ring[p] - (tv[e] * T.win[i]); }
+      if (n < L - off) { int i = n + off; frame[i] = tv[e] * T.win[i]; }
+      else if (n >= N - off) { int i = n - (N - off); frame[i] = -(tv[e] * T.win[i]); }
     }
   }
   BS_SYNC();
@@ -259,32 +262,27 @@ BS_HD float wp_at(const DevGeom &g, const DevTables &T, long long n) {
   return n < g.wpStartLen ? T.wpStart[n] : T.wpSteady[(int)((n - g.wpStartLen) % g.H)];
 }
 
-// one chunk of one (stream, channel): ring persists in global memory between chunks
-BS_HD void synth_stream(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, long long slot0, int nSlots, int mode,
-                        const cf *specOut /* this stream's [slot][C][B] */, float *ringG, float *sm, float *ring, int tid, int nt) {
+// Overlap-add of one output sample (W#48 10700-10932 + the per-sample read 7990-8080): the partial sum carried from
+// earlier chunks, plus this chunk's frames that cover sample n, added in block order exactly like the reference's ring
+// (whose slot starts from 0.0 each time it is re-used), then either emitted (divided by the window-product sum) or
+// kept as the partial sum for the next chunk.
+//   ringBase: first sample the carried ring describes; emit range [ringBase, nE1); frames start at (m + split) * H.
+BS_HD void ola_sample(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, long long n, long long ringBase, long long nE1,
+                      long long slot0, int nv, bool addFrames, const float *frames /* [slot][C][L] of this stream */,
+                      const float *ringOld, float *ringNew /* [L] of this (stream, channel) */) {
   const int L = g.L, H = g.H;
-  for (int i = tid; i < L; i += nt) ring[i] = ringG[i];
-  BS_SYNC();
-  for (int t = 0; t < nSlots; ++t) {
-    long long m = slot0 + t;
-    if (m >= sd.nBlocks) break;
-    int pos = (int)((m * H) % L);
-    const cf *X = specOut + ((size_t)t * g.C + c) * g.B;
-    if (!g.split && (mode & kSynthAdd)) synth_frame(g, T, X, ring, pos, sm, tid, nt);
-    if (mode & kSynthEmit) {
-      long long n0 = m * H;
-      float *outc = sd.out + (size_t)c * sd.outStride - sd.outBase;
-      for (int j = tid; j < H; j += nt) {
-        long long n = n0 + j;
-        int p = pos + j; if (p >= L) p -= L;
-        if (n < sd.nOut) outc[n] = ring[p] / wp_at(g, T, n);
-        ring[p] = 0.f;
-      }
-      BS_SYNC();
+  float acc = (n < ringBase + L) ? ringOld[(int)(n % L)] : 0.f;
+  if (addFrames) {
+    long long mLo = (n - L >= 0 ? (n - L) / H + 1 : 0) - g.split, mHi = n / H - g.split;
+    if (mLo < slot0) mLo = slot0;
+    if (mHi > slot0 + nv - 1) mHi = slot0 + nv - 1;
+    for (long long m = mLo; m <= mHi; ++m) {
+      const long long i = n - (m + g.split) * H;
+      acc = acc + frames[((size_t)(m - slot0) * g.C + c) * L + i];
     }
-    if (g.split && (mode & kSynthAdd)) { int p2 = pos + H; if (p2 >= L) p2 -= L; synth_frame(g, T, X, ring, p2, sm, tid, nt); }
   }
-  for (int i = tid; i < L; i += nt) ringG[i] = ring[i];
+  if (n < nE1) { if (n < sd.nOut) sd.out[(size_t)c * sd.outStride + (n - sd.outBase)] = acc / wp_at(g, T, n); }
+  else ringNew[(int)(n % L)] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -163,11 +163,12 @@ def stage_bytes(name, g):
     """Algorithmic HBM bytes per unit of each kernel (SURVEY.md section 8d stage model)."""
     L, H, B = g["L"], g["H"], g["B"]
     table = {
-        "analysis_kernel": 4 * L + 8 * B,          # per (window, channel): L samples in, B complex bins out
-        "premap_kernel": 8 * B + 4 * B + 4 * B,    # per channel-block: spectrum in, input energy out, map (8B per block, 2 channels) out
-        "preterms_kernel": 16 * B + 8 * B + 64 * B,  # per channel-block: cur+prev spectra, energy+map in, 32-float record / 2 channels out
-        "chain_kernel": 64 * B + 8 * B,            # per channel-block: record in, output spectrum out (state stays on chip within a pass)
-        "synthesis_kernel": 8 * B + 8 * L + 4 * H, # per channel-block: spectrum in, OLA ring read+write, H samples out
+        "analysis_kernel": 4 * L + 8 * B,             # per (window, channel): L samples in, B complex bins out
+        "premap_kernel": 8 * B + 4 * B + 4 * B,       # per channel-block: spectrum in, input energy out, map (8B per block, 2 channels) out
+        "preterms_kernel": 16 * B + 8 * B + 64 * B,   # per channel-block: cur+prev spectra, energy+map in, 128-byte record row / 2 channels out
+        "chain_kernel": 64 * B + 8 * B,               # per channel-block: record rows in, output spectrum out (phase state stays on chip)
+        "isynth_kernel": 8 * B + 4 * L,               # per channel-block: output spectrum in, windowed frame out
+        "ola_kernel": 4 * L + 4 * H,                  # per channel-block: frame in, H output samples out
     }
     return table.get(name)
 
