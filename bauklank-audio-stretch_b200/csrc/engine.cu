@@ -57,35 +57,70 @@ __global__ void __launch_bounds__(256) analysis_kernel(DevGeom g, DevTables T, c
   analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x);
 }
 
-// premap: the map stage for every (stream, block) of the chunk in parallel.  phase 0 = everything except the formant
-// envelope of auto-detect blocks (those wait for freqest_kernel); phase 1 = exactly those.
-__global__ void __launch_bounds__(128) premap_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                     const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, StateDev st,
-                                                     int phase) {
-  extern __shared__ float4 sm4[];
-  float *sm = (float *)sm4;
+// ---- map stage kernels (see kernels.cuh "map stage")
+struct SlotCtx { StreamDev sd; BlockRec rec; BlockRec2 rec2; size_t slot; bool valid; };
+__device__ __forceinline__ SlotCtx slot_ctx(const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2, long long slot0,
+                                            int nSlots, int s, int t) {
+  SlotCtx c; c.sd = streams[s]; c.slot = (size_t)s * nSlots + t;
+  c.valid = slot0 + t < c.sd.nBlocks;
+  if (c.valid) { c.rec = blocks[c.sd.blockBase + slot0 + t]; c.rec2 = blocks2[c.sd.blockBase + slot0 + t]; }
+  return c;
+}
+
+__global__ void __launch_bounds__(256) map_energy_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
+                                                         long long slot0, int nSlots, const cf *specIn, StateDev st) {
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
-  const StreamDev sd = streams[s];
-  const long long m = slot0 + t;
-  if (m >= sd.nBlocks) return;
-  const BlockRec rec = blocks[sd.blockBase + m];
-  const bool autoBase = fm_auto(rec);
-  if (phase == 1 && !autoBase) return;
-  const BlockRec2 rec2 = blocks2[sd.blockBase + m];
-  const size_t CB = (size_t)g.C * g.B, slot = (size_t)s * nSlots + t;
-  const cf *inp = block_input(g, rec2, s, slot0, nSlots, specIn, st.lastInput);
-  float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (phase == 0) {
-    if (g.C == 2) map_stage_a<2>(g, T, rec, inp, inE, mp, st.fmAuto + 2 * slot, sm, tid, nt);
-    else if (g.C == 1) map_stage_a<1>(g, T, rec, inp, inE, mp, st.fmAuto + 2 * slot, sm, tid, nt);
-    else map_stage_a<0>(g, T, rec, inp, inE, mp, st.fmAuto + 2 * slot, sm, tid, nt);
-    if (autoBase) return;
+  const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
+  if (!c.valid) return;
+  const size_t CB = (size_t)g.C * g.B;
+  const cf *inp = block_input(g, c.rec2, s, slot0, nSlots, specIn, st.lastInput);
+  float *inE = st.inEnergy + c.slot * CB, *en = st.energy + c.slot * g.B, *sm = st.smoothed + c.slot * g.B;
+  float *fm = st.fm + c.slot * fm_pitch(g.B), *mp = st.map + c.slot * g.B * 2;
+  if (g.C == 2) map_energy<2>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
+  else if (g.C == 1) map_energy<1>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
+  else map_energy<0>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
+}
+
+// one thread per (stream, block): which = 0 band-energy smoothing (mapped blocks), 1 formant-envelope smoothing
+__global__ void __launch_bounds__(64) map_smooth_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
+                                                        long long slot0, int nSlots, int S, StateDev st, int which) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * nSlots) return;
+  const int t = i % nSlots, s = i / nSlots;
+  const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
+  if (!c.valid) return;
+  if (which == 0) {
+    if (!(c.rec.flags & kMapped)) return;
+    const float fN = (float)(uint32_t)g.N, fH = (float)(uint32_t)g.H, ratio = fN / fH;
+    const float slew = 1.0f / ((ratio * 0.5f) + 1.0f);
+    float *v = st.smoothed + c.slot * g.B;
+    float carry = smooth_pass_g(v, g.B, slew, 0.f);   // smoothEnergy steps 1,2: the carry runs through both
+    smooth_pass_g(v, g.B, slew, carry);
+  } else {
+    if (!(c.rec.flags & kFormants)) return;
+    fm_smooth(g, c.rec, fm_auto(c.rec) ? st.fmBase[c.slot] : 0.f, st.fm + c.slot * fm_pitch(g.B));
   }
-  const float base = autoBase ? st.fmBase[slot] : 0.f;
-  if (g.C == 2) map_stage_b<2>(g, rec, rec2, base, inE, sm, tid, nt);
-  else if (g.C == 1) map_stage_b<1>(g, rec, rec2, base, inE, sm, tid, nt);
-  else map_stage_b<0>(g, rec, rec2, base, inE, sm, tid, nt);
+}
+
+__global__ void __launch_bounds__(128) map_peaks_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
+                                                        long long slot0, int nSlots, StateDev st) {
+  extern __shared__ float4 sm4[];
+  const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
+  const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
+  if (!c.valid || !((c.rec.flags & kMapped) || fm_auto(c.rec))) return;
+  map_peaks(g, c.rec, st.energy + c.slot * g.B, st.smoothed + c.slot * g.B, st.map + c.slot * g.B * 2, st.fmAuto + 2 * c.slot, (float *)sm4,
+            threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) map_fmapply_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
+                                                          long long slot0, int nSlots, StateDev st) {
+  const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
+  const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
+  if (!c.valid || !(c.rec.flags & kFormants)) return;
+  float *inE = st.inEnergy + c.slot * (size_t)g.C * g.B; const float *fm = st.fm + c.slot * fm_pitch(g.B);
+  if (g.C == 2) fm_apply<2>(g, c.rec, c.rec2, fm, inE, threadIdx.x, blockDim.x);
+  else if (g.C == 1) fm_apply<1>(g, c.rec, c.rec2, fm, inE, threadIdx.x, blockDim.x);
+  else fm_apply<0>(g, c.rec, c.rec2, fm, inE, threadIdx.x, blockDim.x);
 }
 
 // the formant base estimate is a two-tap leaky average over the blocks of a stream: one thread per stream
@@ -139,7 +174,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 constexpr int kChainTile = 64;    // bins per staged tile of the carried state
-constexpr int kChainWarps = 4;    // warps per CTA: up to 128 consecutive blocks of one stream in flight
+constexpr int kChainWarps = 8;    // warps per CTA: up to 256 consecutive blocks of one stream in flight
 BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
 BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
   const size_t R = chain_ring(longStep);
@@ -450,14 +485,11 @@ __global__ void __launch_bounds__(256) ola_kernel(DevGeom g, DevTables T, const 
   const StreamDev sd = streams[s];
   long long nvl = sd.nBlocks - slot0; if (nvl > nSlots) nvl = nSlots;
   if (nvl <= 0) return;
-  const int nv = (int)nvl;
-  const long long ringBase = ((mode & kSynthEmit) ? slot0 : slot0 + g.split) * (long long)g.H;
-  const long long nE1 = (mode & kSynthEmit) ? (slot0 + nv) * (long long)g.H : ringBase;
-  const long long n = ringBase + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nE1 + g.L) return;
+  const OlaGeom o = ola_geom(g, slot0, (int)nvl, mode);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= o.xE1 + g.L) return;
   const size_t rc = ((size_t)s * g.C + c) * g.L;
-  ola_sample(g, T, sd, c, n, ringBase, nE1, slot0, nv, (mode & kSynthAdd) != 0, st.frames + (size_t)s * nSlots * g.C * g.L,
-             st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+  ola_sample(g, T, sd, c, x, o, st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
 }
 #endif
 
@@ -489,7 +521,8 @@ struct bsb_engine {
   struct KStat { const char *name; double ms; long long launches, units; };
   std::vector<KStat> kstat;
   bool profiling = false;
-  bool overlap = true;             // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1
+  bool overlap = false;            // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1 (two CUDA
+                                   // streams); measured to gain nothing on B200 -- every kernel is occupancy bound -- so off
   float *recBuf[2] = {nullptr, nullptr};
 #ifndef BS_HOSTEMU
   cudaStream_t sFront = nullptr, sBack = nullptr;
@@ -563,17 +596,21 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
   const int nt = 256;
   (void)nt; (void)qF; (void)qB;
   // units: analyses (window x channel) actually computed; channel-blocks for the other stages
-  long long nNew = 0, nBlk = 0; bool anyAuto = false;
+  long long nNew = 0, nBlk = 0; bool anyAuto = false, anyMapped = false, anyFormants = false;
   for (int s = 0; s < S; ++s) {
     const long long n = std::min<long long>(nSlots, e->hs[s].nBlocks - slot0);
     if (n > 0) nBlk += n;
   }
   if (stages & 1) {
-    if (e->dg.incremental) { nNew = (e->hostBlocks[0].flags & kNew) ? 1 : 0; anyAuto = fm_auto(e->hostBlocks[0]); }
+    if (e->dg.incremental) {
+      const BlockRec &r = e->hostBlocks[0];
+      nNew = (r.flags & kNew) ? 1 : 0; anyAuto = fm_auto(r); anyMapped = r.flags & kMapped; anyFormants = r.flags & kFormants;
+    }
     else for (int s = 0; s < S; ++s)
       for (long long m = slot0; m < slot0 + nSlots && m < e->hs[s].nBlocks; ++m) {
         const BlockRec &r = e->hostBlocks[e->hs[s].blockBase + m];
         nNew += (r.flags & kNew) ? 1 : 0; anyAuto = anyAuto || fm_auto(r);
+        anyMapped = anyMapped || (r.flags & kMapped); anyFormants = anyFormants || (r.flags & kFormants);
       }
   }
   bool needCarry = e->dg.incremental != 0;
@@ -592,8 +629,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
   std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)g.M + g.L + preterms_smem_floats(g.C, g.longStep) + 64) / 4 + 1);
   float *sm = (float *)smv.data();
   const size_t recPerStream = (size_t)((nSlots + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
-  auto mapA = g.C == 2 ? map_stage_a<2> : (g.C == 1 ? map_stage_a<1> : map_stage_a<0>);
-  auto mapB = g.C == 2 ? map_stage_b<2> : (g.C == 1 ? map_stage_b<1> : map_stage_b<0>);
+  auto mapE = g.C == 2 ? map_energy<2> : (g.C == 1 ? map_energy<1> : map_energy<0>);
+  auto fmA = g.C == 2 ? fm_apply<2> : (g.C == 1 ? fm_apply<1> : fm_apply<0>);
   auto termFn = g.C == 2 ? preterms_block<2> : (g.C == 1 ? preterms_block<1> : preterms_block<0>);
   if (stages & 1) {
     account("analysis_kernel", nNew * 2 * g.C);
@@ -608,20 +645,29 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
                            e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1);
       }
     }
-    account("premap_kernel", nBlk * g.C);
-    if (anyAuto) { account("freqest_kernel", nBlk); account("premap_kernel", 0); }
-    for (int s = 0; s < S; ++s) {   // premap (phase 0), freqest, premap (phase 1): per stream in block order
+    account("map_energy_kernel", nBlk * g.C);
+    if (anyMapped) account("map_smooth_kernel", nBlk);
+    if (anyMapped || anyAuto) account("map_peaks_kernel", nBlk);
+    if (anyAuto) account("freqest_kernel", nBlk);
+    if (anyFormants) { account("map_smooth_kernel", 0); account("map_fmapply_kernel", nBlk * g.C); }
+    for (int s = 0; s < S; ++s) {   // the map-stage kernels, per stream in block order
       const StreamDev &sd = e->hs[s];
       for (int t = 0; t < nSlots && slot0 + t < sd.nBlocks; ++t) {
         long long m = slot0 + t; const size_t slot = (size_t)s * nSlots + t;
         const BlockRec rec = e->dBlocks[sd.blockBase + m];
         const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
-        float *inE = st.inEnergy + slot * CB;
-        mapA(e->dg, e->dt, rec, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput), inE, st.map + slot * g.B * 2,
-             st.fmAuto + 2 * slot, sm, 0, 1);
+        float *inE = st.inEnergy + slot * CB, *en = st.energy + slot * g.B, *smo = st.smoothed + slot * g.B, *fm = st.fm + slot * fm_pitch(g.B);
+        float *mp = st.map + slot * g.B * 2;
+        mapE(e->dg, rec, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput), inE, en, smo, fm, mp, 0, 1);
+        if (rec.flags & kMapped) {
+          const float fN = (float)(uint32_t)g.N, fH = (float)(uint32_t)g.H, ratio = fN / fH, slew = 1.0f / ((ratio * 0.5f) + 1.0f);
+          float carry = smooth_pass_g(smo, g.B, slew, 0.f);
+          smooth_pass_g(smo, g.B, slew, carry);
+        }
+        if ((rec.flags & kMapped) || fm_auto(rec)) map_peaks(e->dg, rec, en, smo, mp, st.fmAuto + 2 * slot, sm, 0, 1);
         float base = 0.f;
         if (fm_auto(rec)) base = st.fmBase[slot] = freqest_step(st.freqEst + 2 * s, st.fmAuto + 2 * slot);
-        mapB(e->dg, rec, rec2, base, inE, sm, 0, 1);
+        if (rec.flags & kFormants) { fm_smooth(e->dg, rec, base, fm); fmA(e->dg, rec, rec2, fm, inE, 0, 1); }
       }
     }
     account("preterms_kernel", nBlk * g.C);
@@ -680,13 +726,11 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
       const StreamDev &sd = e->hs[s];
       long long nvl = std::min<long long>(nSlots, sd.nBlocks - slot0);
       if (nvl <= 0) continue;
-      const long long ringBase = ((synthMode & kSynthEmit) ? slot0 : slot0 + g.split) * (long long)g.H;
-      const long long nE1 = (synthMode & kSynthEmit) ? (slot0 + nvl) * (long long)g.H : ringBase;
+      const OlaGeom o = ola_geom(e->dg, slot0, (int)nvl, synthMode);
       for (int c = 0; c < g.C; ++c) {
         const size_t rc = ((size_t)s * g.C + c) * g.L;
-        for (long long n = ringBase; n < nE1 + g.L; ++n)
-          ola_sample(e->dg, e->dt, sd, c, n, ringBase, nE1, slot0, (int)nvl, (synthMode & kSynthAdd) != 0,
-                     st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+        for (int x = 0; x < o.xE1 + g.L; ++x)
+          ola_sample(e->dg, e->dt, sd, c, x, o, st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
       }
     }
     st.ringPar ^= 1;
@@ -711,12 +755,19 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
     if (twoStreams && e->backUsed[buf]) cudaStreamWaitEvent(qF, e->evBack[buf], 0);   // the chain that read this record buffer is done
     span("analysis_kernel", nNew * 2 * g.C, [&] {
       analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
-    span("premap_kernel", nBlk * g.C, [&] {
-      premap_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st, 0); });
-    if (anyAuto) {
-      span("freqest_kernel", nBlk, [&] { freqest_kernel<<<(S + 63) / 64, 64, 0, q>>>(S, e->dStreams, e->dBlocks, slot0, nSlots, st); });
-      span("premap_kernel", 0, [&] {
-        premap_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st, 1); });
+    const unsigned nLane = (unsigned)(((size_t)S * nSlots + 63) / 64);
+    span("map_energy_kernel", nBlk * g.C, [&] {
+      map_energy_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
+    if (anyMapped) span("map_smooth_kernel", nBlk, [&] {
+      map_smooth_kernel<<<nLane, 64, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, st, 0); });
+    if (anyMapped || anyAuto) span("map_peaks_kernel", nBlk, [&] {
+      map_peaks_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
+    if (anyAuto) span("freqest_kernel", nBlk, [&] { freqest_kernel<<<(S + 63) / 64, 64, 0, q>>>(S, e->dStreams, e->dBlocks, slot0, nSlots, st); });
+    if (anyFormants) {
+      span("map_smooth_kernel", 0, [&] {
+        map_smooth_kernel<<<nLane, 64, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, st, 1); });
+      span("map_fmapply_kernel", nBlk * g.C, [&] {
+        map_fmapply_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
     }
     span("preterms_kernel", nBlk * g.C, [&] {
       preterms_kernel<<<nCta, nt, smT, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
@@ -775,7 +826,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
       cudaFuncSetAttribute(isynth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(preterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
       chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep, chain_warps(g.C, g.longStep, 1 << 20))) != cudaSuccess ||
-      cudaFuncSetAttribute(premap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
+      cudaFuncSetAttribute(map_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
     std::fprintf(stderr, "bauklank_stretch: block %d / interval %d needs more shared memory than one SM has\n", block, interval);
     bsb_destroy(e); return nullptr;
   }
@@ -914,10 +965,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B;
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
-  const size_t perSlot = (size_t)S * ((size_t)g.C * g.L * 4 + CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + 2 * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
+  const size_t perSlot = (size_t)S * ((size_t)g.C * g.L * 4 + (size_t)g.B * 12 + CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (e->overlap ? 2 : 1) * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
   if (chunkBlocks <= 0) {
-    const size_t budget = (size_t)48 << 30;
-    chunkBlocks = (int)std::min<size_t>(128, std::max<size_t>(1, budget / perSlot));
+    const size_t budget = (size_t)56 << 30;
+    chunkBlocks = (int)std::min<size_t>(256, std::max<size_t>(1, budget / perSlot));
     if (chunkBlocks > 32) chunkBlocks &= ~31;   // whole warps of the chain wavefront
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
@@ -935,13 +986,14 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.frames = dalloc<float>(nSlotTot * g.C * g.L, own); st.ringPar = 0;
   st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
+  st.energy = dalloc<float>(nSlotTot * g.B, own); st.smoothed = dalloc<float>(nSlotTot * g.B, own); st.fm = dalloc<float>(nSlotTot * fm_pitch(g.B), own);
   const size_t recFloats = (size_t)S * ((chunkBlocks + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
   e->recBuf[0] = dalloc<float>(recFloats, own);
-  e->recBuf[1] = (e->maxBlocks > chunkBlocks) ? dalloc<float>(recFloats, own) : nullptr;   // second buffer only if there is a next chunk
+  e->recBuf[1] = (e->overlap && e->maxBlocks > chunkBlocks) ? dalloc<float>(recFloats, own) : nullptr;   // only for chunk pipelining
   st.rec = e->recBuf[0];
   st.seeds = e->dSeeds; st.parity = 0;
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
-      !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring[0] || !st.ring[1] || !st.frames || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase ||
+      !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring[0] || !st.ring[1] || !st.frames || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase || !st.energy || !st.smoothed || !st.fm ||
       !st.rec) {
     free_batch(e);
     return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);

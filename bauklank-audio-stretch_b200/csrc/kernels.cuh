@@ -1,7 +1,7 @@
 // Device code of the stretch engine: five kernels per time-chunk of blocks
 //
 //   analysis_kernel   (stream, block, {cur,prev}, channel)  window -> half-bin-shifted real FFT -> spectrum in HBM
-//   premap_kernel     (stream, block)  energies, smoothing, peaks, frequency map, formant envelope
+//   map stage         energy / smooth / peaks (/ freqest / fmsmooth / fmapply) kernels, see "map stage" below
 //   preterms_kernel   (stream, block)  per-bin coefficient records of the phase prediction (everything state-free)
 //   chain_kernel      one warp per stream: the bin-to-bin / block-to-block phase recurrence as a 32-block wavefront
 //   isynth_kernel     (stream, block, channel)  inverse FFT -> synthesis window -> frame in HBM
@@ -69,6 +69,8 @@ struct StateDev {
   // per chunk slot
   float *inEnergy;    // [S][T][C][B]
   float *map;         // [S][T][B][2]  {inputBin, freqGrad}
+  float *energy, *smoothed;  // [S][T][B]  channel-summed band energy and its smoothed copy
+  float *fm;          // [S][T][fm_pitch(B)]  formant metric (sqrt of the band energy), smoothed in place
   float *fmAuto;      // [S][T][2]     formant auto-detect: spectral peak (top, index)
   float *fmBase;      // [S][T]        formant base bin after the leaky averages
   float *rec;         // [S][T][B+longStep+1][NR]  term records (one row per wavefront step)
@@ -258,31 +260,46 @@ BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float 
   BS_SYNC();
 }
 
-BS_HD float wp_at(const DevGeom &g, const DevTables &T, long long n) {
-  return n < g.wpStartLen ? T.wpStart[n] : T.wpSteady[(int)((n - g.wpStartLen) % g.H)];
-}
-
 // Overlap-add of one output sample (W#48 10700-10932 + the per-sample read 7990-8080): the partial sum carried from
-// earlier chunks, plus this chunk's frames that cover sample n, added in block order exactly like the reference's ring
+// earlier chunks, plus this chunk's frames that cover the sample, added in block order exactly like the reference's ring
 // (whose slot starts from 0.0 each time it is re-used), then either emitted (divided by the window-product sum) or
-// kept as the partial sum for the next chunk.
-//   ringBase: first sample the carried ring describes; emit range [ringBase, nE1); frames start at (m + split) * H.
-BS_HD void ola_sample(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, long long n, long long ringBase, long long nE1,
-                      long long slot0, int nv, bool addFrames, const float *frames /* [slot][C][L] of this stream */,
-                      const float *ringOld, float *ringNew /* [L] of this (stream, channel) */) {
+// kept as the partial sum for the next chunk.  All positions are relative to ringBase (the first sample the carried
+// ring describes), so the per-sample arithmetic is 32-bit:
+//   x        sample index - ringBase;  emit range [0, xE1);  frame of chunk slot t starts at (t + fsOff) * H
+//   rbModL   ringBase % L;  wpPhase  (ringBase - wpStartLen) mod H  (only used once n >= wpStartLen)
+struct OlaGeom { long long ringBase; int xE1, fsOff, rbModL, wpPhase, nv, addFrames; };
+BS_HHD OlaGeom ola_geom(const DevGeom &g, long long slot0, int nv, int mode) {
+  OlaGeom o;
+  const bool emit = (mode & kSynthEmit) != 0;
+  o.ringBase = (emit ? slot0 : slot0 + g.split) * (long long)g.H;
+  o.xE1 = emit ? nv * g.H : 0;
+  o.fsOff = emit ? g.split : 0;
+  o.rbModL = (int)(o.ringBase % g.L);
+  long long ph = (o.ringBase - g.wpStartLen) % g.H; if (ph < 0) ph += g.H;
+  o.wpPhase = (int)ph;
+  o.nv = nv; o.addFrames = (mode & kSynthAdd) ? 1 : 0;
+  return o;
+}
+BS_HD void ola_sample(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, int x, const OlaGeom &o,
+                      const float *frames /* [slot][C][L] of this stream */, const float *ringOld, float *ringNew /* [L] */) {
   const int L = g.L, H = g.H;
-  float acc = (n < ringBase + L) ? ringOld[(int)(n % L)] : 0.f;
-  if (addFrames) {
-    long long mLo = (n - L >= 0 ? (n - L) / H + 1 : 0) - g.split, mHi = n / H - g.split;
-    if (mLo < slot0) mLo = slot0;
-    if (mHi > slot0 + nv - 1) mHi = slot0 + nv - 1;
-    for (long long m = mLo; m <= mHi; ++m) {
-      const long long i = n - (m + g.split) * H;
-      acc = acc + frames[((size_t)(m - slot0) * g.C + c) * L + i];
-    }
+  int p = o.rbModL + x; p -= (p / L) * L;
+  float acc = (x < L) ? ringOld[p] : 0.f;
+  if (o.addFrames) {
+    int tLo = (x - L >= 0 ? (x - L) / H + 1 : 0) - o.fsOff, tHi = x / H - o.fsOff;
+    if (tLo < 0) tLo = 0;
+    if (tHi > o.nv - 1) tHi = o.nv - 1;
+    for (int t = tLo; t <= tHi; ++t) acc = acc + frames[((size_t)t * g.C + c) * L + (x - (t + o.fsOff) * H)];
   }
-  if (n < nE1) { if (n < sd.nOut) sd.out[(size_t)c * sd.outStride + (n - sd.outBase)] = acc / wp_at(g, T, n); }
-  else ringNew[(int)(n % L)] = acc;
+  if (x < o.xE1) {
+    const long long n = o.ringBase + x;
+    if (n < sd.nOut) {
+      float wp;
+      if (n < g.wpStartLen) wp = T.wpStart[n];
+      else { int q = o.wpPhase + x; q -= (q / H) * H; wp = T.wpSteady[q]; }
+      sd.out[(size_t)c * sd.outStride + (n - sd.outBase)] = acc / wp;
+    }
+  } else ringNew[p] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -375,41 +392,94 @@ BS_HD void make_output(float energy, cf fallback, float re, float im, float &ore
 //                                     bins k+1, k+longStep of block m-1, so consecutive blocks of one stream run as a
 //                                     wavefront -- lane j of a warp walks block m0+j, `lag` bins behind lane j-1.
 //
-// smem of the map stage (floats): energy[B+2] | smoothed[B] | cpk[B/2+2] ints | peaks[B] | misc[16] | segCnt[256]
-BS_HHD size_t map_smem_floats(int B) { return (((size_t)(B + 2) + B + (B / 2 + 2) + B + 16 + 256) + 3) & ~(size_t)3; }
+// The map stage runs as a short pipeline of kernels per chunk; the strictly serial parts (the one-pole smoothers) run
+// with ONE THREAD PER BLOCK -- 32 blocks per warp in lock step -- instead of one thread per CTA:
+//   energy   (bins in parallel)      inputEnergy, band energy sums, smoother input, sqrt metric for the formants
+//   smooth   (one thread per block)  smoothEnergy steps 1,2 on the band energies
+//   peaks    (CTA per block)         findPeaks + updateOutputMap; formant auto-detect peak pick
+//   freqest  (one thread per stream) leaky averages of the formant base over the blocks
+//   fmsmooth (one thread per block)  formant envelope smoothing
+//   fmapply  (bins in parallel)      formant envelope applied to the input energies
+BS_HHD int fm_pitch(int B) { return (B + 2 + 3) & ~3; }
 BS_HHD bool fm_auto(const BlockRec &rec) { return (rec.flags & kFormants) && !(rec.fmBaseFreq > 0.f); }
 
-// phase A: energies, map; for auto-detect formant blocks also the spectral-peak pick feeding the base estimate
+// energy: per bin.  energy[k] = sum over channels in channel order, exactly as the reference accumulates it.
 template <int CT>
-BS_HD void map_stage_a(const DevGeom &g, const DevTables &T, const BlockRec rec, const cf *inp, float *inEnergy, float *mapv,
-                       float *fmAuto /* [2]: top, i1 (int bits) */, float *sm, int tid, int nt) {
+BS_HD void map_energy(const DevGeom &g, const BlockRec rec, const cf *inp, float *inEnergy, float *energy, float *smoothed, float *fm,
+                      float *mapv, int tid, int nt) {
   const int C = CT > 0 ? CT : g.C, B = g.B;
+  const bool mapped = rec.flags & kMapped, formants = rec.flags & kFormants;
+  for (int k = tid; k < B; k += nt) {
+    float e = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const cf v = inp[(size_t)c * B + k];
+      const float en = (v.im * v.im) + (v.re * v.re);
+      inEnergy[(size_t)c * B + k] = en;
+      e = e + en;
+    }
+    if (mapped || formants) energy[k] = e;
+    if (mapped) smoothed[k] = e;
+    else { mapv[2 * k] = (float)(uint32_t)k; mapv[2 * k + 1] = 1.0f; }
+    if (formants) fm[k] = sqrtf(e);
+  }
+  if (formants) for (int k = B + tid; k < fm_pitch(B); k += nt) fm[k] = 0.f;
+}
+
+// One-pole smoother over an array in global memory, one thread per array: backward then forward (W#48 8420-8520).  The
+// next 16 samples are requested before the current 16 are processed, so a thread always has a load in flight.
+BS_HD float smooth_pass_g(float *v, int n, float slew, float s) {
+  constexpr int U = 16;
+  if (n % U != 0 || (((size_t)v) & 15) != 0) {   // odd sizes: plain loop
+    for (int i = n - 1; i >= 0; --i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
+    for (int i = 0; i < n; ++i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
+    return s;
+  }
+  f4 *v4 = (f4 *)v;
+  const int nc = n / U;
+  f4 cur[4], nxt[4];
+  for (int dir = 0; dir < 2; ++dir) {
+    int ch = dir == 0 ? nc - 1 : 0;
+    const int step = dir == 0 ? -1 : 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = v4[ch * 4 + j];
+    for (int it = 0; it < nc; ++it, ch += step) {
+      const int chn = ch + step;
+      if (it + 1 < nc) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nxt[j] = v4[chn * 4 + j];
+      }
+      float *x = (float *)cur;
+      if (dir == 0) {
+#pragma unroll
+        for (int j = U - 1; j >= 0; --j) { s = ((x[j] - s) * slew) + s; x[j] = s; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < U; ++j) { s = ((x[j] - s) * slew) + s; x[j] = s; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v4[ch * 4 + j] = cur[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    }
+  }
+  return s;
+}
+
+// smem of the peaks stage (ints/floats): cpk[B/2+2] | peaks[B] | misc[16] | segCnt[256]
+BS_HHD size_t map_smem_floats(int B) { return (((size_t)(B / 2 + 2) + B + 16 + 256) + 3) & ~(size_t)3; }
+
+// peaks: findPeaks + updateOutputMap from the band energies and their smoothed copy (both in global memory); for
+// auto-detect formant blocks also the spectral-peak pick feeding the base estimate
+BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, const float *smoothed, float *mapv,
+                     float *fmAuto /* [2]: top, i1 (int bits) */, float *sm, int tid, int nt) {
+  const int B = g.B;
   const bool mapped = rec.flags & kMapped;
-  const float fN = (float)(uint32_t)g.N, fH = (float)(uint32_t)g.H, ratio = fN / fH;
-  float *energy = sm, *smoothed = sm + (B + 2);
-  int *cpk = (int *)(smoothed + B);
+  const float fN = (float)(uint32_t)g.N;
+  int *cpk = (int *)sm;
   float *peaksG = (float *)(cpk + (B / 2 + 2));
   int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] monotone flag
   int *segCnt = misc + 16;           // [nt] run starts per thread segment
-  for (int idx = tid; idx < C * B; idx += nt) {
-    cf v = inp[idx];
-    inEnergy[idx] = (v.im * v.im) + (v.re * v.re);
-  }
-  BS_SYNC();
   if (mapped) {
-    for (int k = tid; k < B; k += nt) {
-      float e = 0.f;
-      for (int c = 0; c < C; ++c) e = e + inEnergy[(size_t)c * B + k];
-      energy[k] = e; smoothed[k] = e;
-    }
-    BS_SYNC();
-    if (tid == 0) {
-      // smoothEnergy steps 1,2 (one-pole, carry kept across both)
-      float slew = 1.0f / ((ratio * 0.5f) + 1.0f), carry = 0.f;
-      carry = smooth_pass(smoothed, B, slew, carry);
-      carry = smooth_pass(smoothed, B, slew, carry);
-    }
-    BS_SYNC();
     // findPeaks (W#48 8560-8700): a peak = a maximal run of bins with energy > smoothed.  Runs are independent, so every
     // thread takes the runs that START in its segment of bins (and follows them past the segment end); the peak index is
     // the number of run starts before it (counted per segment, then prefix-summed).
@@ -480,41 +550,30 @@ BS_HD void map_stage_a(const DevGeom &g, const DevTables &T, const BlockRec rec,
       }
       mapv[2 * k] = ib; mapv[2 * k + 1] = gr;
     }
-  } else {
-    for (int k = tid; k < B; k += nt) { mapv[2 * k] = (float)(uint32_t)k; mapv[2 * k + 1] = 1.0f; }
   }
-  BS_SYNC();
-  if (fm_auto(rec)) {
-    float *fm = energy;  // [B+2]
-    for (int k = tid; k < B + 2; k += nt) {
-      float e = 0.f;
-      if (k < B) for (int c = 0; c < C; ++c) e = e + inEnergy[(size_t)c * B + k];
-      fm[k] = e;
+  if (fm_auto(rec) && tid == 0) {   // `energy` holds the channel-summed input energy = the formant metric before its sqrt
+    const float *fm = energy;
+    auto at = [&](int i) { return i < B ? fm[i] : 0.f; };
+    int i1 = 0, i2 = 0, i3 = 0;
+    for (int i = 1; i <= B - 2; ++i) {
+      float v = fm[i];
+      if (v < fm[i - 1]) continue;
+      if (v <= at(i + 1)) continue;
+      if (v <= fm[i3]) continue;
+      if (fm[i2] >= v) { i3 = i; continue; }
+      if (fm[i1] < v) { i3 = i2; i2 = i1; i1 = i; continue; }
+      i3 = i2; i2 = i;
     }
-    BS_SYNC();
-    if (tid == 0) {
-      int i1 = 0, i2 = 0, i3 = 0;
-      for (int i = 1; i <= B - 2; ++i) {
-        float v = fm[i];
-        if (v < fm[i - 1]) continue;
-        if (v <= fm[i + 1]) continue;
-        if (v <= fm[i3]) continue;
-        if (fm[i2] >= v) { i3 = i; continue; }
-        if (fm[i1] < v) { i3 = i2; i2 = i1; i1 = i; continue; }
-        i3 = i2; i2 = i;
-      }
-      float top = fm[i1]; double dtop = (double)top;
-      if ((double)fm[i2] > (dtop * 0.1)) {
-        int d = i1 - i2; if (d < 0) d = -d;
+    float top = fm[i1]; double dtop = (double)top;
+    if ((double)fm[i2] > (dtop * 0.1)) {
+      int d = i1 - i2; if (d < 0) d = -d;
+      if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
+      if (!((double)fm[i3] <= (dtop * 0.01))) {
+        d = i1 - i3; if (d < 0) d = -d;
         if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
-        if (!((double)fm[i3] <= (dtop * 0.01))) {
-          d = i1 - i3; if (d < 0) d = -d;
-          if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
-        }
       }
-      fmAuto[0] = top; fmAuto[1] = __int_as_float_hd(i1);
     }
-    BS_SYNC();
+    fmAuto[0] = top; fmAuto[1] = __int_as_float_hd(i1);
   }
 }
 
@@ -530,27 +589,20 @@ BS_HD float freqest_step(float *freqEst, const float *fmAuto) {
   return ww / (nw + 1e-30f);
 }
 
-// phase B: formant envelope applied to the input energies (needs the base bin)
+// formant envelope smoothing, one thread per block (W#48 8962-9040): fm = sqrt(channel-summed energy), written by the
+// energy stage; slew from the base bin (fixed, or the auto-detected estimate)
+BS_HD void fm_smooth(const DevGeom &g, const BlockRec rec, float baseBinAuto, float *fm) {
+  const float fN = (float)(uint32_t)g.N, base = rec.fmBaseFreq;
+  const float baseBin = (base > 0.f) ? ((base * fN) + -0.5f) : baseBinAuto;
+  const float slew = (float)(1.0 / (((double)baseBin * 0.5) + 1.0));
+  const float st = smooth_pass_g(fm, g.B, slew, 0.f);
+  smooth_pass_g(fm, g.B, slew, st);
+}
+// formant envelope applied to the input energies (W#48 9042-9312), per bin
 template <int CT>
-BS_HD void map_stage_b(const DevGeom &g, const BlockRec rec, const BlockRec2 rec2, float baseBinAuto, float *inEnergy, float *sm, int tid, int nt) {
+BS_HD void fm_apply(const DevGeom &g, const BlockRec rec, const BlockRec2 rec2, const float *fm, float *inEnergy, int tid, int nt) {
   const int C = CT > 0 ? CT : g.C, B = g.B;
-  if (!(rec.flags & kFormants)) return;
   const float fN = (float)(uint32_t)g.N;
-  float *fm = sm;  // [B+2]
-  for (int k = tid; k < B + 2; k += nt) {
-    float e = 0.f;
-    if (k < B) for (int c = 0; c < C; ++c) e = e + inEnergy[(size_t)c * B + k];
-    fm[k] = sqrtf(e);
-  }
-  BS_SYNC();
-  if (tid == 0) {
-    const float base = rec.fmBaseFreq;
-    const float baseBin = (base > 0.f) ? ((base * fN) + -0.5f) : baseBinAuto;
-    float slew = (float)(1.0 / (((double)baseBin * 0.5) + 1.0));
-    float st = smooth_pass(fm, B, slew, 0.f);
-    smooth_pass(fm, B, slew, st);
-  }
-  BS_SYNC();
   const bool comp = rec.flags & kFormantComp;
   for (int k = tid; k < B; k += nt) {
     float f = ((float)k + 0.5f) / fN;
@@ -568,7 +620,6 @@ BS_HD void map_stage_b(const DevGeom &g, const BlockRec rec, const BlockRec2 rec
     float g2 = env / (metric + 1e-30f); g2 = g2 * g2;
     for (int c = 0; c < C; ++c) { size_t o = (size_t)c * B + k; inEnergy[o] = g2 * inEnergy[o]; }
   }
-  BS_SYNC();
 }
 
 // ---- term stage: per-(block, bin) records.  One row of NR floats per wavefront step of a block: row r holds the chain

@@ -156,8 +156,8 @@ def test_overlap_switch_does_not_change_results(bs, golden):
     clip = torch.from_numpy(cases.make_clip(case["clip"])).cuda()
     for on in (True, False):
         eng = cases.make_batch(bs, case, 2)
+        eng.set_overlap(on)          # before plan(): the second record buffer is allocated at commit time
         outs = eng.plan([clip], [cases.batch_drive(bs, case, clip.shape[1])], chunk_blocks=32)
-        eng.set_overlap(on)
         eng.run(); eng.run()
         torch.cuda.synchronize()
         assert_matches_golden("KA6", outs[0].cpu().numpy(), golden)
