@@ -178,7 +178,8 @@ constexpr int kChainWarps = 8;    // warps per CTA: up to 256 consecutive blocks
 BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
 BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
   const size_t R = chain_ring(longStep);
-  return (size_t)warps * (2 * R * C * 32 * sizeof(cf)) + 2 * (size_t)kChainTile * C * sizeof(cf) + 2 * (size_t)warps * C * sizeof(cf);
+  return (size_t)warps * (2 * R * C * 32 * sizeof(cf) + 32 * (size_t)nr_pitch(C) * sizeof(float)) + 2 * (size_t)kChainTile * C * sizeof(cf) +
+         2 * (size_t)warps * C * sizeof(cf) + 16;
 }
 
 // ---- branch-free IEEE division / square root for the chain's hot loop.
@@ -342,22 +343,36 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     cf last[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) last[c].re = last[c].im = 0.f;
-    // The record row and the spectral rotation of a step are fetched into registers one step ahead (two register sets,
-    // ping-pong): a step takes longer than a DRAM round trip, so the loads are complete when the next step starts.
-    float4 bufA[NR / 4], bufB[NR / 4];
-    cf rotA, rotB; rotA.re = rotA.im = rotB.re = rotB.im = 0.f;
+    // Record rows: the 32 rows a warp needs in one step are one contiguous run of 32 row pitches (wavefront-major
+    // storage).  The warp fetches the run of step t+1 with fully coalesced 16-byte loads while it computes step t, then
+    // parks it in its shared-memory stage (XOR-swizzled by row so that both the row-major writes and the row-per-lane
+    // reads are bank-conflict free); every lane then picks up its own row with a few LDS.128.
+    constexpr int RQ = NRP / 4;                               // float4 per row pitch
+    float4 *stage = (float4 *)(hand + 2 * (size_t)nW * C) + (size_t)warp * 32 * RQ;
+    const float4 *grpRun = grp4 - (size_t)lane * (NRP / 4);   // group base (grp4 carries this lane's row offset)
+    const int nDiag = rows + 31 * D;
+    float4 ld[RQ];
+    cf rotNxt; rotNxt.re = rotNxt.im = 0.f;
+    auto fetch = [&](int t) {     // diagonal of step t: u = t + OA - 32*warp*D; lane l's row there is u - l*D
+      const int u = t + OA - 32 * warp * D;
+      if (u >= 0 && u < nDiag) {
+        const float4 *src = grpRun + (size_t)u * (32 * RQ) + lane;
 #pragma unroll
-    for (int i = 0; i < NR / 4; ++i) bufA[i] = bufB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fetch = [&](int t, float4 *buf, cf &rot) {   // row = local time + OA: chain part of bin row-ls-1, S5 part of bin row
-      const int r = t - j * D + OA;
-      if (active && r >= 1 && r < rows) {
-        const float4 *src = grp4 + (size_t)(r + lane * D) * (32 * NRP / 4);
+        for (int i = 0; i < RQ; ++i) ld[i] = __ldcs(src + i * 32);
+      }
+      const int r = u - lane * D;
+      if (r >= 1 && r < B) rotNxt = specRot[r];
+    };
+    auto park = [&]() {           // element i*32+lane of the run = row (i*32+lane)/RQ, chunk (i*32+lane)%RQ
 #pragma unroll
-        for (int i = 0; i < NR / 4; ++i) buf[i] = __ldcs(src + i);
-        rot = specRot[r < B ? r : 0];
+      for (int i = 0; i < RQ; ++i) {
+        const int e = i * 32 + lane, rr = e / RQ, cc = e % RQ;
+        stage[rr * RQ + (cc ^ (rr & (RQ - 1) & 7))] = ld[i];
       }
     };
-    auto step = [&](int t, const float4 *buf, const cf rot) {
+    fetch(0); park(); __syncwarp();
+    cf rot = rotNxt;
+    auto step = [&](int t) {
       // slot 0's S5 stage reads bin t+OA this step.  The buffer of tile i-1 was last read one step BEFORE the step with
       // (t+OA) % TL == 0; threads that are ahead may only overwrite it once everybody has passed the barrier after that
       // read, i.e. from the step with (t+OA) % TL == 1 on.  The tile is complete long before it is needed; the wait
@@ -366,10 +381,15 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
       if (q0 > TL && (q0 % TL) == 1) { request_tile(q0 / TL + 1); cp_async_commit(); }
       if ((q0 % TL) == TL - 1) cp_async_wait<0>();
       __syncthreads();
-      const float *row = (const float *)buf;
       const int tau = t - j * D, q = tau + OA, k = tau - ls;
       const bool validQ = active && q >= 1 && q < B, validK = active && k >= 0 && k < B;
       if (!__any_sync(0xffffffffu, validQ || validK)) return;   // the whole warp is before its first or past its last bin
+      float row[NR];
+#pragma unroll
+      for (int i = 0; i < NR / 4; ++i) {
+        const float4 v = stage[lane * RQ + (i ^ (lane & (RQ - 1) & 7))];
+        row[4 * i] = v.x; row[4 * i + 1] = v.y; row[4 * i + 2] = v.z; row[4 * i + 3] = v.w;
+      }
       const int qc = q & (2 * TL - 1);                      // position of bin q in the two-tile window (slot 0 only)
       // S1 + S5 for bin q: previous block's output from the lane above (shuffle), the warp above (hand) or the state
       cf n5[C];
@@ -409,14 +429,12 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
         }
       }
     };
-    fetch(0, bufA, rotA);
-    for (int t = 0; t <= tEnd; t += 2) {
-      fetch(t + 1, bufB, rotB);
-      step(t, bufA, rotA);
-      if (t + 1 <= tEnd) {
-        fetch(t + 2, bufA, rotA);
-        step(t + 1, bufB, rotB);
-      }
+    for (int t = 0; t <= tEnd; ++t) {
+      fetch(t + 1);                 // in flight during the whole step
+      step(t);
+      __syncwarp();                 // every lane has read its row of step t
+      park(); rot = rotNxt;
+      __syncwarp();
     }
     cp_async_wait<0>();
     __syncthreads();
