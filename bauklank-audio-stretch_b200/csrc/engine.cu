@@ -351,11 +351,12 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     float4 *stage = (float4 *)(hand + 2 * (size_t)nW * C) + (size_t)warp * 32 * RQ;
     const float4 *grpRun = grp4 - (size_t)lane * (NRP / 4);   // group base (grp4 carries this lane's row offset)
     const int nDiag = rows + 31 * D;
+    const bool warpLive = p0 + 32 * warp < nValid;            // this warp's record group exists (it has at least one block)
     float4 ld[RQ];
     cf rotNxt; rotNxt.re = rotNxt.im = 0.f;
     auto fetch = [&](int t) {     // diagonal of step t: u = t + OA - 32*warp*D; lane l's row there is u - l*D
       const int u = t + OA - 32 * warp * D;
-      if (u >= 0 && u < nDiag) {
+      if (warpLive && u >= 0 && u < nDiag) {
         const float4 *src = grpRun + (size_t)u * (32 * RQ) + lane;
 #pragma unroll
         for (int i = 0; i < RQ; ++i) ld[i] = __ldcs(src + i * 32);
