@@ -37,6 +37,7 @@ _BATCH_SIG = {
                                     C.c_longlong, C.POINTER(Segment), C.c_int, C.c_uint32]),
     "bsb_commit": (C.c_int, [C.c_void_p, C.c_int]),
     "bsb_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bsb_run_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "bsb_rebind": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "bsb_total_blocks": (C.c_longlong, [C.c_void_p]),
     "bsb_stream_blocks": (C.c_longlong, [C.c_void_p, C.c_int]),

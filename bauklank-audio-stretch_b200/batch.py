@@ -145,6 +145,24 @@ class BatchStretch:
         self._check(self.lib.bsb_run(self.h, C.c_void_p(cuda_stream)))
         return self.outputs
 
+    def run_host(self, host_clips, host_outs, cuda_stream=None):
+        """Like run(), for audio in host memory: host_clips[i] / host_outs[i] are float32 [channels, n] arrays (pinned
+        torch CPU tensors or numpy) matching the planned shapes.  The planned device tensors serve as staging; copies
+        and kernels are pipelined chunk by chunk inside the library."""
+        n = len(self._keep)
+        assert len(host_clips) == n and len(host_outs) == n
+        if cuda_stream is None:
+            cuda_stream = 0
+            if self._keep and hasattr(self._keep[0][0], "data_ptr"):
+                import torch
+                cuda_stream = torch.cuda.current_stream().cuda_stream
+        for (clip, out, _), hc, ho in zip(self._keep, host_clips, host_outs):
+            assert tuple(hc.shape) == tuple(clip.shape) and tuple(ho.shape) == tuple(out.shape)
+        ins = (C.c_void_p * n)(*[_ptr(x) for x in host_clips])
+        outs = (C.c_void_p * n)(*[_ptr(x) for x in host_outs])
+        self._check(self.lib.bsb_run_host(self.h, ins, outs, C.c_void_p(cuda_stream)))
+        return host_outs
+
     def total_blocks(self): return self.lib.bsb_total_blocks(self.h)
     def stream_blocks(self, i): return self.lib.bsb_stream_blocks(self.h, i)
     def chunk_blocks(self): return self.lib.bsb_chunk_blocks(self.h)

@@ -534,6 +534,8 @@ struct bsb_engine {
   int chunk = 0; long long maxBlocks = 0, totalBlocks = 0, launches = 0;
   std::vector<long long> blockBase;
   std::vector<BlockRec> hostBlocks;
+  std::vector<long long> needEnd;   // [chunk][stream]: clip samples (per channel) the chunk's analysis windows reach
+  int nChunks = 0;
   bool committed = false;
   // per-kernel accounting of the last bsb_run: launches and units always; device time when profiling is on
   // (one CUDA event pair per launch, read back lazily so the run itself is never serialised)
@@ -544,7 +546,7 @@ struct bsb_engine {
                                    // streams); measured to gain nothing on B200 -- every kernel is occupancy bound -- so off
   float *recBuf[2] = {nullptr, nullptr};
 #ifndef BS_HOSTEMU
-  cudaStream_t sFront = nullptr, sBack = nullptr;
+  cudaStream_t sFront = nullptr, sBack = nullptr, sIn = nullptr, sOut = nullptr;
   cudaEvent_t evFront[2] = {nullptr, nullptr}, evBack[2] = {nullptr, nullptr}, evFork = nullptr, evJoin[2] = {nullptr, nullptr};
   bool backUsed[2] = {false, false};
   struct Span { int k; cudaEvent_t a, b; };
@@ -835,6 +837,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   e->dt.wpStart = upload(e, e->T.wpStart, e->owned); e->dt.wpSteady = upload(e, e->T.wpSteady, e->owned);
 #ifndef BS_HOSTEMU
   cudaStreamCreateWithFlags(&e->sFront, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&e->sBack, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&e->sIn, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&e->sOut, cudaStreamNonBlocking);
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&e->evFront[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&e->evBack[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming);
@@ -870,6 +873,8 @@ void bsb_destroy(bsb_engine *e) {
   if (e->evFork) cudaEventDestroy(e->evFork);
   if (e->sFront) cudaStreamDestroy(e->sFront);
   if (e->sBack) cudaStreamDestroy(e->sBack);
+  if (e->sIn) cudaStreamDestroy(e->sIn);
+  if (e->sOut) cudaStreamDestroy(e->sOut);
 #endif
   delete e;
 }
@@ -992,6 +997,20 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
   e->chunk = chunkBlocks;
+  e->nChunks = (int)((e->maxBlocks + chunkBlocks - 1) / chunkBlocks);
+  e->needEnd.assign((size_t)std::max(1, e->nChunks) * S, 0);
+  for (int s = 0; s < S; ++s) {   // running maximum of the analysis windows' reach, chunk by chunk (for bsb_run_host)
+    long long reach = 0;
+    for (int i = 0; i < e->nChunks; ++i) {
+      const long long m0 = (long long)i * chunkBlocks, m1 = std::min<long long>(m0 + chunkBlocks, e->hs[s].nBlocks);
+      for (long long m = m0; m < m1; ++m)
+        for (int w = 0; w < 2; ++w) {
+          const Window &x = windows[2 * (e->blockBase[s] + m) + w];
+          if (x.hi > x.lo) reach = std::max(reach, x.start + x.hi);
+        }
+      e->needEnd[(size_t)i * S + s] = std::min<long long>(reach, e->hs[s].clipLen);
+    }
+  }
   auto &own = e->batchOwned;
   e->dStreams = upload(e, e->hs, own); e->dBlocks = upload(e, blocks, own); e->dBlocks2 = upload(e, blocks2, own);
   e->dWindows = upload(e, windows, own); e->dSeeds = upload(e, seeds, own);
@@ -1021,38 +1040,81 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   return 0;
 }
 
-int bsb_run(bsb_engine *e, void *cudaStream) {
+// Shared by bsb_run (device-resident audio) and bsb_run_host (host audio, copies pipelined chunk by chunk on two
+// extra streams: the clip samples chunk i+1 needs go up while chunk i computes, the output samples of chunk i-1 come
+// down at the same time).
+static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float *const *hOuts) {
   if (!e->committed) return e->fail("bsb_run needs a committed batch");
   const Geometry &g = e->g;
   const int S = (int)e->streams.size();
-  const size_t CB = (size_t)g.C * g.B;
-  stream_t q = (stream_t)cudaStream;
-  StateDev &st = e->st;
   reset_state(e, q);
   e->launches = 0;
   for (auto &k : e->kstat) { k.ms = 0.0; k.launches = 0; k.units = 0; }
-#ifndef BS_HOSTEMU
-  e->spans.clear(); e->evUsed = 0;
-#endif
 #ifdef BS_HOSTEMU
+  for (int s = 0; s < S && hClips; ++s)
+    std::memcpy((void *)e->streams[s].clip, hClips[s], (size_t)g.C * e->hs[s].clipLen * sizeof(float));
   for (long long slot0 = 0, i = 0; slot0 < e->maxBlocks; slot0 += e->chunk, ++i)
     if (launch_chunk(e, slot0, e->chunk, q, q, 0, 3, kSynthEmit | kSynthAdd)) return -1;
+  for (int s = 0; s < S && hOuts; ++s)
+    std::memcpy(hOuts[s], e->streams[s].out, (size_t)g.C * e->hs[s].nOut * sizeof(float));
 #else
+  e->spans.clear(); e->evUsed = 0;
   const bool two = e->overlap && e->recBuf[1] != nullptr && e->maxBlocks > e->chunk;
-  if (two) {   // fork: both internal streams start after everything already queued on the caller's stream
+  const bool host = hClips != nullptr && hOuts != nullptr;
+  if (two || host) {   // fork: the internal streams start after everything already queued on the caller's stream
     cudaEventRecord(e->evFork, q);
-    cudaStreamWaitEvent(e->sFront, e->evFork, 0); cudaStreamWaitEvent(e->sBack, e->evFork, 0);
+    if (two) { cudaStreamWaitEvent(e->sFront, e->evFork, 0); cudaStreamWaitEvent(e->sBack, e->evFork, 0); }
+    if (host) { cudaStreamWaitEvent(e->sIn, e->evFork, 0); cudaStreamWaitEvent(e->sOut, e->evFork, 0); }
     e->backUsed[0] = e->backUsed[1] = false;
   }
+  std::vector<long long> copied(host ? S : 0, 0);
   long long i = 0;
-  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk, ++i)
-    if (launch_chunk(e, slot0, e->chunk, two ? e->sFront : q, two ? e->sBack : q, two ? (int)(i & 1) : 0, 3, kSynthEmit | kSynthAdd)) return -1;
+  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk, ++i) {
+    stream_t qF = two ? e->sFront : q, qB = two ? e->sBack : q;
+    if (host) {   // clip samples first needed by this chunk, all channels of a stream in one strided copy
+      for (int s = 0; s < S; ++s) {
+        const long long need = e->needEnd[(size_t)i * S + s], have = copied[s];
+        if (need > have) {
+          const StreamDev &d = e->hs[s];
+          cudaMemcpy2DAsync((void *)(d.clip + have), (size_t)d.clipLen * sizeof(float), hClips[s] + have, (size_t)d.clipLen * sizeof(float),
+                            (size_t)(need - have) * sizeof(float), (size_t)g.C, cudaMemcpyHostToDevice, e->sIn);
+          copied[s] = need;
+        }
+      }
+      cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, e->sIn); cudaStreamWaitEvent(qF, ev, 0);
+    }
+    if (launch_chunk(e, slot0, e->chunk, qF, qB, two ? (int)(i & 1) : 0, 3, kSynthEmit | kSynthAdd)) return -1;
+    if (host) {   // the output samples this chunk emitted
+      cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, qB); cudaStreamWaitEvent(e->sOut, ev, 0);
+      for (int s = 0; s < S; ++s) {
+        const StreamDev &d = e->hs[s];
+        const long long n0 = std::min<long long>(slot0 * g.H, d.nOut);
+        const long long n1 = std::min<long long>(std::min<long long>(slot0 + e->chunk, d.nBlocks) * (long long)g.H, d.nOut);
+        if (n1 > n0)
+          cudaMemcpy2DAsync(hOuts[s] + n0, (size_t)d.nOut * sizeof(float), d.out + n0, (size_t)d.outStride * sizeof(float),
+                            (size_t)(n1 - n0) * sizeof(float), (size_t)g.C, cudaMemcpyDeviceToHost, e->sOut);
+      }
+    }
+  }
   if (two) {   // join
     cudaEventRecord(e->evJoin[0], e->sFront); cudaEventRecord(e->evJoin[1], e->sBack);
     cudaStreamWaitEvent(q, e->evJoin[0], 0); cudaStreamWaitEvent(q, e->evJoin[1], 0);
   }
+  if (host) {
+    cudaEvent_t a = e->get_event(), b = e->get_event();
+    cudaEventRecord(a, e->sIn); cudaEventRecord(b, e->sOut);
+    cudaStreamWaitEvent(q, a, 0); cudaStreamWaitEvent(q, b, 0);
+  }
+  if (cudaGetLastError() != cudaSuccess) return e->fail("copy or launch failed");
 #endif
   return 0;
+}
+
+int bsb_run(bsb_engine *e, void *cudaStream) { return run_impl(e, (stream_t)cudaStream, nullptr, nullptr); }
+
+int bsb_run_host(bsb_engine *e, const float *const *hClips, float *const *hOuts, void *cudaStream) {
+  if (!hClips || !hOuts) return e->fail("bsb_run_host needs host clip and output pointers");
+  return run_impl(e, (stream_t)cudaStream, hClips, hOuts);
 }
 
 void bsb_set_overlap(bsb_engine *e, int on) { e->overlap = on != 0; }

@@ -251,10 +251,13 @@ def main_gpu(args):
     h_out = torch.empty(outs_all.shape, dtype=torch.float32, pin_memory=True)
     clips_all.zero_()
     e2e_steps = args.steps
+    h_clips = [h_in[i] for i in range(S)]
+    h_outs, off = [], 0
+    for n in n_out:
+        h_outs.append(h_out[off:off + 2 * n].view(2, n)); off += 2 * n
+
     def e2e_step():
-        clips_all.copy_(h_in, non_blocking=True)
-        eng.run()
-        h_out.copy_(outs_all, non_blocking=True)
+        eng.run_host(h_clips, h_outs)      # H2D of every clip, all kernels, D2H of every output (pipelined per time chunk)
     e2e_step()
     barrier()
     a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

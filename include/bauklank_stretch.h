@@ -81,6 +81,11 @@ int bsb_add_streaming(bsb_engine *e, int stream, const float *d_clip, long long 
 int bsb_commit(bsb_engine *e, int chunk_blocks);
 /* run every block of every stream on `cuda_stream` (a cudaStream_t); state is reset first */
 int bsb_run(bsb_engine *e, void *cuda_stream);
+/* Same as bsb_run for audio that lives in HOST memory (ideally pinned): h_clips[s] / h_outs[s] are planar f32
+ * [channels][clip_len] / [channels][n_out] of stream s.  The device buffers given to bsb_add_* are used as staging; the
+ * copies are pipelined with the kernels time chunk by time chunk (input of chunk i+1 and output of chunk i-1 move
+ * while chunk i computes).  Everything is ordered after, and joined back into, `cuda_stream`. */
+int bsb_run_host(bsb_engine *e, const float *const *h_clips, float *const *h_outs, void *cuda_stream);
 /* rebind the device I/O pointers of an already planned batch (same shapes) without re-planning */
 int bsb_rebind(bsb_engine *e, int stream, const float *d_clip, float *d_out);
 long long bsb_total_blocks(const bsb_engine *e);

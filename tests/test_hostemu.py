@@ -90,3 +90,14 @@ def test_error_behaviour(emu):
     eng.close()
     with pytest.raises(RuntimeError):      # block < 8
         bs.BatchStretch(2, 48000.0, block_samples=4, interval_samples=1, lib=emu)
+
+
+def test_run_host_entry_point(emu, golden):
+    case = cases.CASES["KA5"]
+    clip = cases.make_clip(case["clip"])
+    eng = cases.make_batch(bs, case, 2, lib=emu)
+    outs = eng.plan([np.zeros_like(clip)], [cases.batch_drive(bs, case, clip.shape[1])], chunk_blocks=5)
+    ho = [np.zeros_like(outs[0])]
+    eng.run_host([clip], ho)
+    assert_matches_golden("KA5", ho[0], golden)
+    eng.close()
