@@ -81,12 +81,14 @@ __global__ void __launch_bounds__(256) map_energy_kernel(DevGeom g, const Stream
   else map_energy<0>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
 }
 
-// one thread per (stream, block): which = 0 band-energy smoothing (mapped blocks), 1 formant-envelope smoothing
-__global__ void __launch_bounds__(64) map_smooth_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
-                                                        long long slot0, int nSlots, int S, StateDev st, int which) {
+// one thread per (stream, block): which = 0 band-energy smoothing (mapped blocks), 1 formant-envelope smoothing.
+// Launched over slices [t0, t0+nT) of the chunk's slots whose arrays fit the L2 together (four sweeps re-read them).
+__global__ void __launch_bounds__(32) map_smooth_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
+                                                        long long slot0, int nSlots, int S, int t0, int nT, StateDev st, int which) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S * nSlots) return;
-  const int t = i % nSlots, s = i / nSlots;
+  if (i >= S * nT) return;
+  const int t = t0 + i / S, s = i % S;
+  if (t >= nSlots) return;
   const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
   if (!c.valid) return;
   if (which == 0) {
@@ -499,16 +501,23 @@ __global__ void __launch_bounds__(256) isynth_kernel(DevGeom g, DevTables T, con
 }
 
 __global__ void __launch_bounds__(256) ola_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots, int mode,
-                                                  StateDev st) {
+                                                  StateDev st, int quad) {
   const int s = blockIdx.y / g.C, c = blockIdx.y % g.C;
   const StreamDev sd = streams[s];
   long long nvl = sd.nBlocks - slot0; if (nvl > nSlots) nvl = nSlots;
   if (nvl <= 0) return;
   const OlaGeom o = ola_geom(g, slot0, (int)nvl, mode);
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= o.xE1 + g.L) return;
   const size_t rc = ((size_t)s * g.C + c) * g.L;
-  ola_sample(g, T, sd, c, x, o, st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+  const float *frames = st.frames + (size_t)s * nSlots * g.C * g.L;
+  if (quad) {
+    const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (x >= o.xE1 + g.L) return;
+    ola_quad(g, T, sd, c, x, o, frames, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+  } else {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= o.xE1 + g.L) return;
+    ola_sample(g, T, sd, c, x, o, frames, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+  }
 }
 #endif
 
@@ -750,8 +759,12 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
       const OlaGeom o = ola_geom(e->dg, slot0, (int)nvl, synthMode);
       for (int c = 0; c < g.C; ++c) {
         const size_t rc = ((size_t)s * g.C + c) * g.L;
-        for (int x = 0; x < o.xE1 + g.L; ++x)
-          ola_sample(e->dg, e->dt, sd, c, x, o, st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+        if (ola_quad_ok(e->dg))
+          for (int x = 0; x < o.xE1 + g.L; x += 4)
+            ola_quad(e->dg, e->dt, sd, c, x, o, st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
+        else
+          for (int x = 0; x < o.xE1 + g.L; ++x)
+            ola_sample(e->dg, e->dt, sd, c, x, o, st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
       }
     }
     st.ringPar ^= 1;
@@ -776,17 +789,25 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
     if (twoStreams && e->backUsed[buf]) cudaStreamWaitEvent(qF, e->evBack[buf], 0);   // the chain that read this record buffer is done
     span("analysis_kernel", nNew * 2 * g.C, [&] {
       analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
-    const unsigned nLane = (unsigned)(((size_t)S * nSlots + 63) / 64);
     span("map_energy_kernel", nBlk * g.C, [&] {
       map_energy_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
-    if (anyMapped) span("map_smooth_kernel", nBlk, [&] {
-      map_smooth_kernel<<<nLane, 64, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, st, 0); });
+    // slices of slots whose smoother arrays (S * slice * B floats) stay L2 resident across the four sweeps
+    const int smSlice = (int)std::max<size_t>(1, std::min<size_t>((size_t)nSlots, ((size_t)80 << 20) / ((size_t)S * g.B * sizeof(float))));
+    auto smooth_all = [&](int which) {
+      for (int t0 = 0; t0 < nSlots; t0 += smSlice) {
+        const int nT = std::min(smSlice, nSlots - t0);
+        bool any = false;
+        for (int s = 0; s < S && !any; ++s) any = slot0 + t0 < e->hs[s].nBlocks;
+        if (!any) break;
+        map_smooth_kernel<<<(unsigned)(((size_t)S * nT + 31) / 32), 32, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, t0, nT, st, which);
+      }
+    };
+    if (anyMapped) span("map_smooth_kernel", nBlk, [&] { smooth_all(0); });
     if (anyMapped || anyAuto) span("map_peaks_kernel", nBlk, [&] {
       map_peaks_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
     if (anyAuto) span("freqest_kernel", nBlk, [&] { freqest_kernel<<<(S + 63) / 64, 64, 0, q>>>(S, e->dStreams, e->dBlocks, slot0, nSlots, st); });
     if (anyFormants) {
-      span("map_smooth_kernel", 0, [&] {
-        map_smooth_kernel<<<nLane, 64, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, st, 1); });
+      span("map_smooth_kernel", 0, [&] { smooth_all(1); });
       span("map_fmapply_kernel", nBlk * g.C, [&] {
         map_fmapply_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
     }
@@ -808,7 +829,9 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
         isynth_kernel<<<(unsigned)((size_t)S * nSlots * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, e->specOut, st); });
     const long long span_n = (long long)std::min<long long>(nSlots, e->maxBlocksOr1(slot0)) * g.H + g.L;
     span("ola_kernel", nBlk * g.C, [&] {
-      ola_kernel<<<dim3((unsigned)((span_n + 255) / 256), (unsigned)(S * g.C)), 256, 0, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, st); });
+      const int quad = ola_quad_ok(e->dg) ? 1 : 0;
+      const long long nThr = quad ? (span_n + 3) / 4 : span_n;
+      ola_kernel<<<dim3((unsigned)((nThr + 255) / 256), (unsigned)(S * g.C)), 256, 0, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, st, quad); });
     st.ringPar ^= 1;
   }
   cudaError_t ce = cudaGetLastError();

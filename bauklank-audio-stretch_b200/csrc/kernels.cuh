@@ -280,6 +280,45 @@ BS_HHD OlaGeom ola_geom(const DevGeom &g, long long slot0, int nv, int mode) {
   o.nv = nv; o.addFrames = (mode & kSynthAdd) ? 1 : 0;
   return o;
 }
+// four consecutive samples at once (x, L, H, the ring base and the frame starts all multiples of 4): same additions in
+// the same order per sample, 16-byte loads, the index divisions shared by the four
+BS_HD void ola_quad(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, int x, const OlaGeom &o,
+                    const float *frames, const float *ringOld, float *ringNew) {
+  const int L = g.L, H = g.H;
+  int p = o.rbModL + x; p -= (p / L) * L;
+  f4 acc = {0.f, 0.f, 0.f, 0.f};
+  if (x < L) acc = *(const f4 *)(ringOld + p);
+  if (o.addFrames) {
+    int tLo = (x - L >= 0 ? (x - L) / H + 1 : 0) - o.fsOff, tHi = x / H - o.fsOff;
+    if (tLo < 0) tLo = 0;
+    if (tHi > o.nv - 1) tHi = o.nv - 1;
+    for (int t = tLo; t <= tHi; ++t) {
+      const f4 v = *(const f4 *)(frames + ((size_t)t * g.C + c) * L + (x - (t + o.fsOff) * H));
+      acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
+    }
+  }
+  if (x < o.xE1) {
+    const long long n = o.ringBase + x;
+    if (n < sd.nOut) {
+      f4 wp;
+      if (n + 3 < g.wpStartLen) wp = *(const f4 *)(T.wpStart + n);
+      else if (n >= g.wpStartLen) { int q = o.wpPhase + x; q -= (q / H) * H; wp = *(const f4 *)(T.wpSteady + q); }
+      else {   // the quad straddles the end of the start-up table
+        float w[4];
+        for (int i = 0; i < 4; ++i) { const long long ni = n + i; int q = o.wpPhase + x + i; q -= (q / H) * H; w[i] = ni < g.wpStartLen ? T.wpStart[ni] : T.wpSteady[q]; }
+        wp.x = w[0]; wp.y = w[1]; wp.z = w[2]; wp.w = w[3];
+      }
+      float *dst = sd.out + (size_t)c * sd.outStride + (n - sd.outBase);
+      const float r0 = acc.x / wp.x, r1 = acc.y / wp.y, r2 = acc.z / wp.z, r3 = acc.w / wp.w;
+      dst[0] = r0;
+      if (n + 1 < sd.nOut) dst[1] = r1;
+      if (n + 2 < sd.nOut) dst[2] = r2;
+      if (n + 3 < sd.nOut) dst[3] = r3;
+    }
+  } else *(f4 *)(ringNew + p) = acc;
+}
+BS_HHD bool ola_quad_ok(const DevGeom &g) { return (g.L % 4 == 0) && (g.H % 4 == 0) && (g.wpStartLen % 4 == 0); }
+
 BS_HD void ola_sample(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, int x, const OlaGeom &o,
                       const float *frames /* [slot][C][L] of this stream */, const float *ringOld, float *ringNew /* [L] */) {
   const int L = g.L, H = g.H;
@@ -465,8 +504,23 @@ BS_HD float smooth_pass_g(float *v, int n, float slew, float s) {
   return s;
 }
 
-// smem of the peaks stage (ints/floats): cpk[B/2+2] | peaks[B] | misc[16] | segCnt[256]
-BS_HHD size_t map_smem_floats(int B) { return (((size_t)(B / 2 + 2) + B + 16 + 256) + 3) & ~(size_t)3; }
+// smem of the peaks stage: energy[B] f32 | cpk[B/2+2] i32 | peaks[B] f32 | misc[16] i32 | wordCnt[W+1] i32 | mask[W+1] u32,
+// W = ceil(B/32)
+BS_HHD size_t map_smem_floats(int B) { return (((size_t)B + (B / 2 + 2) + B + 16 + 2 * ((B + 31) / 32 + 2)) + 3) & ~(size_t)3; }
+BS_HD int popc_hd(uint32_t x) {
+#ifdef BS_HOSTEMU
+  return __builtin_popcount(x);
+#else
+  return __popc(x);
+#endif
+}
+BS_HD int ffs_hd(uint32_t x) {   // index of the lowest set bit (x != 0)
+#ifdef BS_HOSTEMU
+  return __builtin_ctz(x);
+#else
+  return __ffs((int)x) - 1;
+#endif
+}
 
 // peaks: findPeaks + updateOutputMap from the band energies and their smoothed copy (both in global memory); for
 // auto-detect formant blocks also the spectral-peak pick feeding the base estimate
@@ -475,32 +529,50 @@ BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, 
   const int B = g.B;
   const bool mapped = rec.flags & kMapped;
   const float fN = (float)(uint32_t)g.N;
-  int *cpk = (int *)sm;
+  const int nWords = (B + 31) / 32;
+  float *smE = sm;
+  int *cpk = (int *)(smE + B);
   float *peaksG = (float *)(cpk + (B / 2 + 2));
   int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] monotone flag
-  int *segCnt = misc + 16;           // [nt] run starts per thread segment
+  int *wordCnt = misc + 16;          // run starts per 32-bin word, then their exclusive prefix sum
+  uint32_t *mask = (uint32_t *)(wordCnt + (nWords + 2));   // bit k&31 of word k>>5: energy[k] > smoothed[k]
   if (mapped) {
-    // findPeaks (W#48 8560-8700): a peak = a maximal run of bins with energy > smoothed.  Runs are independent, so every
-    // thread takes the runs that START in its segment of bins (and follows them past the segment end); the peak index is
-    // the number of run starts before it (counted per segment, then prefix-summed).
-    {
-      const int seg = (B + nt - 1) / nt, k0 = tid * seg, k1 = (k0 + seg < B) ? k0 + seg : B;
-      int cnt = 0;
-      for (int k = k0; k < k1; ++k)
-        if (!(energy[k] <= smoothed[k]) && (k == 0 || energy[k - 1] <= smoothed[k - 1])) ++cnt;
-      segCnt[tid] = cnt;
-      BS_SYNC();
-      if (tid == 0) { int acc = 0; for (int i = 0; i < nt; ++i) { int c = segCnt[i]; segCnt[i] = acc; acc += c; } misc[0] = acc; misc[1] = 1; }
-      BS_SYNC();
-      int nP = segCnt[tid];
-      for (int k = k0; k < k1; ++k) {
-        if (!(!(energy[k] <= smoothed[k]) && (k == 0 || energy[k - 1] <= smoothed[k - 1]))) continue;
+    // findPeaks (W#48 8560-8700): a peak = a maximal run of bins with energy > smoothed.  Runs are independent: the
+    // comparison flags are packed into bit words (coalesced reads, warp ballot) and the energies staged in shared
+    // memory; every thread then owns the runs that START in its 32-bin word and follows them past the word's end; the
+    // peak index is the number of run starts before it (prefix sum over the words).
+#ifdef BS_HOSTEMU
+    for (int w = tid; w < nWords; w += nt) {
+      uint32_t m = 0;
+      for (int j = 0; j < 32 && 32 * w + j < B; ++j) { const int k = 32 * w + j; smE[k] = energy[k]; if (!(energy[k] <= smoothed[k])) m |= 1u << j; }
+      mask[w] = m;
+    }
+#else
+    for (int k0 = (tid & ~31); k0 < nWords * 32; k0 += nt) {   // nt is a multiple of 32: a warp covers one word per trip
+      const int k = k0 + (tid & 31);
+      bool ab = false;
+      if (k < B) { const float e = energy[k]; smE[k] = e; ab = !(e <= smoothed[k]); }
+      const uint32_t m = __ballot_sync(0xffffffffu, ab);
+      if ((tid & 31) == 0) mask[k0 >> 5] = m;
+    }
+#endif
+    BS_SYNC();
+    for (int w = tid; w < nWords; w += nt) {
+      const uint32_t m = mask[w], carry = w > 0 ? (mask[w - 1] >> 31) : 0u;
+      wordCnt[w] = popc_hd(m & ~((m << 1) | carry));
+    }
+    BS_SYNC();
+    if (tid == 0) { int acc = 0; for (int w = 0; w < nWords; ++w) { int c = wordCnt[w]; wordCnt[w] = acc; acc += c; } misc[0] = acc; misc[1] = 1; }
+    BS_SYNC();
+    for (int w = tid; w < nWords; w += nt) {
+      const uint32_t m = mask[w], carry = w > 0 ? (mask[w - 1] >> 31) : 0u;
+      uint32_t starts = m & ~((m << 1) | carry);
+      int nP = wordCnt[w];
+      while (starts) {
+        const int k = 32 * w + ffs_hd(starts);
+        starts &= starts - 1;
         float sum = 0.f, wsum = 0.f;
-        for (int kk = k; kk < B; ++kk) {
-          float en = energy[kk];
-          if (en <= smoothed[kk]) break;
-          sum = en + sum; wsum = (en * (float)kk) + wsum;
-        }
+        for (int kk = k; kk < B && ((mask[kk >> 5] >> (kk & 31)) & 1u); ++kk) { const float en = smE[kk]; sum = en + sum; wsum = (en * (float)kk) + wsum; }
         float avg = wsum / sum;
         float f = (avg + 0.5f) / fN;
         float o = (map_freq(f, rec.pkMult, rec.pkLimit) * fN) + -0.5f;
@@ -508,7 +580,9 @@ BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, 
         cpk[nP] = trunc_i32(ceilf(o));
         ++nP;
       }
-      BS_SYNC();
+    }
+    BS_SYNC();
+    {
       const int nAll = misc[0];
       for (int i = tid + 1; i < nAll; i += nt) if (cpk[i] < cpk[i - 1]) misc[1] = 0;   // benign race: every writer stores 0
     }

@@ -64,7 +64,7 @@ if os.path.exists(rep):
             for w, i in idx:
                 f.write("%-72s %s %s\n" % (w, r[i], units[i]))
             try:
-                name = r[hdr.index("Kernel Name")].split("(")[0]
+                name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].strip()
                 def b(col):
                     v = float(r[hdr.index(col)].replace(",", "")); u = units[hdr.index(col)]
                     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
@@ -75,6 +75,6 @@ if os.path.exists(rep):
     tp = os.path.join(P, "traffic.json")
     cur = json.load(open(tp)) if os.path.exists(tp) else {}
     for k, v in traffic.items():
-        cur[k] = sum(v) / len(v)
-    cur["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch from the latest ncu --set full capture of each kernel (profile workload, see profiles/*_top_kernel_ncu.txt)"
+        cur[k] = max(v)          # the fullest captured launch (a whole chunk)
+    cur["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of the fullest captured launch (one whole chunk: 256 streams x 256 blocks) in the latest ncu --set full capture of each kernel, see profiles/*_top_kernel_ncu.txt"
     json.dump(cur, open(tp, "w"), indent=1, sort_keys=True)
