@@ -792,7 +792,9 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
     span("map_energy_kernel", nBlk * g.C, [&] {
       map_energy_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     // slices of slots whose smoother arrays (S * slice * B floats) stay L2 resident across the four sweeps
-    const int smSlice = (int)std::max<size_t>(1, std::min<size_t>((size_t)nSlots, ((size_t)80 << 20) / ((size_t)S * g.B * sizeof(float))));
+    // (measured: slicing to keep the arrays L2 resident leaves too few threads in flight to cover the load latency, so
+    // one launch covers the whole chunk and the sweeps stream through HBM)
+    const int smSlice = nSlots;
     auto smooth_all = [&](int which) {
       for (int t0 = 0; t0 < nSlots; t0 += smSlice) {
         const int nT = std::min(smSlice, nSlots - t0);
