@@ -82,50 +82,95 @@ BS_HD int trunc_i32(float x) { return fabsf(x) < 2147483648.0f ? (int)x : INT32_
 struct alignas(16) f4 { float x, y, z, w; };
 
 // ------------------------------------------------------------------------------------------------------------
-// radix-4 DIT passes on split arrays (W#21/W#34 forward, W#20/W#33 inverse), `outer` sub-transforms of length
-// `inner` side by side.  Data starts in (ar, ai); returns 0 if the result is in (ar, ai), 1 if in (br, bi).
+// One radix-4 butterfly of the reference's decimation-in-time pass (W#34 forward / W#33 inverse), in registers, in
+// place: (A, B, C, D) <- outputs 0..3.  Operation order is the reference's; twiddles are applied even when trivial.
+template <bool INV>
+BS_HD void bfly4(float &Ar, float &Ai, float &Br, float &Bi, float &Cr, float &Ci, float &Dr, float &Di, const cf tB, const cf tC, const cf tD) {
+  float dRe, bRe, cRe, dIm, bIm, cIm;
+  if (!INV) {
+    dRe = (Dr * tD.re) - (Di * tD.im); bRe = (Br * tB.re) - (Bi * tB.im); cRe = (Cr * tC.re) - (Ci * tC.im);
+    dIm = (Di * tD.re) + (Dr * tD.im); bIm = (Bi * tB.re) + (Br * tB.im); cIm = (Ci * tC.re) + (Cr * tC.im);
+  } else {
+    dRe = (Di * tD.im) + (Dr * tD.re); bRe = (Bi * tB.im) + (Br * tB.re); cRe = (Ci * tC.im) + (Cr * tC.re);
+    dIm = (Di * tD.re) - (Dr * tD.im); bIm = (Bi * tB.re) - (Br * tB.im); cIm = (Ci * tC.re) - (Cr * tC.im);
+  }
+  const float bdRe = dRe + bRe, acRe = cRe + Ar, bdIm = dIm + bIm, acIm = Ai + cIm;
+  const float x = INV ? (dIm - bIm) : (bIm - dIm), y = Ar - cRe;
+  const float z = INV ? (bRe - dRe) : (dRe - bRe), w = Ai - cIm;
+  Ar = bdRe + acRe; Ai = bdIm + acIm;
+  Br = x + y;       Bi = z + w;
+  Cr = acRe - bdRe; Ci = acIm - bdIm;
+  Dr = y - x;       Di = w - z;
+}
+
+// The reference's radix-4 DIT passes on split arrays (W#21/W#34 forward, W#20/W#33 inverse), `outer` sub-transforms of
+// length `inner` (a power of two) side by side.  Consecutive passes are fused two at a time: a thread takes the 16
+// inputs of four first-level butterflies, keeps their outputs in registers and feeds them straight into the four
+// second-level butterflies they belong to -- the same butterflies on the same values as two separate passes, one
+// shared-memory round trip and one barrier fewer.  All index arithmetic is shifts and masks.
+// Data starts in (ar, ai); returns 0 if the result is in (ar, ai), 1 if in (br, bi).
 template <bool INV>
 BS_HD int pow2_ffts(const DevGeom &g, const cf *tw, float *ar, float *ai, float *br, float *bi, int tid, int nt) {
   const int inner = g.inner, outer = g.outer;
   if (inner <= 1) return 0;
   int lg = 0; while ((1 << lg) < inner) ++lg;
   float *sr = ar, *si = ai, *dr = br, *di = bi;
-  int which = 0, size = 1;
+  int which = 0, lgSize = 0;
   if (lg & 1) {
     const int stride = inner >> 1, total = outer * stride;
     for (int idx = tid; idx < total; idx += nt) {
-      int sub = idx / stride, s = idx - sub * stride, p0 = sub * inner + s, p1 = p0 + stride;
+      int sub = idx >> (lg - 1), s = idx & (stride - 1), p0 = sub * inner + s, p1 = p0 + stride;
       float a_i = si[p0], b_i = si[p1], b_r = sr[p1], a_r = sr[p0];
       dr[p0] = b_r + a_r; di[p0] = b_i + a_i; dr[p1] = a_r - b_r; di[p1] = a_i - b_i;
     }
     BS_SYNC();
-    float *t; t = sr; sr = dr; dr = t; t = si; si = di; di = t; which ^= 1; size = 2;
+    float *t; t = sr; sr = dr; dr = t; t = si; si = di; di = t; which ^= 1; lgSize = 1;
   }
-  while (size < inner) {
-    size <<= 2;
-    const int stride = inner / size, q = size >> 2, step = inner / size, per = inner >> 2, total = outer * per;
-    for (int idx = tid; idx < total; idx += nt) {
-      int sub = idx / per, r = idx - sub * per, i = r / stride, s = r - i * stride, base = sub * inner;
-      cf tB = tw[i * step], tC = tw[2 * i * step], tD = tw[3 * i * step];
-      int pa = base + (4 * i) * stride + s;
-      float Ar = sr[pa], Ai = si[pa], Br = sr[pa + stride], Bi = si[pa + stride];
-      float Cr = sr[pa + 2 * stride], Ci = si[pa + 2 * stride], Dr = sr[pa + 3 * stride], Di = si[pa + 3 * stride];
-      float dRe, bRe, cRe, dIm, bIm, cIm;
-      if (!INV) {
-        dRe = (Dr * tD.re) - (Di * tD.im); bRe = (Br * tB.re) - (Bi * tB.im); cRe = (Cr * tC.re) - (Ci * tC.im);
-        dIm = (Di * tD.re) + (Dr * tD.im); bIm = (Bi * tB.re) + (Br * tB.im); cIm = (Ci * tC.re) + (Cr * tC.im);
-      } else {
-        dRe = (Di * tD.im) + (Dr * tD.re); bRe = (Bi * tB.im) + (Br * tB.re); cRe = (Ci * tC.im) + (Cr * tC.re);
-        dIm = (Di * tD.re) - (Dr * tD.im); bIm = (Bi * tB.re) - (Br * tB.im); cIm = (Ci * tC.re) - (Cr * tC.im);
+  while (lgSize < lg) {
+    if (lg - lgSize >= 4) {
+      // fused passes A (size 4*s0) and B (size 16*s0)
+      const int lgQA = lgSize, lgStrideA = lg - lgSize - 2, lgStrideB = lgStrideA - 2, lgQB = lgSize + 2;
+      const int strideA = 1 << lgStrideA, strideB = 1 << lgStrideB, qA = 1 << lgQA;
+      const int lgPer = lg - 4, total = outer << lgPer;            // items per sub-transform: qA * strideB = inner/16
+      for (int idx = tid; idx < total; idx += nt) {
+        const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), iA = r >> lgStrideB, sB = r & (strideB - 1), base = sub * inner;
+        float vr[4][4], vi[4][4];   // [a][j]
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const int p = base + ((4 * iA + j) << lgStrideA) + (a << lgStrideB) + sB; vr[a][j] = sr[p]; vi[a][j] = si[p]; }
+        {
+          const cf tB = tw[iA << lgStrideA], tC = tw[(2 * iA) << lgStrideA], tD = tw[(3 * iA) << lgStrideA];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) bfly4<INV>(vr[a][0], vi[a][0], vr[a][1], vi[a][1], vr[a][2], vi[a][2], vr[a][3], vi[a][3], tB, tC, tD);
+        }
+#pragma unroll
+        for (int jA = 0; jA < 4; ++jA) {
+          const int iB = iA + (jA << lgQA);
+          const cf tB = tw[iB << lgStrideB], tC = tw[(2 * iB) << lgStrideB], tD = tw[(3 * iB) << lgStrideB];
+          bfly4<INV>(vr[0][jA], vi[0][jA], vr[1][jA], vi[1][jA], vr[2][jA], vi[2][jA], vr[3][jA], vi[3][jA], tB, tC, tD);
+#pragma unroll
+          for (int jB = 0; jB < 4; ++jB) { const int p = base + ((iB + (jB << lgQB)) << lgStrideB) + sB; dr[p] = vr[jB][jA]; di[p] = vi[jB][jA]; }
+        }
       }
-      float bdRe = dRe + bRe, acRe = cRe + Ar, bdIm = dIm + bIm, acIm = Ai + cIm;
-      float x = INV ? (dIm - bIm) : (bIm - dIm), y = Ar - cRe;
-      float z = INV ? (bRe - dRe) : (dRe - bRe), w = Ai - cIm;
-      int po = base + i * stride + s, qs = q * stride;
-      dr[po] = bdRe + acRe;          di[po] = bdIm + acIm;
-      dr[po + qs] = x + y;           di[po + qs] = z + w;
-      dr[po + 2 * qs] = acRe - bdRe; di[po + 2 * qs] = acIm - bdIm;
-      dr[po + 3 * qs] = y - x;       di[po + 3 * qs] = w - z;
+      lgSize += 4;
+    } else {
+      // single pass (size 4*s0)
+      const int lgStride = lg - lgSize - 2, stride = 1 << lgStride, lgQ = lgSize, lgPer = lg - 2, total = outer << lgPer;
+      for (int idx = tid; idx < total; idx += nt) {
+        const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), i = r >> lgStride, s = r & (stride - 1), base = sub * inner;
+        const cf tB = tw[i << lgStride], tC = tw[(2 * i) << lgStride], tD = tw[(3 * i) << lgStride];
+        const int pa = base + ((4 * i) << lgStride) + s;
+        float Ar = sr[pa], Ai = si[pa], Br = sr[pa + stride], Bi = si[pa + stride];
+        float Cr = sr[pa + 2 * stride], Ci = si[pa + 2 * stride], Dr = sr[pa + 3 * stride], Di = si[pa + 3 * stride];
+        bfly4<INV>(Ar, Ai, Br, Bi, Cr, Ci, Dr, Di, tB, tC, tD);
+        const int po = base + (i << lgStride) + s, qs = 1 << (lgQ + lgStride);
+        dr[po] = Ar;          di[po] = Ai;
+        dr[po + qs] = Br;     di[po + qs] = Bi;
+        dr[po + 2 * qs] = Cr; di[po + 2 * qs] = Ci;
+        dr[po + 3 * qs] = Dr; di[po + 3 * qs] = Di;
+      }
+      lgSize += 2;
     }
     BS_SYNC();
     float *t; t = sr; sr = dr; dr = t; t = si; si = di; di = t; which ^= 1;
@@ -184,7 +229,18 @@ BS_HD void outer_stage(const DevGeom &g, const DevTables &T, float *dr, float *d
 }
 
 // position of packed sample j after the interleave step of the split FFT (plan types 1-5): j = i*outer + s -> s*inner + i
-BS_HD int deint(const DevGeom &g, int j) { return g.outer < 2 ? j : (j % g.outer) * g.inner + j / g.outer; }
+BS_HD int deint(const DevGeom &g, int j) {
+  switch (g.outer) {   // constant divisors: multiply-shift instead of a runtime division
+    case 1: return j;
+    case 2: return (j & 1) * g.inner + (j >> 1);
+    case 3: return (j % 3) * g.inner + j / 3;
+    case 4: return (j & 3) * g.inner + (j >> 2);
+    case 5: return (j % 5) * g.inner + j / 5;
+    case 6: return (j % 6) * g.inner + j / 6;
+    case 8: return (j & 7) * g.inner + (j >> 3);
+    default: return (j % g.outer) * g.inner + j / g.outer;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // analysis of one window of one channel (W#35): window, zero-phase rotate, zero-pad, modified real FFT.
