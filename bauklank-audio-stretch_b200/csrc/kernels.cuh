@@ -107,13 +107,17 @@ BS_HD void bfly4(float &Ar, float &Ai, float &Br, float &Bi, float &Cr, float &C
 // length `inner` (a power of two) side by side.  Consecutive passes are fused two at a time: a thread takes the 16
 // inputs of four first-level butterflies, keeps their outputs in registers and feeds them straight into the four
 // second-level butterflies they belong to -- the same butterflies on the same values as two separate passes, one
-// shared-memory round trip and one barrier fewer.  All index arithmetic is shifts and masks.
+// shared-memory round trip and one barrier fewer.  All index arithmetic is shifts and masks; for the common
+// geometries (LG = log2(inner), OUTER, NT = threads compile-time constants) every stride is an immediate and the pass
+// loop unrolls completely.  LG == 0: run-time geometry.
 // Data starts in (ar, ai); returns 0 if the result is in (ar, ai), 1 if in (br, bi).
-template <bool INV>
-BS_HD int pow2_ffts(const DevGeom &g, const cf *tw, float *ar, float *ai, float *br, float *bi, int tid, int nt) {
-  const int inner = g.inner, outer = g.outer;
+template <bool INV, int LG, int OUTER, int NT>
+BS_HD int pow2_ffts_t(const DevGeom &g, const cf *tw, float *ar, float *ai, float *br, float *bi, int tid, int ntRun) {
+  const int inner = LG ? (1 << LG) : g.inner, outer = LG ? OUTER : g.outer, nt = NT ? NT : ntRun;
   if (inner <= 1) return 0;
-  int lg = 0; while ((1 << lg) < inner) ++lg;
+  int lgRun = 0;
+  if (!LG) while ((1 << lgRun) < inner) ++lgRun;
+  const int lg = LG ? LG : lgRun;
   float *sr = ar, *si = ai, *dr = br, *di = bi;
   int which = 0, lgSize = 0;
   if (lg & 1) {
@@ -126,31 +130,35 @@ BS_HD int pow2_ffts(const DevGeom &g, const cf *tw, float *ar, float *ai, float 
     BS_SYNC();
     float *t; t = sr; sr = dr; dr = t; t = si; si = di; di = t; which ^= 1; lgSize = 1;
   }
-  while (lgSize < lg) {
+#pragma unroll
+  for (int stage = 0; stage < 8; ++stage) {
+    if (lgSize >= lg) break;
     if (lg - lgSize >= 4) {
       // fused passes A (size 4*s0) and B (size 16*s0)
       const int lgQA = lgSize, lgStrideA = lg - lgSize - 2, lgStrideB = lgStrideA - 2, lgQB = lgSize + 2;
-      const int strideA = 1 << lgStrideA, strideB = 1 << lgStrideB, qA = 1 << lgQA;
+      const int strideB = 1 << lgStrideB;
       const int lgPer = lg - 4, total = outer << lgPer;            // items per sub-transform: qA * strideB = inner/16
       for (int idx = tid; idx < total; idx += nt) {
-        const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), iA = r >> lgStrideB, sB = r & (strideB - 1), base = sub * inner;
+        const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), iA = r >> lgStrideB, sB = r & (strideB - 1);
+        const int base = sub * inner + (iA << (lgStrideA + 2)) + sB;
         float vr[4][4], vi[4][4];   // [a][j]
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const int p = base + ((4 * iA + j) << lgStrideA) + (a << lgStrideB) + sB; vr[a][j] = sr[p]; vi[a][j] = si[p]; }
+          for (int j = 0; j < 4; ++j) { const int p = base + (j << lgStrideA) + (a << lgStrideB); vr[a][j] = sr[p]; vi[a][j] = si[p]; }
         {
           const cf tB = tw[iA << lgStrideA], tC = tw[(2 * iA) << lgStrideA], tD = tw[(3 * iA) << lgStrideA];
 #pragma unroll
           for (int a = 0; a < 4; ++a) bfly4<INV>(vr[a][0], vi[a][0], vr[a][1], vi[a][1], vr[a][2], vi[a][2], vr[a][3], vi[a][3], tB, tC, tD);
         }
+        const int obase = sub * inner + (iA << lgStrideB) + sB;
 #pragma unroll
         for (int jA = 0; jA < 4; ++jA) {
           const int iB = iA + (jA << lgQA);
           const cf tB = tw[iB << lgStrideB], tC = tw[(2 * iB) << lgStrideB], tD = tw[(3 * iB) << lgStrideB];
           bfly4<INV>(vr[0][jA], vi[0][jA], vr[1][jA], vi[1][jA], vr[2][jA], vi[2][jA], vr[3][jA], vi[3][jA], tB, tC, tD);
 #pragma unroll
-          for (int jB = 0; jB < 4; ++jB) { const int p = base + ((iB + (jB << lgQB)) << lgStrideB) + sB; dr[p] = vr[jB][jA]; di[p] = vi[jB][jA]; }
+          for (int jB = 0; jB < 4; ++jB) { const int p = obase + (jA << (lgQA + lgStrideB)) + (jB << (lgQB + lgStrideB)); dr[p] = vr[jB][jA]; di[p] = vi[jB][jA]; }
         }
       }
       lgSize += 4;
@@ -176,6 +184,19 @@ BS_HD int pow2_ffts(const DevGeom &g, const cf *tw, float *ar, float *ai, float 
     float *t; t = sr; sr = dr; dr = t; t = si; si = di; di = t; which ^= 1;
   }
   return which;
+}
+// dispatch on the geometry: the presets and the kiosk's shipped configuration get fully specialised code
+template <bool INV>
+BS_HD int pow2_ffts(const DevGeom &g, const cf *tw, float *ar, float *ai, float *br, float *bi, int tid, int nt) {
+#ifndef BS_HOSTEMU
+  if (nt == 256) {
+    if (g.inner == 1024 && g.outer == 3) return pow2_ffts_t<INV, 10, 3, 256>(g, tw, ar, ai, br, bi, tid, nt);   // 48 kHz presetDefault
+    if (g.inner == 512 && g.outer == 5) return pow2_ffts_t<INV, 9, 5, 256>(g, tw, ar, ai, br, bi, tid, nt);     // 48 kHz presetCheaper
+    if (g.inner == 1024 && g.outer == 5) return pow2_ffts_t<INV, 10, 5, 256>(g, tw, ar, ai, br, bi, tid, nt);   // kiosk blockMs 200
+    if (g.inner == 2048 && g.outer == 3) return pow2_ffts_t<INV, 11, 3, 256>(g, tw, ar, ai, br, bi, tid, nt);   // 96 kHz presetDefault
+  }
+#endif
+  return pow2_ffts_t<INV, 0, 0, 0>(g, tw, ar, ai, br, bi, tid, nt);
 }
 
 // outer twiddles + final DFT-3 / DFT-5 across the sub-transforms, in place (plan steps 8 and 10/12; W#35 4404-4625
