@@ -544,25 +544,25 @@ BS_HD void map_energy(const DevGeom &g, const BlockRec rec, const cf *inp, float
 // One-pole smoother over an array in global memory, one thread per array: backward then forward (W#48 8420-8520).  The
 // next 16 samples are requested before the current 16 are processed, so a thread always has a load in flight.
 BS_HD float smooth_pass_g(float *v, int n, float slew, float s) {
-  constexpr int U = 16;
-  if (n % U != 0 || (((size_t)v) & 15) != 0) {   // odd sizes: plain loop
+  constexpr int U = 32, Q = U / 4;   // one whole 128-byte line per tile
+  if (n % U != 0 || (((size_t)v) & 127) != 0) {   // odd sizes: plain loop
     for (int i = n - 1; i >= 0; --i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
     for (int i = 0; i < n; ++i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
     return s;
   }
   f4 *v4 = (f4 *)v;
   const int nc = n / U;
-  f4 cur[4], nxt[4];
+  f4 cur[Q], nxt[Q];
   for (int dir = 0; dir < 2; ++dir) {
     int ch = dir == 0 ? nc - 1 : 0;
     const int step = dir == 0 ? -1 : 1;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cur[j] = v4[ch * 4 + j];
+    for (int j = 0; j < Q; ++j) cur[j] = v4[ch * Q + j];
     for (int it = 0; it < nc; ++it, ch += step) {
       const int chn = ch + step;
       if (it + 1 < nc) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) nxt[j] = v4[chn * 4 + j];
+        for (int j = 0; j < Q; ++j) nxt[j] = v4[chn * Q + j];
       }
       float *x = (float *)cur;
       if (dir == 0) {
@@ -573,9 +573,9 @@ BS_HD float smooth_pass_g(float *v, int n, float slew, float s) {
         for (int j = 0; j < U; ++j) { s = ((x[j] - s) * slew) + s; x[j] = s; }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v4[ch * 4 + j] = cur[j];
+      for (int j = 0; j < Q; ++j) v4[ch * Q + j] = cur[j];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+      for (int j = 0; j < Q; ++j) cur[j] = nxt[j];
     }
   }
   return s;
