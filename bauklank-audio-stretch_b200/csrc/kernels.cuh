@@ -269,20 +269,39 @@ BS_HD int deint(const DevGeom &g, int j) {
 BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, int tid, int nt) {
   const int M = g.M, N = g.N, L = g.L, off = g.off;
   float *ar = sm, *ai = sm + M, *br = sm + 2 * M, *bi = sm + 3 * M;
-  for (int j = tid; j < M; j += nt) {
-    float t[2];
-    for (int e = 0; e < 2; ++e) {
-      int n = 2 * j + e, i; float sgn;
-      if (n < L - off) { i = n + off; sgn = 1.f; }
-      else if (n >= N - off) { i = n - (N - off); sgn = -1.f; }
-      else { t[e] = 0.f; continue; }
-      float xv = (i >= w.lo && i < w.hi) ? x[w.start + i] : 0.f;
-      float wv = T.win[i];
-      t[e] = xv * (sgn < 0.f ? -wv : wv);
+  // window * sample for the packed pair (2j, 2j+1): second half of the window first (zero-phase rotation), the first
+  // half at the end with the half-bin shift's sign flip, zeros between.  Four pairs per trip, every global load of the
+  // trip issued before the first use.
+  constexpr int UN = 4;
+  for (int j0 = tid; j0 < M; j0 += nt * UN) {
+    float xv[UN][2], wv[UN][2]; cf rt[UN]; bool zr[UN][2];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * nt;
+      if (j < M) {
+        rt[u] = T.rot[j];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = 2 * j + e;
+          const bool inA = n < L - off, inC = n >= N - off, valid = inA || inC;
+          const int i = inA ? n + off : n - (N - off);
+          zr[u][e] = !valid;
+          xv[u][e] = (valid && i >= w.lo && i < w.hi) ? x[w.start + i] : 0.f;
+          const float wn = valid ? T.win[i] : 0.f;
+          wv[u][e] = inA ? wn : -wn;
+        }
+      }
     }
-    cf r = T.rot[j];
-    int d = deint(g, j);
-    ar[d] = (r.re * t[0]) - (r.im * t[1]); ai[d] = (r.im * t[0]) + (r.re * t[1]);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * nt;
+      if (j < M) {
+        const float t0 = zr[u][0] ? 0.f : xv[u][0] * wv[u][0], t1 = zr[u][1] ? 0.f : xv[u][1] * wv[u][1];
+        const cf r = rt[u];
+        const int d = deint(g, j);
+        ar[d] = (r.re * t0) - (r.im * t1); ai[d] = (r.im * t0) + (r.re * t1);
+      }
+    }
   }
   BS_SYNC();
   int which = pow2_ffts<false>(g, T.tw, ar, ai, br, bi, tid, nt);
@@ -309,15 +328,25 @@ BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float 
   const int M = g.M, N = g.N, L = g.L, off = g.off;
   float *ar = sm, *ai = sm + M, *br = sm + 2 * M, *bi = sm + 3 * M;
   const int half = M >> 1;
-  for (int i = tid; i <= half; i += nt) {
-    if (i == half - 1 && !(M & 1)) continue;
-    int j = M - 1 - i; cf u = T.untangle[i];
-    cf xi_ = X[i], xj_ = X[j];
-    float sI = xj_.im + xi_.im, dR = xi_.re - xj_.re;
-    float p = (sI * u.im) + (dR * u.re), sR = xj_.re + xi_.re;
-    float q = (sI * u.re) - (dR * u.im), dI = xi_.im - xj_.im;
-    int di_ = deint(g, i), dj = deint(g, j);
-    ar[di_] = p + sR; ai[di_] = q + dI; ar[dj] = sR - p; ai[dj] = q - dI;
+  constexpr int UN = 4;   // four bin pairs per trip, their global loads issued together
+  for (int i0 = tid; i0 <= half; i0 += nt * UN) {
+    cf uu[UN], xa[UN], xb[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + u * nt;
+      if (i <= half) { uu[u] = T.untangle[i]; xa[u] = X[i]; xb[u] = X[M - 1 - i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int i = i0 + u * nt;
+      if (i > half || (i == half - 1 && !(M & 1))) continue;   // pair half-1 is rewritten by pair half in the reference loop
+      const int j = M - 1 - i; const cf un = uu[u], xi_ = xa[u], xj_ = xb[u];
+      float sI = xj_.im + xi_.im, dR = xi_.re - xj_.re;
+      float p = (sI * un.im) + (dR * un.re), sR = xj_.re + xi_.re;
+      float q = (sI * un.re) - (dR * un.im), dI = xi_.im - xj_.im;
+      int di_ = deint(g, i), dj = deint(g, j);
+      ar[di_] = p + sR; ai[di_] = q + dI; ar[dj] = sR - p; ai[dj] = q - dI;
+    }
   }
   BS_SYNC();
   int which = pow2_ffts<true>(g, T.tw, ar, ai, br, bi, tid, nt);
