@@ -19,6 +19,14 @@ class Segment(C.Structure):
                 ("active", C.c_int32), ("formant_compensation", C.c_int32)]
 
 
+class Quantum(C.Structure):
+    """``bsb_quantum``: one render quantum of a resolved control trace."""
+    _fields_ = [("rate", C.c_double), ("input_samples_end", C.c_longlong), ("valid_start", C.c_longlong),
+                ("valid_end", C.c_longlong), ("semitones", C.c_float), ("tonality_limit", C.c_float),
+                ("formant_semitones", C.c_float), ("formant_base", C.c_float), ("formant_compensation", C.c_int32),
+                ("active", C.c_int32)]
+
+
 _BATCH_SIG = {
     "bsb_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "bsb_create_preset": (C.c_void_p, [C.c_int, C.c_double, C.c_int]),
@@ -33,6 +41,9 @@ _BATCH_SIG = {
     "bsb_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "bsb_add_kiosk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
                                 C.POINTER(Segment), C.c_int, C.c_uint32]),
+    "bsb_add_kiosk_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
+                                      C.POINTER(Quantum), C.c_longlong, C.c_uint32]),
+    "bsb_query_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "bsb_add_streaming": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int,
                                     C.c_longlong, C.POINTER(Segment), C.c_int, C.c_uint32]),
     "bsb_commit": (C.c_int, [C.c_void_p, C.c_int]),

@@ -45,6 +45,15 @@ class StreamingDrive:
         return self.n_out * self.n_calls
 
 
+@dataclass
+class TableDrive:
+    """Buffer playback resolved quantum by quantum (``worklet.WorkletTimeline.resolve`` -> ``table``)."""
+    n_out: int
+    table: object            # ctypes array of _capi.Quantum
+    quantum: int = 128
+    seed: int = 1
+
+
 def _ptr(a):
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
@@ -111,6 +120,15 @@ class BatchStretch:
             else:
                 assert clip.flags["C_CONTIGUOUS"] and clip.dtype == np.float32
             clip_len = int(clip.shape[1])
+            if isinstance(d, TableDrive):
+                n_out = int(d.n_out)
+                segs = d.table
+                out = outputs[i] if outputs is not None else _alloc_like(clip, self.channels, n_out)
+                self._check(self.lib.bsb_add_kiosk_table(self.h, i, _ptr(clip), clip_len, _ptr(out), n_out, int(d.quantum),
+                                                         d.table, len(d.table), int(d.seed) & 0xFFFFFFFF))
+                self._keep.append((clip, out, segs))
+                outs.append(out)
+                continue
             segs = (_capi.Segment * len(d.segments))(*d.segments)
             if isinstance(d, KioskDrive):
                 n_out = int(d.n_out)

@@ -175,9 +175,9 @@ inline void apply_segment_params(Params &p, const Segment &s, double sampleRate)
   p.setFormantBase((float)(s.formantBaseHz / sampleRate));
 }
 
-inline Window clip_window(long long start, int L, int validFrom, long long clipLen) {
+inline Window clip_window(long long start, int L, int validFrom, long long clipLen, long long clipFrom = 0) {
   Window w; w.start = start;
-  long long lo = std::max<long long>(validFrom, -start), hi = std::min<long long>(L, clipLen - start);
+  long long lo = std::max<long long>(validFrom, clipFrom - start), hi = std::min<long long>(L, clipLen - start);
   if (lo < 0) lo = 0;
   if (hi < lo) hi = lo;
   w.lo = (int)lo; w.hi = (int)hi;
@@ -215,6 +215,39 @@ inline void plan_kiosk(const Geometry &g, double sampleRate, int quantum, long l
       // ring after seek = [zeros(cap-n)][clip[end-n, end)]; cur = last L of it, prev = the L ending H earlier
       plan.windows[2 * bi + 0] = clip_window(end - L, L, (cap - n) - H, clipLen);
       plan.windows[2 * bi + 1] = clip_window(end - cap, L, cap - n, clipLen);
+    });
+    ctl.endCall(0);
+    pos += q;
+  }
+}
+
+// The same drive from a per-quantum table (what a host-side mirror of the worklet's time map resolves a control trace
+// into): for quantum k the f32 values the three setters receive (app/SignalsmithStretch.mjs:847-849), the segment's rate
+// and Math.round(inputTime * sampleRate) (:897), and the range of clip samples the buffer store holds at that moment.
+struct Quantum {
+  double rate; long long inputSamplesEnd, validStart, validEnd;
+  float semitones, tonalityLimit, formantSemitones, formantBase;
+  int formantCompensation, active;
+};
+inline void plan_kiosk_table(const Geometry &g, int quantum, long long nOut, const Quantum *qs, long long nQ, StreamPlan &plan) {
+  Control ctl(g);
+  const int L = g.L, H = g.H, cap = L + H;
+  const int bufLen = g.inLat + g.outLat;
+  plan.nOut = nOut;
+  long long pos = 0;
+  for (long long k = 0; pos < nOut && k < nQ; ++k) {
+    const Quantum &qq = qs[k];
+    const int q = (int)std::min<long long>(quantum, nOut - pos);
+    ctl.p.setTransposeSemitones(qq.semitones, qq.tonalityLimit);
+    ctl.p.setFormantSemitones(qq.formantSemitones, qq.formantCompensation ? 1 : 0);
+    ctl.p.setFormantBase(qq.formantBase);
+    const long long end = qq.inputSamplesEnd;
+    ctl.seek(qq.rate);
+    const int n = std::min(bufLen, cap);
+    ctl.run(plan, 0, q, 0, q, [&](int, int, int, bool, bool isNew, long long bi) {
+      if (!isNew) return;
+      plan.windows[2 * bi + 0] = clip_window(end - L, L, (cap - n) - H, qq.validEnd, qq.validStart);
+      plan.windows[2 * bi + 1] = clip_window(end - cap, L, cap - n, qq.validEnd, qq.validStart);
     });
     ctl.endCall(0);
     pos += q;

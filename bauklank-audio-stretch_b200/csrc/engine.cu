@@ -968,6 +968,33 @@ int bsb_add_kiosk(bsb_engine *e, int si, const float *dClip, long long clipLen, 
   return 0;
 }
 
+int bsb_add_kiosk_table(bsb_engine *e, int si, const float *dClip, long long clipLen, float *dOut, long long nOut, int quantum,
+                        const bsb_quantum *table, long long nQuanta, uint32_t seed) {
+  if (si < 0 || si >= (int)e->streams.size()) return e->fail("stream index out of range");
+  if (quantum < 1 || nOut < 0 || clipLen < 0 || !table) return e->fail("bad sizes");
+  if (nQuanta * quantum < nOut) return e->fail("the quantum table is shorter than the requested output");
+  std::vector<Quantum> qs((size_t)nQuanta);
+  for (long long k = 0; k < nQuanta; ++k) {
+    const bsb_quantum &t = table[k];
+    if (!t.active) return e->fail("inactive quanta (process(q,q) on silence) are not supported by the batched path");
+    if (t.valid_start < 0 || t.valid_end > clipLen || t.valid_end < t.valid_start) return e->fail("quantum %lld: valid range outside the clip", k);
+    qs[k] = Quantum{t.rate, t.input_samples_end, t.valid_start, t.valid_end, t.semitones, t.tonality_limit, t.formant_semitones,
+                    t.formant_base, t.formant_compensation, t.active};
+  }
+  Stream &s = e->streams[si];
+  s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
+  plan_kiosk_table(e->g, quantum, nOut, qs.data(), nQuanta, s.plan);
+  s.planned = true; e->committed = false;
+  return 0;
+}
+
+int bsb_query_geometry(int block, int interval, int split, int out[6]) {
+  if (block < 8 || interval < 1 || interval > block) return -1;
+  const Geometry g = make_geometry(1, block, interval, split);
+  out[0] = g.N; out[1] = g.B; out[2] = g.inLat; out[3] = g.outLat; out[4] = g.longStep; out[5] = g.inner * 16 + g.outer;
+  return 0;
+}
+
 int bsb_add_streaming(bsb_engine *e, int si, const float *dClip, long long clipLen, float *dOut, int nIn, int nOut, long long nCalls,
                       const bsb_segment *segs, int nSegs, uint32_t seed) {
   if (si < 0 || si >= (int)e->streams.size()) return e->fail("stream index out of range");

@@ -74,6 +74,20 @@ int bsb_begin(bsb_engine *e, int n_streams);
 /* buffer-playback drive: per render quantum `seek(bufferLength, rate); process(0, quantum)` (:883-943) */
 int bsb_add_kiosk(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, long long n_out,
                   int quantum, const bsb_segment *segments, int n_segments, uint32_t seed);
+/* The same drive, already resolved quantum by quantum (what a host-side mirror of the worklet's time map,
+ * app/SignalsmithStretch.mjs:603-744 + :840-897, turns a control trace into): for render quantum k the f32 values the
+ * three setters receive (:847-849), the segment's rate and Math.round(inputTime * sampleRate) (:897), and the range
+ * [valid_start, valid_end) of clip samples the worklet's buffer store holds at that moment (zero outside). */
+typedef struct bsb_quantum {
+  double rate;
+  long long input_samples_end, valid_start, valid_end;
+  float semitones, tonality_limit, formant_semitones, formant_base;
+  int32_t formant_compensation, active;
+} bsb_quantum;
+int bsb_add_kiosk_table(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, long long n_out,
+                        int quantum, const bsb_quantum *table, long long n_quanta, uint32_t seed);
+/* configure() arithmetic without a device (W#25): out = {fftSamples, bands, inputLatency, outputLatency, longStep, inner*16+outer} */
+int bsb_query_geometry(int block_samples, int interval_samples, int split_computation, int out[6]);
 /* streaming drive: `process(n_in, n_out)` n_calls times over a contiguous input (:870-882 generalised) */
 int bsb_add_streaming(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, int n_in,
                       int n_out, long long n_calls, const bsb_segment *segments, int n_segments, uint32_t seed);

@@ -181,3 +181,21 @@ def test_run_host_pipelined_copies(bs, golden):
         for n, y in zip(names, hout):
             assert_matches_golden(n, y.numpy(), golden)
     eng.close()
+
+
+def test_control_trace_through_the_quantum_table(bs):
+    """A worklet control trace (schedule calls with seeks, re-rates, a loop, formant changes) resolved on the host into
+    the per-quantum table and run on the GPU == the oracle driven quantum by quantum like WasmProcessor.process."""
+    import torch
+    import test_worklet
+    clip = refdrive.survey_clip(30000)
+    n_out = 40000
+    ref = bs.WorkletTimeline(48000.0).render(refdrive.PortEngine(), n_out, events=test_worklet._trace(), clip=clip)
+    tl = bs.WorkletTimeline(48000.0); tl.addBuffers(clip)
+    recs = tl.resolve(n_out, events=test_worklet._trace())
+    eng = bs.BatchStretch(2, 48000.0)
+    outs = eng.plan([torch.from_numpy(clip).cuda()], [bs.TableDrive(n_out, bs.WorkletTimeline.table(recs))])
+    eng.run(); torch.cuda.synchronize()
+    same, err, snr = cases.compare(outs[0].cpu().numpy(), ref)
+    assert err <= MAX_ABS_ERR and snr >= MIN_SNR_DB and same, (same, err, snr)
+    eng.close()
