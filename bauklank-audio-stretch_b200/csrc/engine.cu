@@ -192,17 +192,11 @@ BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
 // recomputes that step with the plain operators.  Within the safe range both give the correctly rounded result.
 __device__ __forceinline__ float mufu_rcp(float d) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
 __device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-// safe ranges (checked on the bit patterns, two integer instructions each): |numerator| and denominator in
-// [2^-60, 2^60] keep the reciprocal, the quotient and the FFMA residual far inside the normal range; an energy quotient
-// that feeds the square root needs energy >= 2^-40 on top (quotient >= 2^-100 > the 2^-101 bound of nvcc's fast path).
-__device__ __forceinline__ bool out_of_range(float v, unsigned loBits, unsigned hiBits) {   // v must be a positive normal in range
-  return (unsigned)(__float_as_int(v) - (int)loBits) > (hiBits - loBits);
-}
-constexpr unsigned kLo60 = 0x21800000u /* 2^-60 */, kHi60 = 0x5d800000u /* 2^60 */, kLo40 = 0x2b800000u /* 2^-40 */;
-__device__ __forceinline__ float div_fast(float x, float d, bool &slow, unsigned loNum = kLo60) {   // zero numerator passes through, as in div_pos
+__device__ __forceinline__ float div_fast(float x, float d, bool &slow) {   // zero numerator passes through, as in div_pos
   const bool z = (x == 0.f);
   const float xs = z ? 1.0f : x;
-  slow |= out_of_range(fabsf(xs), loNum, kHi60) || out_of_range(d, kLo60, kHi60);
+  const int ex = (__float_as_int(xs) >> 23) & 0xff, ed = (__float_as_int(d) >> 23) & 0xff;   // biased exponents
+  slow |= (unsigned)(ex - 32) > 190u || (unsigned)(ed - 32) > 190u || (unsigned)(ex - ed + 90) > 180u || d < 0.f;
   float r = mufu_rcp(d);
   const float t = __fmaf_rn(-d, r, 1.0f);
   r = __fmaf_rn(r, t, r);
@@ -211,10 +205,10 @@ __device__ __forceinline__ float div_fast(float x, float d, bool &slow, unsigned
   q = __fmaf_rn(r, e, q);
   return z ? x : q;
 }
-__device__ __forceinline__ float sqrt_fast(float x, bool &slow, bool checked = false) {           // zero passes through, as in sqrt_z
+__device__ __forceinline__ float sqrt_fast(float x, bool &slow) {           // zero passes through, as in sqrt_z
   const bool z = (x == 0.f);
   const float xs = z ? 1.0f : x;
-  if (!checked) slow |= (unsigned)(__float_as_int(xs) - 0x0d000000) > 0x727fffffu;
+  slow |= (unsigned)(__float_as_int(xs) - 0x0d000000) > 0x727fffffu;
   const float y = mufu_rsq(xs);
   float sq = __fmul_rn(xs, y);
   const float h = __fmul_rn(y, 0.5f);
@@ -235,7 +229,7 @@ __device__ __forceinline__ void make_output_fast(float energy, cf fb, float re, 
   const bool big = n2 > 1e-15f;
   const float divF = ((fb.re * fb.re) + 1e-15f) + (fb.im * fb.im);
   const float re2 = big ? re : fb.re, im2 = big ? im : fb.im, div = big ? n2 : divF;
-  const float sc = sqrt_fast(div_fast(energy, div, slow, kLo40), slow, true);   // energy in {0} U [2^-40, 2^60], div in [2^-60, 2^60]
+  const float sc = sqrt_fast(div_fast(energy, div, slow), slow);
   o.im = sc * im2; o.re = sc * re2;
 }
 // chain_bin (kernels.cuh) with selects instead of branches; same operations in the same order
