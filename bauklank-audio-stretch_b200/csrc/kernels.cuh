@@ -80,6 +80,7 @@ struct StateDev {
 
 BS_HD int trunc_i32(float x) { return fabsf(x) < 2147483648.0f ? (int)x : INT32_MIN; }
 struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(8) f2 { float x, y; };
 
 // ------------------------------------------------------------------------------------------------------------
 // One radix-4 butterfly of the reference's decimation-in-time pass (W#34 forward / W#33 inverse), in registers, in
@@ -201,14 +202,16 @@ BS_HD int pow2_ffts(const DevGeom &g, const cf *tw, float *ar, float *ai, float 
 
 // outer twiddles + final DFT-3 / DFT-5 across the sub-transforms, in place (plan steps 8 and 10/12; W#35 4404-4625
 // forward, W#48 10408-10628 inverse)
-template <bool INV>
-BS_HD void outer_stage(const DevGeom &g, const DevTables &T, float *dr, float *di, int tid, int nt) {
-  const int inner = g.inner, outer = g.outer;
+template <bool INV, int OUTER>
+BS_HD void outer_stage_t(const DevGeom &g, const DevTables &T, float *dr, float *di, int tid, int nt) {
+  const int inner = g.inner, outer = OUTER ? OUTER : g.outer;   // OUTER fixed: the per-sub-transform arrays stay in registers
   if (outer < 2) return;
   for (int i = tid; i < inner; i += nt) {
     float xr[5], xi[5];
     xr[0] = dr[i]; xi[0] = di[i];
-    for (int s = 1; s < outer; ++s) {
+#pragma unroll
+    for (int s = 1; s < (OUTER ? OUTER : 5); ++s) {
+      if (s >= outer) break;
       float vr = dr[i + s * inner], vi = di[i + s * inner];
       float wr = T.otr[i + inner * (s - 1)], wi = T.oti[i + inner * (s - 1)];
       if (!INV) { xr[s] = (wr * vr) - (wi * vi); xi[s] = (wi * vr) + (vi * wr); }
@@ -249,6 +252,13 @@ BS_HD void outer_stage(const DevGeom &g, const DevTables &T, float *dr, float *d
   BS_SYNC();
 }
 
+template <bool INV>
+BS_HD void outer_stage(const DevGeom &g, const DevTables &T, float *dr, float *di, int tid, int nt) {
+  if (g.outer == 3) outer_stage_t<INV, 3>(g, T, dr, di, tid, nt);
+  else if (g.outer == 5) outer_stage_t<INV, 5>(g, T, dr, di, tid, nt);
+  else outer_stage_t<INV, 0>(g, T, dr, di, tid, nt);
+}
+
 // position of packed sample j after the interleave step of the split FFT (plan types 1-5): j = i*outer + s -> s*inner + i
 BS_HD int deint(const DevGeom &g, int j) {
   switch (g.outer) {   // constant divisors: multiply-shift instead of a runtime division
@@ -270,37 +280,43 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
   const int M = g.M, N = g.N, L = g.L, off = g.off;
   float *ar = sm, *ai = sm + M, *br = sm + 2 * M, *bi = sm + 3 * M;
   // window * sample for the packed pair (2j, 2j+1): second half of the window first (zero-phase rotation), the first
-  // half at the end with the half-bin shift's sign flip, zeros between.  Four pairs per trip, every global load of the
-  // trip issued before the first use.
-  constexpr int UN = 4;
-  for (int j0 = tid; j0 < M; j0 += nt * UN) {
-    float xv[UN][2], wv[UN][2]; cf rt[UN]; bool zr[UN][2];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int j = j0 + u * nt;
-      if (j < M) {
-        rt[u] = T.rot[j];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int n = 2 * j + e;
-          const bool inA = n < L - off, inC = n >= N - off, valid = inA || inC;
-          const int i = inA ? n + off : n - (N - off);
-          zr[u][e] = !valid;
-          xv[u][e] = (valid && i >= w.lo && i < w.hi) ? x[w.start + i] : 0.f;
-          const float wn = valid ? T.win[i] : 0.f;
-          wv[u][e] = inA ? wn : -wn;
-        }
+  // half at the end with the half-bin shift's sign flip, zeros between.
+  const int nA = L - off, cStart = N - off;
+  if ((((nA | cStart | off) & 1) == 0) && w.lo == 0 && w.hi == L) {
+    // common case: the whole window lies inside the clip and the region boundaries fall between pairs -- no per-sample
+    // range checks, the two window coefficients of a pair come as one 8-byte load
+    const float *xs = x + w.start;
+    const int jA = nA >> 1, jC = cStart >> 1;
+    for (int j = tid; j < M; j += nt) {
+      float t0 = 0.f, t1 = 0.f;
+      if (j < jA) {
+        const int i = 2 * j + off;
+        const f2 wv = *(const f2 *)(T.win + i);
+        t0 = xs[i] * wv.x; t1 = xs[i + 1] * wv.y;
+      } else if (j >= jC) {
+        const int i = 2 * j - cStart;
+        const f2 wv = *(const f2 *)(T.win + i);
+        t0 = xs[i] * -wv.x; t1 = xs[i + 1] * -wv.y;
       }
+      const cf r = T.rot[j];
+      const int d = deint(g, j);
+      ar[d] = (r.re * t0) - (r.im * t1); ai[d] = (r.im * t0) + (r.re * t1);
     }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int j = j0 + u * nt;
-      if (j < M) {
-        const float t0 = zr[u][0] ? 0.f : xv[u][0] * wv[u][0], t1 = zr[u][1] ? 0.f : xv[u][1] * wv[u][1];
-        const cf r = rt[u];
-        const int d = deint(g, j);
-        ar[d] = (r.re * t0) - (r.im * t1); ai[d] = (r.im * t0) + (r.re * t1);
+  } else {
+    for (int j = tid; j < M; j += nt) {
+      float t[2];
+      for (int e = 0; e < 2; ++e) {
+        const int n = 2 * j + e;
+        const bool inA = n < nA, inC = n >= cStart;
+        if (!(inA || inC)) { t[e] = 0.f; continue; }
+        const int i = inA ? n + off : n - cStart;
+        const float xv = (i >= w.lo && i < w.hi) ? x[w.start + i] : 0.f;
+        const float wv = T.win[i];
+        t[e] = xv * (inA ? wv : -wv);
       }
+      const cf r = T.rot[j];
+      const int d = deint(g, j);
+      ar[d] = (r.re * t[0]) - (r.im * t[1]); ai[d] = (r.im * t[0]) + (r.re * t[1]);
     }
   }
   BS_SYNC();
@@ -352,15 +368,22 @@ BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float 
   int which = pow2_ffts<true>(g, T.tw, ar, ai, br, bi, tid, nt);
   float *rr = which ? br : ar, *ri = which ? bi : ai;
   outer_stage<true>(g, T, rr, ri, tid, nt);
+  const int nA = L - off, cStart = N - off;
+  const bool evenCuts = ((nA | cStart | off) & 1) == 0;
   for (int j = tid; j < M; j += nt) {
-    cf r = T.rot[j];
-    float t1 = (r.re * ri[j]) - (r.im * rr[j]);
-    float t0 = (r.im * ri[j]) + (r.re * rr[j]);
-    float tv[2] = {t0, t1};
-    for (int e = 0; e < 2; ++e) {
-      int n = 2 * j + e;
-      if (n < L - off) { int i = n + off; frame[i] = tv[e] * T.win[i]; }
-      else if (n >= N - off) { int i = n - (N - off); frame[i] = -(tv[e] * T.win[i]); }
+    const cf r = T.rot[j];
+    const float t1 = (r.re * ri[j]) - (r.im * rr[j]);
+    const float t0 = (r.im * ri[j]) + (r.re * rr[j]);
+    if (evenCuts) {   // both samples of the pair in the same half of the window: one 8-byte coefficient load, one 8-byte store
+      if (j < (nA >> 1)) { const int i = 2 * j + off; const f2 wv = *(const f2 *)(T.win + i); f2 o; o.x = t0 * wv.x; o.y = t1 * wv.y; *(f2 *)(frame + i) = o; }
+      else if (j >= (cStart >> 1)) { const int i = 2 * j - cStart; const f2 wv = *(const f2 *)(T.win + i); f2 o; o.x = -(t0 * wv.x); o.y = -(t1 * wv.y); *(f2 *)(frame + i) = o; }
+    } else {
+      const float tv[2] = {t0, t1};
+      for (int e = 0; e < 2; ++e) {
+        const int n = 2 * j + e;
+        if (n < nA) { const int i = n + off; frame[i] = tv[e] * T.win[i]; }
+        else if (n >= cStart) { const int i = n - cStart; frame[i] = -(tv[e] * T.win[i]); }
+      }
     }
   }
   BS_SYNC();
