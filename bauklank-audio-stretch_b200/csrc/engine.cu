@@ -854,7 +854,18 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   if (e->g.longStep < 1 || e->g.longStep > 32) { delete e; return nullptr; }
   make_tables(e->g, e->T);
   const Geometry &g = e->g;
-  e->dg = DevGeom{g.C, g.L, g.H, g.N, g.B, g.M, g.inner, g.outer, g.split, g.longStep, g.L >> 1, (int)e->T.wpStart.size(), 0};
+  e->dg = DevGeom{g.C, g.L, g.H, g.N, g.B, g.M, g.inner, g.outer, g.split, g.longStep, g.L >> 1, (int)e->T.wpStart.size(), 0, 1u, 0};
+  {   // multiply-shift division by `outer`, verified for every index it will see
+    bool ok = false;
+    for (int sh = 0; sh <= 20 && !ok; ++sh) {
+      const unsigned long long mg = (((unsigned long long)1 << sh) + g.outer - 1) / g.outer;
+      if (mg * (unsigned long long)(g.M > 0 ? g.M - 1 : 0) >= ((unsigned long long)1 << 32)) break;
+      ok = true;
+      for (int j = 0; j < g.M && ok; ++j) ok = (int)(((unsigned)j * (unsigned)mg) >> sh) == j / g.outer;
+      if (ok) { e->dg.divMagic = (unsigned)mg; e->dg.divShift = sh; }
+    }
+    if (!ok) { delete e; return nullptr; }
+  }
   e->dt.win = upload(e, e->T.win, e->owned); e->dt.tw = upload(e, e->T.tw, e->owned);
   e->dt.otr = upload(e, e->T.otr, e->owned); e->dt.oti = upload(e, e->T.oti, e->owned);
   e->dt.untangle = upload(e, e->T.untangle, e->owned); e->dt.rot = upload(e, e->T.rot, e->owned);

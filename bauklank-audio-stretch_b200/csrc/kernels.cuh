@@ -41,6 +41,7 @@ struct DevGeom {
   int C, L, H, N, B, M, inner, outer, split, longStep, off;  // off = L>>1 (analysis/synthesis offset)
   int wpStartLen;
   int incremental;  // blocks arrive one at a time (compat shim): always carry the input spectrum forward
+  unsigned divMagic; int divShift;   // j / outer == (j * divMagic) >> divShift for every j < M (checked at create time)
 };
 enum : int { kSynthEmit = 1, kSynthAdd = 2 };
 struct DevTables {
@@ -261,16 +262,8 @@ BS_HD void outer_stage(const DevGeom &g, const DevTables &T, float *dr, float *d
 
 // position of packed sample j after the interleave step of the split FFT (plan types 1-5): j = i*outer + s -> s*inner + i
 BS_HD int deint(const DevGeom &g, int j) {
-  switch (g.outer) {   // constant divisors: multiply-shift instead of a runtime division
-    case 1: return j;
-    case 2: return (j & 1) * g.inner + (j >> 1);
-    case 3: return (j % 3) * g.inner + j / 3;
-    case 4: return (j & 3) * g.inner + (j >> 2);
-    case 5: return (j % 5) * g.inner + j / 5;
-    case 6: return (j % 6) * g.inner + j / 6;
-    case 8: return (j & 7) * g.inner + (j >> 3);
-    default: return (j % g.outer) * g.inner + j / g.outer;
-  }
+  const int q = (int)(((unsigned)j * g.divMagic) >> g.divShift);   // j / outer without a division or a branch
+  return (j - q * g.outer) * g.inner + q;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -287,20 +280,29 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
     // range checks, the two window coefficients of a pair come as one 8-byte load
     const float *xs = x + w.start;
     const int jA = nA >> 1, jC = cStart >> 1;
-    for (int j = tid; j < M; j += nt) {
-      float t0 = 0.f, t1 = 0.f;
-      if (j < jA) {
-        const int i = 2 * j + off;
-        const f2 wv = *(const f2 *)(T.win + i);
-        t0 = xs[i] * wv.x; t1 = xs[i + 1] * wv.y;
-      } else if (j >= jC) {
-        const int i = 2 * j - cStart;
-        const f2 wv = *(const f2 *)(T.win + i);
-        t0 = xs[i] * -wv.x; t1 = xs[i + 1] * -wv.y;
+    constexpr int UN = 6;   // six pairs per trip: all their loads are issued before the first one is used
+    for (int j0 = tid; j0 < M; j0 += nt * UN) {
+      float x0[UN], x1[UN]; f2 wv[UN]; cf rt[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int j = j0 + u * nt;
+        const bool inA = j < jA, live = j < M && (inA || j >= jC);
+        const int i = live ? (inA ? 2 * j + off : 2 * j - cStart) : 0;
+        x0[u] = live ? xs[i] : 0.f; x1[u] = live ? xs[i + 1] : 0.f;
+        wv[u] = *(const f2 *)(T.win + i);
+        rt[u] = T.rot[j < M ? j : 0];
       }
-      const cf r = T.rot[j];
-      const int d = deint(g, j);
-      ar[d] = (r.re * t0) - (r.im * t1); ai[d] = (r.im * t0) + (r.re * t1);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int j = j0 + u * nt;
+        if (j < M) {
+          const bool inA = j < jA, live = inA || j >= jC;
+          const float t0 = live ? x0[u] * (inA ? wv[u].x : -wv[u].x) : 0.f, t1 = live ? x1[u] * (inA ? wv[u].y : -wv[u].y) : 0.f;
+          const cf r = rt[u];
+          const int d = deint(g, j);
+          ar[d] = (r.re * t0) - (r.im * t1); ai[d] = (r.im * t0) + (r.re * t1);
+        }
+      }
     }
   } else {
     for (int j = tid; j < M; j += nt) {
