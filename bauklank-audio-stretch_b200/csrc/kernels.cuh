@@ -275,10 +275,12 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
   // window * sample for the packed pair (2j, 2j+1): second half of the window first (zero-phase rotation), the first
   // half at the end with the half-bin shift's sign flip, zeros between.
   const int nA = L - off, cStart = N - off;
-  if ((((nA | cStart | off) & 1) == 0) && w.lo == 0 && w.hi == L) {
-    // common case: the whole window lies inside the clip and the region boundaries fall between pairs -- no per-sample
-    // range checks, the two window coefficients of a pair come as one 8-byte load
+  if (((nA | cStart | off) & 1) == 0) {
+    // common case: the region boundaries fall between pairs -- the two window coefficients of a pair come as one 8-byte
+    // load.  Samples outside [lo, hi) read as zero: the clip's ends, and the first H samples of every "previous" window
+    // of presetDefault, whose pre-roll is one interval short.
     const float *xs = x + w.start;
+    const int lo = w.lo, hi = w.hi;
     const int jA = nA >> 1, jC = cStart >> 1;
     constexpr int UN = 6;   // six pairs per trip: all their loads are issued before the first one is used
     for (int j0 = tid; j0 < M; j0 += nt * UN) {
@@ -288,7 +290,7 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
         const int j = j0 + u * nt;
         const bool inA = j < jA, live = j < M && (inA || j >= jC);
         const int i = live ? (inA ? 2 * j + off : 2 * j - cStart) : 0;
-        x0[u] = live ? xs[i] : 0.f; x1[u] = live ? xs[i + 1] : 0.f;
+        x0[u] = (live && i >= lo && i < hi) ? xs[i] : 0.f; x1[u] = (live && i + 1 >= lo && i + 1 < hi) ? xs[i + 1] : 0.f;
         wv[u] = *(const f2 *)(T.win + i);
         rt[u] = T.rot[j < M ? j : 0];
       }
