@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
                                                                  const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
                                                                  cf *specOut, StateDev st) {
   extern __shared__ float4 sm4[];
-  constexpr int NR = (9 + 8 * C + 3) & ~3, NRP = (NR + 31) & ~31, SO = 9 + 5 * C, TL = kChainTile;
+  constexpr int NR = (9 + 8 * C + 3) & ~3, NRP = (C == 2) ? 24 : ((NR + 31) & ~31), SO = 9 + 5 * C, TL = kChainTile;
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = blockDim.x >> 5, j = threadIdx.x;
   const StreamDev sd = streams[s];
   const int B = g.B, ls = g.longStep, D = ls + 2, OA = 1, R = chain_ring(ls), RM = R - 1;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
 #pragma unroll
       for (int i = 0; i < RQ; ++i) {
         const int e = i * 32 + lane, rr = e / RQ, cc = e % RQ;
-        stage[rr * RQ + (cc ^ (rr & (RQ - 1) & 7))] = ld[i];
+        stage[rr * RQ + ((RQ % 8) ? cc : (cc ^ (rr & 7)))] = ld[i];   // XOR swizzle where the row is a multiple of 8 pieces
       }
     };
     fetch(0); park(); __syncwarp();
@@ -388,10 +388,19 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
       const bool validQ = active && q >= 1 && q < B, validK = active && k >= 0 && k < B;
       if (!__any_sync(0xffffffffu, validQ || validK)) return;   // the whole warp is before its first or past its last bin
       float row[NR];
+      {
+        constexpr int NP = (C == 2) ? 6 : NR / 4;             // stored 16-byte pieces that carry fields
+        float phys[4 * NP];
 #pragma unroll
-      for (int i = 0; i < NR / 4; ++i) {
-        const float4 v = stage[lane * RQ + (i ^ (lane & (RQ - 1) & 7))];
-        row[4 * i] = v.x; row[4 * i + 1] = v.y; row[4 * i + 2] = v.z; row[4 * i + 3] = v.w;
+        for (int i = 0; i < NP; ++i) {
+          const float4 v = stage[lane * RQ + ((RQ % 8) ? i : (i ^ (lane & 7)))];
+          phys[4 * i] = v.x; phys[4 * i + 1] = v.y; phys[4 * i + 2] = v.z; phys[4 * i + 3] = v.w;
+        }
+        if (C == 2) unpack2_row(phys, row);
+        else {
+#pragma unroll
+          for (int i = 0; i < NR; ++i) row[i] = phys[i];
+        }
       }
       const int qc = q & (2 * TL - 1);                      // position of bin q in the two-tile window (slot 0 only)
       // S1 + S5 for bin q: previous block's output from the lane above (shuffle), the warp above (hand) or the state

@@ -841,7 +841,25 @@ BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
 // group the rows of the 32 blocks are interleaved along diagonals u = row + lane*lag, so that the 32 rows a warp
 // consumes in one step are ONE contiguous run (32 row pitches) instead of 32 cursors in 32 different blocks' records.
 // The row pitch is a whole number of 128-byte lines, so a row is always written and read as full lines.
-BS_HHD int nr_pitch(int C) { return (nr_floats(C) + 31) & ~31; }
+// Stereo rows are stored compactly in 24 floats = 96 bytes (three whole 32-byte sectors): the logical row has 25 fields;
+// the max-channel index travels in the sign bit of channel 1's energy (energies are never negative) and the fields
+// behind it move up by one.  Other channel counts keep the logical row, padded to whole 128-byte lines.
+BS_HHD int nr_pitch(int C) { return C == 2 ? 24 : (nr_floats(C) + 31) & ~31; }
+BS_HHD int nr_stage(int C) { return C == 2 ? 36 : nr_pitch(C) + 4; }   // row stride of preterms' shared-memory staging
+BS_HD float pack2_field(const float *logical, int f) {                 // physical field f of a stereo row
+  if (f < 8) return logical[f];
+  float v = logical[f + 1];
+  if (f == 13 && __float_as_int_hd(logical[8]) == 1) v = -v;            // logical[14] = energy of channel 1 (>= +0)
+  return v;
+}
+BS_HD void unpack2_row(const float *phys, float *logical) {            // 24 physical -> 25 logical fields (28 allocated)
+#pragma unroll
+  for (int f = 0; f < 8; ++f) logical[f] = phys[f];
+#pragma unroll
+  for (int f = 8; f < 24; ++f) logical[f + 1] = phys[f];
+  logical[8] = __int_as_float_hd((int)((unsigned)__float_as_int_hd(phys[13]) >> 31));
+  logical[14] = __int_as_float_hd(__float_as_int_hd(phys[13]) & 0x7fffffff);
+}
 BS_HHD int chain_lag(int longStep) { return longStep + 2; }
 BS_HHD size_t rec_group_floats(int B, int longStep, int C) { return (size_t)(rec_rows(B, longStep) + 31 * chain_lag(longStep)) * 32 * nr_pitch(C); }
 BS_HHD size_t rec_row_stride(int C) { return (size_t)32 * nr_pitch(C); }
@@ -854,7 +872,7 @@ BS_HHD size_t rec_slot_offset(int slot, int B, int longStep, int C) {
 // Rows are produced in tiles of kTermTile bins staged in shared memory, so that every record row leaves the SM as part
 // of one contiguous, 16-byte-vectorised burst (a row mixes two bins R0 apart, hence the R0 rows carried tile to tile).
 constexpr int kTermTile = 256;
-BS_HHD size_t preterms_smem_floats(int C, int longStep) { return (size_t)(kTermTile + longStep + 1) * (nr_pitch(C) + 4); }
+BS_HHD size_t preterms_smem_floats(int C, int longStep) { return (size_t)(kTermTile + longStep + 1) * nr_stage(C); }
 
 template <int CT>
 BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec rec, uint32_t rng0, const cf *inp,
@@ -864,7 +882,7 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
                           float *predEOut /* nullptr unless this is the stream's last block of the chunk */,
                           float *recRows /* row 0 of this block; rows are rec_row_stride apart */, float *sm, int tid, int nt) {
   const int C = CT > 0 ? CT : g.C, B = g.B, R0 = g.longStep + 1, SO = 9 + 5 * C, TB = kTermTile;
-  const int NRP = nr_pitch(C), NR = NRP + 4;   // NR: row stride in shared memory (pitch + 4 floats against bank conflicts)
+  const int NRP = nr_pitch(C), NR = nr_stage(C);   // NR: row stride of the staging rows (padded against bank conflicts)
   const size_t rowStride = rec_row_stride(C);
   const bool isNew = rec.flags & kNew;
   const cf *prv = isNew ? inPrev : inp;
@@ -944,9 +962,13 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
     // local rows [0, nOut) are complete: global rows k0 .. k0+nOut-1 (the last tile also flushes the R0 trailing rows)
     const bool lastTile = k0 + TB >= B;
     const int nOut = lastTile ? nb + R0 : TB;
-    for (int i = tid; i < nOut * (NRP / 4); i += nt) {   // whole 128-byte lines, 8 threads per line
+    for (int i = tid; i < nOut * (NRP / 4); i += nt) {   // whole sectors / lines, one 16-byte piece per thread
       const int r = i / (NRP / 4), f = i - r * (NRP / 4);
-      ((f4 *)(recRows + (size_t)(k0 + r) * rowStride))[f] = ((const f4 *)(sm + (size_t)r * NR))[f];
+      const float *lg = sm + (size_t)r * NR;
+      f4 v;
+      if (CT == 2) { v.x = pack2_field(lg, 4 * f); v.y = pack2_field(lg, 4 * f + 1); v.z = pack2_field(lg, 4 * f + 2); v.w = pack2_field(lg, 4 * f + 3); }
+      else v = ((const f4 *)lg)[f];
+      ((f4 *)(recRows + (size_t)(k0 + r) * rowStride))[f] = v;
     }
     BS_SYNC();
     if (!lastTile)   // chain parts of this tile's last R0 bins belong to the first R0 rows of the next tile
@@ -1023,13 +1045,21 @@ inline void chain_host(const DevGeom &g, const DevTables &T, const BlockRec *blo
     const bool isNew = blocks[t].flags & kNew;
     const float *rr = rec + rec_slot_offset(t, B, ls, C);
     cf *so = specOut + (size_t)t * C * B;
-    for (int q = 1; q < B; ++q)
+    float lg[(9 + 8 * C + 3) & ~3];
+    auto load_row = [&](size_t row) -> const float * {   // logical view of a stored row
+      const float *p = rr + row * NR;
+      if (C == 2) { unpack2_row(p, lg); return lg; }
+      return p;
+    };
+    for (int q = 1; q < B; ++q) {
+      const float *row = load_row((size_t)q);
       for (int c = 0; c < C; ++c) {
-        const float *b = rr + (size_t)q * NR + SO + 3 * c;
+        const float *b = row + SO + 3 * c;
         o5[(size_t)c * B + q] = s5_bin(stateOut[(size_t)c * B + q], isNew, T.specRot[q], b[0], b[1], b[2]);
       }
+    }
     for (int k = 0; k < B; ++k) {
-      const float *r = rr + (size_t)(k + R0) * NR;
+      const float *r = load_row((size_t)(k + R0));
       const int mc = __float_as_int_hd(r[8]);
       cf z = {0.f, 0.f}, out[C];
       chain_bin<C>(r, mc, k, B, ls, k > 0 ? so[(size_t)mc * B + k - 1] : z, k >= ls ? so[(size_t)mc * B + k - ls] : z,

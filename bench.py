@@ -168,8 +168,8 @@ def stage_bytes(name, g):
         "map_smooth_kernel": 4 * B * 8,               # per block: 4 sweeps over the smoothed array, read + write each
         "map_peaks_kernel": 8 * B + 8 * B,            # per block: energy + smoothed in, map out
         "map_fmapply_kernel": 4 * B + 8 * B,          # per channel-block: envelope in, input energy read + write
-        "preterms_kernel": 16 * B + 8 * B + 64 * B,   # per channel-block: cur+prev spectra, energy+map in, 128-byte record row / 2 channels out
-        "chain_kernel": 64 * B + 8 * B,               # per channel-block: record rows in, output spectrum out (phase state stays on chip)
+        "preterms_kernel": 16 * B + 8 * B + 48 * B,   # per channel-block: cur+prev spectra, energy+map in, 96-byte record row / 2 channels out
+        "chain_kernel": 48 * B + 8 * B,               # per channel-block: record rows in, output spectrum out (phase state stays on chip)
         "isynth_kernel": 8 * B + 4 * L,               # per channel-block: output spectrum in, windowed frame out
         "ola_kernel": 4 * L + 4 * H,                  # per channel-block: frame in, H output samples out
     }
