@@ -896,7 +896,11 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
     for (int i = tid; i < nb; i += nt) {
       const int k = k0 + i;
       float *ra = sm + (size_t)(i + R0) * NR, *rb = sm + (size_t)i * NR + SO;   // local rows: chain part R0 rows further down
-      const float ib = mapv[2 * k], fl = floorf(ib), grad = mapv[2 * k + 1];
+      // The loads below form three dependent levels (map entries -> per-channel gathers -> gathers of the maximum
+      // channel); everything inside a level is issued together, boundary cases are selected away afterwards.
+      const int kN = (k + 1 < B) ? k + 1 : k, kL = (k + longStep < B) ? k + longStep : k;
+      const float ib = mapv[2 * k], grad = mapv[2 * k + 1], ib1 = mapv[2 * kN], ibL = mapv[2 * kL];
+      const float fl = floorf(ib);
       const int low = trunc_i32(fl); const float fr = ib - fl;
       const float gpos = grad > 0.f ? grad : 0.f;
       int lowP = 0; float frP = 0.f, gP = 0.f;
@@ -924,37 +928,28 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
       }
       ra[8] = __int_as_float_hd(mc);
       const cf *ic = inp + (size_t)mc * B;
-      // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep ...
+      // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep and downward neighbours k+1,
+      // k+longStep (whose predIn is re-interpolated here for channel mc).  With random time factors (timeFactor > 2)
+      // the "up" pair and the "down" pair each draw one value, in bin order.
+      float btfU = tf, btfD = tf;
+      if (randomTF) {
+        if (k > 0) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k)); btfU = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
+        if (k < B - 1) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k + 1)); btfD = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
+      }
+      const float xU1 = ib - btfU, xUL = ib - (btfU * fLong), xD1 = ib1 - btfD, xDL = ibL - (btfD * fLong);
+      const float fl1 = floorf(ib1), flL = floorf(ibL);
+      const int lU1 = trunc_i32(floorf(xU1)), lUL = trunc_i32(floorf(xUL)), lD1 = trunc_i32(floorf(xD1)), lDL = trunc_i32(floorf(xDL));
+      const cf dU1 = lerp_c(ic, B, lU1, xU1 - (float)lU1), dUL = lerp_c(ic, B, lUL, xUL - (float)lUL);
+      const cf uN = lerp_c(ic, B, trunc_i32(fl1), ib1 - fl1), dD1 = lerp_c(ic, B, lD1, xD1 - (float)lD1);
+      const cf uL = lerp_c(ic, B, trunc_i32(flL), ibL - flL), dDL = lerp_c(ic, B, lDL, xDL - (float)lDL);
       float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
       if (k > 0) {
-        float btf = tf;
-        if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
-        float x = ib - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
-        cf d = lerp_c(ic, B, lo2, fr2);
-        u1 = (d.re * pIm) - (d.im * pRe); u0 = (d.im * pIm) + (d.re * pRe);
-        if (k >= longStep) {
-          x = ib - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
-          d = lerp_c(ic, B, lo2, fr2);
-          u2 = (d.im * pIm) + (d.re * pRe); u3 = (d.re * pIm) - (d.im * pRe);
-        }
+        u1 = (dU1.re * pIm) - (dU1.im * pRe); u0 = (dU1.im * pIm) + (dU1.re * pRe);
+        if (k >= longStep) { u2 = (dUL.im * pIm) + (dUL.re * pRe); u3 = (dUL.re * pIm) - (dUL.im * pRe); }
       }
-      // ... and downward neighbours k+1, k+longStep (their predIn is re-interpolated here for channel mc)
       if (k < B - 1) {
-        float btf = tf;
-        if (randomTF) { uint32_t x = minstd_jump(rng0, (uint32_t)(2 * k + 1)); btf = (rscale * (float)(uint32_t)(x - 1u)) + rlo; }
-        const float ib1 = mapv[2 * (k + 1)], fl1 = floorf(ib1);
-        const cf u = lerp_c(ic, B, trunc_i32(fl1), ib1 - fl1);
-        float x = ib1 - btf; int lo2 = trunc_i32(floorf(x)); float fr2 = x - (float)lo2;
-        cf d = lerp_c(ic, B, lo2, fr2);
-        d0 = (d.im * u.im) + (d.re * u.re); d1 = (d.re * u.im) - (d.im * u.re);
-        if (k < B - longStep) {
-          const int kk = k + longStep;
-          const float ibL = mapv[2 * kk], flL = floorf(ibL);
-          const cf uL = lerp_c(ic, B, trunc_i32(flL), ibL - flL);
-          x = ibL - (btf * fLong); lo2 = trunc_i32(floorf(x)); fr2 = x - (float)lo2;
-          d = lerp_c(ic, B, lo2, fr2);
-          d2 = (d.im * uL.im) + (d.re * uL.re); d3 = (d.re * uL.im) - (d.im * uL.re);
-        }
+        d0 = (dD1.im * uN.im) + (dD1.re * uN.re); d1 = (dD1.re * uN.im) - (dD1.im * uN.re);
+        if (k < B - longStep) { d2 = (dDL.im * uL.im) + (dDL.re * uL.re); d3 = (dDL.re * uL.im) - (dDL.im * uL.re); }
       }
       ra[0] = u0; ra[1] = u1; ra[2] = u2; ra[3] = u3; ra[4] = d0; ra[5] = d1; ra[6] = d2; ra[7] = d3;
     }
