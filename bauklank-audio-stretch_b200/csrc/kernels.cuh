@@ -845,7 +845,7 @@ BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
 // the max-channel index travels in the sign bit of channel 1's energy (energies are never negative) and the fields
 // behind it move up by one.  Other channel counts keep the logical row, padded to whole 128-byte lines.
 BS_HHD int nr_pitch(int C) { return C == 2 ? 24 : (nr_floats(C) + 31) & ~31; }
-BS_HHD int nr_stage(int C) { return C == 2 ? 36 : nr_pitch(C) + 4; }   // row stride of preterms' shared-memory staging
+BS_HHD int nr_stage(int C) { return C == 2 ? 29 : nr_pitch(C) + 4; }   // row stride of preterms' staging rows (odd for stereo: conflict-free scalar access)
 BS_HD float pack2_field(const float *logical, int f) {                 // physical field f of a stereo row
   if (f < 8) return logical[f];
   float v = logical[f + 1];
