@@ -176,7 +176,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 constexpr int kChainTile = 64;    // bins per staged tile of the carried state
-constexpr int kChainAhead = 3;    // steps by which the L2 prefetch of the record rows leads their load
 constexpr int kChainWarps = 8;    // warps per CTA: up to 256 consecutive blocks of one stream in flight
 BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
 BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
@@ -364,11 +363,6 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
 #pragma unroll
         for (int i = 0; i < RQ; ++i) ld[i] = __ldcs(src + i * 32);
       }
-      // ... and ask the L2 for the run three steps further on (one 128-byte line per lane): by the time its turn to be
-      // loaded comes, it no longer has to come from HBM
-      const int up = u + kChainAhead;
-      if (warpLive && up >= 0 && up < nDiag && lane < (32 * RQ * 16) / 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(grpRun + (size_t)up * (32 * RQ)) + lane * 128));
       const int r = u - lane * D;
       if (r >= 1 && r < B) rotNxt = specRot[r];
     };
