@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) map_energy_kernel(DevGeom g, const Stream
   else map_energy<0>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
 }
 
-// one thread per (stream, block): which = 0 band-energy smoothing (mapped blocks), 1 formant-envelope smoothing.
+// one thread per (stream, block): which = 0 band-energy smoothing (mapped blocks), 1 formant-envelope smoothing,
+// 2 formant auto-detect pick (each strictly serial over the bins of a block).
 // Launched over slices [t0, t0+nT) of the chunk's slots whose arrays fit the L2 together (four sweeps re-read them).
 __global__ void __launch_bounds__(32) map_smooth_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
                                                         long long slot0, int nSlots, int S, int t0, int nT, StateDev st, int which) {
@@ -98,9 +99,12 @@ __global__ void __launch_bounds__(32) map_smooth_kernel(DevGeom g, const StreamD
     float *v = st.smoothed + c.slot * g.B;
     float carry = smooth_pass_g(v, g.B, slew, 0.f);   // smoothEnergy steps 1,2: the carry runs through both
     smooth_pass_g(v, g.B, slew, carry);
-  } else {
+  } else if (which == 1) {
     if (!(c.rec.flags & kFormants)) return;
     fm_smooth(g, c.rec, fm_auto(c.rec) ? st.fmBase[c.slot] : 0.f, st.fm + c.slot * fm_pitch(g.B));
+  } else {
+    if (!fm_auto(c.rec)) return;
+    fm_auto_pick(g, st.energy + c.slot * g.B, st.fmAuto + 2 * c.slot);
   }
 }
 
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(128) map_peaks_kernel(DevGeom g, const StreamD
   extern __shared__ float4 sm4[];
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
   const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
-  if (!c.valid || !((c.rec.flags & kMapped) || fm_auto(c.rec))) return;
+  if (!c.valid || !(c.rec.flags & kMapped)) return;
   map_peaks(g, c.rec, st.energy + c.slot * g.B, st.smoothed + c.slot * g.B, st.map + c.slot * g.B * 2, st.fmAuto + 2 * c.slot, (float *)sm4,
             threadIdx.x, blockDim.x);
 }
@@ -686,8 +690,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
     }
     account("map_energy_kernel", nBlk * g.C);
     if (anyMapped) account("map_smooth_kernel", nBlk);
-    if (anyMapped || anyAuto) account("map_peaks_kernel", nBlk);
-    if (anyAuto) account("freqest_kernel", nBlk);
+    if (anyMapped) account("map_peaks_kernel", nBlk);
+    if (anyAuto) { account("map_smooth_kernel", 0); account("freqest_kernel", nBlk); }
     if (anyFormants) { account("map_smooth_kernel", 0); account("map_fmapply_kernel", nBlk * g.C); }
     for (int s = 0; s < S; ++s) {   // the map-stage kernels, per stream in block order
       const StreamDev &sd = e->hs[s];
@@ -703,8 +707,9 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
           float carry = smooth_pass_g(smo, g.B, slew, 0.f);
           smooth_pass_g(smo, g.B, slew, carry);
         }
-        if ((rec.flags & kMapped) || fm_auto(rec)) map_peaks(e->dg, rec, en, smo, mp, st.fmAuto + 2 * slot, sm, 0, 1);
+        if (rec.flags & kMapped) map_peaks(e->dg, rec, en, smo, mp, st.fmAuto + 2 * slot, sm, 0, 1);
         float base = 0.f;
+        if (fm_auto(rec)) fm_auto_pick(e->dg, en, st.fmAuto + 2 * slot);
         if (fm_auto(rec)) base = st.fmBase[slot] = freqest_step(st.freqEst + 2 * s, st.fmAuto + 2 * slot);
         if (rec.flags & kFormants) { fm_smooth(e->dg, rec, base, fm); fmA(e->dg, rec, rec2, fm, inE, 0, 1); }
       }
@@ -814,8 +819,9 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
       }
     };
     if (anyMapped) span("map_smooth_kernel", nBlk, [&] { smooth_all(0); });
-    if (anyMapped || anyAuto) span("map_peaks_kernel", nBlk, [&] {
+    if (anyMapped) span("map_peaks_kernel", nBlk, [&] {
       map_peaks_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
+    if (anyAuto) span("map_smooth_kernel", 0, [&] { smooth_all(2); });
     if (anyAuto) span("freqest_kernel", nBlk, [&] { freqest_kernel<<<(S + 63) / 64, 64, 0, q>>>(S, e->dStreams, e->dBlocks, slot0, nSlots, st); });
     if (anyFormants) {
       span("map_smooth_kernel", 0, [&] { smooth_all(1); });

@@ -572,7 +572,7 @@ BS_HD void make_output(float energy, cf fallback, float re, float im, float &ore
 //   freqest  (one thread per stream) leaky averages of the formant base over the blocks
 //   fmsmooth (one thread per block)  formant envelope smoothing
 //   fmapply  (bins in parallel)      formant envelope applied to the input energies
-BS_HHD int fm_pitch(int B) { return (B + 2 + 3) & ~3; }
+BS_HHD int fm_pitch(int B) { return (B + 2 + 31) & ~31; }   // whole 128-byte lines: the smoother's tiled path needs aligned rows
 BS_HHD bool fm_auto(const BlockRec &rec) { return (rec.flags & kFormants) && !(rec.fmBaseFreq > 0.f); }
 
 // energy: per bin.  energy[k] = sum over channels in channel order, exactly as the reference accumulates it.
@@ -758,30 +758,36 @@ BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, 
       mapv[2 * k] = ib; mapv[2 * k + 1] = gr;
     }
   }
-  if (fm_auto(rec) && tid == 0) {   // `energy` holds the channel-summed input energy = the formant metric before its sqrt
-    const float *fm = energy;
-    auto at = [&](int i) { return i < B ? fm[i] : 0.f; };
-    int i1 = 0, i2 = 0, i3 = 0;
-    for (int i = 1; i <= B - 2; ++i) {
-      float v = fm[i];
-      if (v < fm[i - 1]) continue;
-      if (v <= at(i + 1)) continue;
-      if (v <= fm[i3]) continue;
-      if (fm[i2] >= v) { i3 = i; continue; }
-      if (fm[i1] < v) { i3 = i2; i2 = i1; i1 = i; continue; }
-      i3 = i2; i2 = i;
-    }
-    float top = fm[i1]; double dtop = (double)top;
-    if ((double)fm[i2] > (dtop * 0.1)) {
-      int d = i1 - i2; if (d < 0) d = -d;
-      if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
-      if (!((double)fm[i3] <= (dtop * 0.01))) {
-        d = i1 - i3; if (d < 0) d = -d;
-        if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
-      }
-    }
-    fmAuto[0] = top; fmAuto[1] = __int_as_float_hd(i1);
+}
+
+// formant auto-detect: the three largest local maxima of the channel-summed energy in scan order, then the harmonic
+// fix-ups (W#48 8820-8900).  Strictly sequential over the bins; one thread per block.
+BS_HD void fm_auto_pick(const DevGeom &g, const float *fm /* channel-summed energy [B] */, float *fmAuto /* [2]: top, i1 (int bits) */) {
+  const int B = g.B;
+  int i1 = 0, i2 = 0, i3 = 0;
+  float f1 = fm[0], f2 = f1, f3 = f1;          // fm[i1], fm[i2], fm[i3] kept in registers
+  float prev = fm[0], cur = B > 1 ? fm[1] : 0.f;
+  for (int i = 1; i <= B - 2; ++i) {
+    const float nxt = fm[i + 1], v = cur;
+    const float below = prev;
+    prev = cur; cur = nxt;
+    if (v < below) continue;
+    if (v <= nxt) continue;
+    if (v <= f3) continue;
+    if (f2 >= v) { i3 = i; f3 = v; continue; }
+    if (f1 < v) { i3 = i2; f3 = f2; i2 = i1; f2 = f1; i1 = i; f1 = v; continue; }
+    i3 = i2; f3 = f2; i2 = i; f2 = v;
   }
+  float top = f1; double dtop = (double)top;
+  if ((double)f2 > (dtop * 0.1)) {
+    int d = i1 - i2; if (d < 0) d = -d;
+    if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
+    if (!((double)f3 <= (dtop * 0.01))) {
+      d = i1 - i3; if (d < 0) d = -d;
+      if (d > i1 / 8 && d < (i1 * 7) / 8) i1 = i1 % d;
+    }
+  }
+  fmAuto[0] = top; fmAuto[1] = __int_as_float_hd(i1);
 }
 
 // the two leaky averages of the formant base estimate, one block (W#48 8900-8960); returns the base bin
