@@ -199,3 +199,26 @@ def test_control_trace_through_the_quantum_table(bs):
     same, err, snr = cases.compare(outs[0].cpu().numpy(), ref)
     assert err <= MAX_ABS_ERR and snr >= MIN_SNR_DB and same, (same, err, snr)
     eng.close()
+
+
+def test_edge_cases_empty_tiny_and_ragged_on_gpu(bs):
+    """Empty output, one output sample, a clip shorter than the block, ragged ends, playing past the clip's end --
+    all in one batch, each equal to the oracle."""
+    import torch
+    rng = np.random.default_rng(5)
+    specs = [(0, 3000, 1.0, 0.0), (1, 3000, 1.0, 3.0), (777, 100, 0.5, -2.0), (1441, 9000, 2.0, 5.0), (12345, 2000, 1.3, 0.0),
+             (20000, 20000, 0.9, 7.0)]
+    clips, drives, refs = [], [], []
+    for n_out, n_in, rate, st in specs:
+        clip = (0.2 * rng.standard_normal((2, n_in))).astype(np.float32)
+        clips.append(torch.from_numpy(clip).cuda())
+        drives.append(bs.KioskDrive(n_out, [bs.segment(rate=rate, semitones=st)]))
+        e = refdrive.PortEngine()
+        case = dict(drive="kiosk", sr=48000, n_out=n_out, preset="default", segments=[cases.seg(rate=rate, semitones=st)])
+        refs.append(cases.run_case(e, case, clip=clip)); e.close()
+    eng = bs.BatchStretch(2, 48000.0)
+    outs = eng.plan(clips, drives, chunk_blocks=3)
+    eng.run(); torch.cuda.synchronize()
+    for (n_out, *_), o, r in zip(specs, outs, refs):
+        assert tuple(o.shape) == (2, n_out) and cases.compare(o.cpu().numpy(), r)[0], n_out
+    eng.close()

@@ -101,3 +101,30 @@ def test_run_host_entry_point(emu, golden):
     eng.run_host([clip], ho)
     assert_matches_golden("KA5", ho[0], golden)
     eng.close()
+
+
+def test_edge_cases_empty_tiny_and_ragged(emu):
+    """Empty output, one output sample, a clip shorter than the block, output ending mid-interval and mid-quantum, and a
+    stream that plays far past the end of its clip -- in one batch next to a normal stream; each equals the oracle."""
+    rng = np.random.default_rng(5)
+    specs = [(0, 3000, 1.0, 0.0), (1, 3000, 1.0, 3.0), (777, 100, 0.5, -2.0), (1441, 9000, 2.0, 5.0), (12345, 2000, 1.3, 0.0),
+             (20000, 20000, 0.9, 7.0)]
+    clips, drives, refs = [], [], []
+    for n_out, n_in, rate, st in specs:
+        clip = (0.2 * rng.standard_normal((2, n_in))).astype(np.float32)
+        clips.append(clip)
+        drives.append(bs.KioskDrive(n_out, [bs.segment(rate=rate, semitones=st)]))
+        e = refdrive.PortEngine()
+        case = dict(drive="kiosk", sr=48000, n_out=n_out, preset="default", segments=[cases.seg(rate=rate, semitones=st)])
+        refs.append(cases.run_case(e, case, clip=clip)); e.close()
+    eng = bs.BatchStretch(2, 48000.0, lib=emu)
+    outs = eng.plan(clips, drives, chunk_blocks=3)
+    eng.run()
+    for (n_out, *_), o, r in zip(specs, outs, refs):
+        assert o.shape == (2, n_out) and cases.compare(np.array(o), r)[0], n_out
+    assert eng.stream_blocks(0) == 0 and eng.stream_blocks(1) == 1 and eng.stream_blocks(3) == 2
+    eng.close()
+    # a batch whose every stream is empty is legal and does nothing
+    eng = bs.BatchStretch(2, 48000.0, lib=emu)
+    outs = eng.plan([clips[0]], [bs.KioskDrive(0, [bs.segment()])]); eng.run(); eng.close()
+    assert outs[0].shape == (2, 0)
