@@ -222,3 +222,32 @@ def test_edge_cases_empty_tiny_and_ragged_on_gpu(bs):
     for (n_out, *_), o, r in zip(specs, outs, refs):
         assert tuple(o.shape) == (2, n_out) and cases.compare(o.cpu().numpy(), r)[0], n_out
     eng.close()
+
+
+@pytest.mark.parametrize("channels,block,interval,split,sr", [
+    (1, 1000, 250, 0, 32000), (3, 1536, 384, 1, 48000), (4, 2500, 700, 0, 44100), (5, 960, 240, 1, 96000),
+    (6, 3000, 1000, 0, 48000), (7, 514, 130, 1, 22050), (8, 4800, 1920, 1, 48000), (2, 5762, 1441, 0, 48000),
+    (2, 1111, 277, 1, 48000), (2, 14000, 3500, 0, 96000)])
+def test_other_channel_counts_and_geometries_against_live_oracle(channels, block, interval, split, sr, bs):
+    """Every chain_kernel<C> instantiation and the run-time FFT geometries (outer factors 1..8, odd block sizes that
+    take the generic pack / overlap-add paths), each with transpose + formant shift, against the CPU oracle."""
+    import torch
+    rng = np.random.default_rng(channels * 1000 + block)
+    n_in = int(0.9 * sr)
+    clip = (0.15 * rng.standard_normal((channels, n_in))).astype(np.float32)
+    t = np.arange(n_in) / sr
+    for c in range(channels):
+        clip[c] += (0.3 * np.sin(2 * np.pi * (180.0 + 40 * c) * t)).astype(np.float32)
+    rate = float(rng.choice([0.45, 0.8, 1.0, 1.7]))
+    n_out = int(0.8 * sr / max(rate, 0.6))
+    segs = [cases.seg(rate=rate, semitones=float(rng.integers(-7, 8)), tonality_hz=6000.0,
+                      formant_semitones=float(rng.integers(-2, 3)), formant_compensation=bool(channels % 2), formant_base_hz=0.0 if channels % 3 else 150.0)]
+    case = dict(drive="kiosk", sr=sr, n_out=n_out, block=(block, interval, split), segments=segs, seed=3)
+    e = refdrive.PortEngine(seed=3)
+    ref = cases.run_case(e, case, clip=clip); e.close()
+    eng = bs.BatchStretch(channels, sr, block_samples=block, interval_samples=interval, split_computation=bool(split))
+    outs = eng.plan([torch.from_numpy(clip).cuda()], [cases.batch_drive(bs, case, n_in)], chunk_blocks=40)
+    eng.run(); torch.cuda.synchronize()
+    same, err, snr = cases.compare(outs[0].cpu().numpy(), ref)
+    assert err <= MAX_ABS_ERR and snr >= MIN_SNR_DB and same, (same, err, snr)
+    eng.close()
