@@ -438,7 +438,8 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           ringO[((size_t)(k & RM) * C + c) * 32] = out[c];
-          __stcs(reinterpret_cast<float2 *>(so + (size_t)c * B + k), make_float2(out[c].re, out[c].im));
+          // two bins per 16-byte store: bin k-1 (still in `last`) and bin k, on odd k (B is even, so the last bin is odd)
+          if (k & 1) __stcs(reinterpret_cast<float4 *>(so + (size_t)c * B + k - 1), make_float4(last[c].re, last[c].im, out[c].re, out[c].im));
           if (isLast) stOut[(size_t)c * B + k] = out[c];
           if (lane == 31) hand[((size_t)(t & 1) * nW + warp) * C + c] = out[c];
           last[c] = out[c];
