@@ -346,10 +346,9 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
     cp_async_wait<0>();
     __syncthreads();
 
-    cf last[C], h1[C], h2[C];   // outputs of the previous three chain bins of this lane
+    cf last[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { last[c].re = last[c].im = 0.f; h1[c] = h2[c] = last[c]; }
-    const bool quadStore = (B & 3) == 0;
+    for (int c = 0; c < C; ++c) last[c].re = last[c].im = 0.f;
     // Record rows: the 32 rows a warp needs in one step are one contiguous run of 32 row pitches (wavefront-major
     // storage).  The warp fetches the run of step t+1 with fully coalesced 16-byte loads while it computes step t, then
     // parks it in its shared-memory stage (XOR-swizzled by row so that both the row-major writes and the row-per-lane
@@ -439,16 +438,8 @@ __global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevT
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           ringO[((size_t)(k & RM) * C + c) * 32] = out[c];
-          // four bins = one whole 32-byte sector per store pair: bins k-3..k-1 are still in registers (B % 4 == 0 here;
-          // otherwise two bins per store on odd k -- B is always even)
-          if (quadStore) {
-            if ((k & 3) == 3) {
-              float4 *dst = reinterpret_cast<float4 *>(so + (size_t)c * B + k - 3);
-              __stcs(dst, make_float4(h2[c].re, h2[c].im, h1[c].re, h1[c].im));
-              __stcs(dst + 1, make_float4(last[c].re, last[c].im, out[c].re, out[c].im));
-            }
-            h2[c] = h1[c]; h1[c] = last[c];
-          } else if (k & 1) __stcs(reinterpret_cast<float4 *>(so + (size_t)c * B + k - 1), make_float4(last[c].re, last[c].im, out[c].re, out[c].im));
+          // two bins per 16-byte store: bin k-1 (still in `last`) and bin k, on odd k (B is even, so the last bin is odd)
+          if (k & 1) __stcs(reinterpret_cast<float4 *>(so + (size_t)c * B + k - 1), make_float4(last[c].re, last[c].im, out[c].re, out[c].im));
           if (isLast) stOut[(size_t)c * B + k] = out[c];
           if (lane == 31) hand[((size_t)(t & 1) * nW + warp) * C + c] = out[c];
           last[c] = out[c];
