@@ -878,13 +878,7 @@ BS_HHD size_t rec_slot_offset(int slot, int B, int longStep, int C) {
 // Rows are produced in tiles of kTermTile bins staged in shared memory, so that every record row leaves the SM as part
 // of one contiguous, 16-byte-vectorised burst (a row mixes two bins R0 apart, hence the R0 rows carried tile to tile).
 constexpr int kTermTile = 256;
-// For one or two channels a tile's gathers are served from shared memory: the bins of the input spectra / energies
-// the tile can touch (a contiguous range, found from the tile's map entries) are staged with coalesced loads first.
-constexpr int kTermCap = 576;   // staged bins per tile: 256 output bins mapped down an octave, plus the long-step reach
-BS_HHD size_t preterms_view_floats(int C) { return C <= 2 ? (size_t)kTermCap * C * 5 + 8 : 0; }   // inp (2) + prev (2) + energy (1) per bin
-BS_HHD size_t preterms_smem_floats(int C, int longStep) {
-  return (((size_t)(kTermTile + longStep + 1) * nr_stage(C) + 3) & ~(size_t)3) + preterms_view_floats(C);
-}
+BS_HHD size_t preterms_smem_floats(int C, int longStep) { return (size_t)(kTermTile + longStep + 1) * nr_stage(C); }
 
 template <int CT>
 BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec rec, uint32_t rng0, const cf *inp,
@@ -903,53 +897,8 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
   const float tf = rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor;
   const float rlo = ((tf > 2.0f) ? 4.0f : 0.0f) - tf, rscale = (tf - rlo) * 0x1p-31f, fLong = (float)longStep;
   const bool randomTF = !(tf <= 2.0f);
-  // staged views (see preterms_view_floats): [C][cap] cf input, [C][cap] cf previous (already rotated), [C][cap] f32 energy
-  const bool canStage = C <= 2 && !randomTF;
-  float *vw = sm + ((((size_t)(TB + R0) * NR) + 3) & ~(size_t)3);
-  cf *inpS = (cf *)vw, *prvS = inpS + (size_t)C * kTermCap;
-  float *inES = (float *)(prvS + (size_t)C * kTermCap);
-  int *range = (int *)(inES + (size_t)C * kTermCap);   // [0] lowest, [1] highest bin index the tile's gathers can touch
   for (int k0 = 0; k0 < B; k0 += TB) {
     const int nb = (B - k0 < TB) ? B - k0 : TB;
-    // gather sources of this tile: global arrays, or their staged copies re-based so that view[bin] works unchanged
-    const cf *inpV[2] = {inp, inp + B}, *prvV[2] = {prv, prv + B};
-    const float *inEV[2] = {inEnergy, inEnergy + B};
-    const cf *rotV = prvRot;
-    if (canStage) {
-      if (tid == 0) { range[0] = INT32_MAX; range[1] = INT32_MIN; }
-      BS_SYNC();
-      for (int i = tid; i < nb; i += nt) {
-        const int k = k0 + i, kN = (k + 1 < B) ? k + 1 : k, kL = (k + longStep < B) ? k + longStep : k;
-        const float ib = mapv[2 * k], ib1 = mapv[2 * kN], ibL = mapv[2 * kL], tl = tf * fLong;
-        const float p[7] = {ib, ib - tf, ib - tl, ib1, ib1 - tf, ibL, ibL - tl};
-        int lo = INT32_MAX, hi = INT32_MIN;
-        for (int j = 0; j < 7; ++j) { const int f = trunc_i32(floorf(p[j])); lo = f < lo ? f : lo; hi = f > hi ? f : hi; }
-#ifdef BS_HOSTEMU
-        range[0] = lo < range[0] ? lo : range[0]; range[1] = hi + 1 > range[1] ? hi + 1 : range[1];
-#else
-        atomicMin(&range[0], lo); atomicMax(&range[1], hi + 1);
-#endif
-      }
-      BS_SYNC();
-      int lo = range[0] < 0 ? 0 : range[0], hi = range[1] + 1 > B ? B : range[1] + 1;
-      if (hi < lo) hi = lo;
-      BS_SYNC();   // everybody has read the range before thread 0 resets it for the next tile
-      if (hi - lo <= kTermCap) {
-        const int n = hi - lo;
-        for (int i = tid; i < C * n; i += nt) {
-          const int c = i / n, j = i - c * n, idx = lo + j;
-          const cf v = inp[(size_t)c * B + idx];
-          inpS[(size_t)c * kTermCap + j] = v;
-          prvS[(size_t)c * kTermCap + j] = isNew ? rot_prev(inPrev[(size_t)c * B + idx], T.specRot[idx]) : v;
-          inES[(size_t)c * kTermCap + j] = inEnergy[(size_t)c * B + idx];
-        }
-        for (int c = 0; c < C; ++c) {
-          inpV[c] = inpS + (size_t)c * kTermCap - lo; prvV[c] = prvS + (size_t)c * kTermCap - lo; inEV[c] = inES + (size_t)c * kTermCap - lo;
-        }
-        rotV = nullptr;
-      }
-      BS_SYNC();
-    }
     for (int i = tid; i < nb; i += nt) {
       const int k = k0 + i;
       float *ra = sm + (size_t)(i + R0) * NR, *rb = sm + (size_t)i * NR + SO;   // local rows: chain part R0 rows further down
@@ -968,9 +917,9 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
       // S5 coefficients (W#48 9314-9455) and the maximum-energy channel
       int mc = 0; float me = 0.f, pRe = 0.f, pIm = 0.f;
       for (int c = 0; c < C; ++c) {
-        const float en = lerp_f(C <= 2 ? inEV[c] : inEnergy + (size_t)c * B, B, low, fr) * gpos;
-        const cf in = lerp_c(C <= 2 ? inpV[c] : inp + (size_t)c * B, B, low, fr);
-        const cf pv = lerp_prev(C <= 2 ? prvV[c] : prv + (size_t)c * B, rotV, B, low, fr);
+        const float en = lerp_f(inEnergy + (size_t)c * B, B, low, fr) * gpos;
+        const cf in = lerp_c(inp + (size_t)c * B, B, low, fr);
+        const cf pv = lerp_prev(prv + (size_t)c * B, prvRot, B, low, fr);
         const float prevE = prevMap ? (lerp_f(prevInE + (size_t)c * B, B, lowP, frP) * gP) : prevEState[(size_t)c * B + k];
         if (predEOut) predEOut[(size_t)c * B + k] = en;
         const float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
@@ -984,7 +933,7 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
         ra[9 + 5 * c + 4] = (pRe * cIm) - (pIm * cRe);
       }
       ra[8] = __int_as_float_hd(mc);
-      const cf *ic = C <= 2 ? inpV[mc] : inp + (size_t)mc * B;
+      const cf *ic = inp + (size_t)mc * B;
       // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep and downward neighbours k+1,
       // k+longStep (whose predIn is re-interpolated here for channel mc).  With random time factors (timeFactor > 2)
       // the "up" pair and the "down" pair each draw one value, in bin order.
