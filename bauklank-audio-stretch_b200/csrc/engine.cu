@@ -13,6 +13,7 @@
 
 #ifndef BS_HOSTEMU
 #include <cuda_runtime.h>
+#include "chain.cuh"
 #endif
 
 namespace bs {
@@ -166,296 +167,6 @@ __global__ void __launch_bounds__(256) preterms_kernel(DevGeom g, DevTables T, c
   if (g.C == 2) preterms_block<2>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, sm, tid, nt);
   else if (g.C == 1) preterms_block<1>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, sm, tid, nt);
   else preterms_block<0>(g, T, rec, rng0, inp, prev, inE, mp, pInE, pMap, pE, pEo, rr, sm, tid, nt);
-}
-
-// ---- chain: one warp per stream.  Lane j walks block p0+j of the chunk, `D` bins behind lane j-1, so that the
-// previous block's output at bins k+1 and k+longStep has just been produced one lane up (warp shuffle) when bin k
-// needs it.  Lane 0 takes the previous block from the carried state, the last lane writes the state back.
-// All global inputs are staged with cp.async a few steps ahead: per-lane records in 16-byte pieces, the carried state
-// as coalesced 64-bin tiles.
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-constexpr int kChainTile = 64;    // bins per staged tile of the carried state
-constexpr int kChainWarps = 8;    // warps per CTA: up to 256 consecutive blocks of one stream in flight
-BS_HHD int chain_ring(int longStep) { int r = 4; while (r < longStep + 2) r <<= 1; return r; }
-BS_HHD size_t chain_smem_bytes(int C, int longStep, int warps) {
-  const size_t R = chain_ring(longStep);
-  return (size_t)warps * (2 * R * C * 32 * sizeof(cf) + 32 * (size_t)nr_pitch(C) * sizeof(float)) + 2 * (size_t)kChainTile * C * sizeof(cf) +
-         2 * (size_t)warps * C * sizeof(cf) + 16;
-}
-
-// ---- branch-free IEEE division / square root for the chain's hot loop.
-// `x / d` and `sqrtf(x)` compile to a MUFU seed + FFMA refinement guarded by a range check that branches to a slow
-// subroutine; eight such guarded regions per step serialise the instruction stream of a loop that is latency bound to
-// begin with.  The helpers below run the SAME refinement sequences (they are what nvcc emits on the fast path, see
-// profiles/), without the branch, and report operands outside a conservative safe range in `slow`; the caller then
-// recomputes that step with the plain operators.  Within the safe range both give the correctly rounded result.
-__device__ __forceinline__ float mufu_rcp(float d) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d)); return r; }
-__device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float div_fast(float x, float d, bool &slow) {   // zero numerator passes through, as in div_pos
-  const bool z = (x == 0.f);
-  const float xs = z ? 1.0f : x;
-  const int ex = (__float_as_int(xs) >> 23) & 0xff, ed = (__float_as_int(d) >> 23) & 0xff;   // biased exponents
-  slow |= (unsigned)(ex - 32) > 190u || (unsigned)(ed - 32) > 190u || (unsigned)(ex - ed + 90) > 180u || d < 0.f;
-  float r = mufu_rcp(d);
-  const float t = __fmaf_rn(-d, r, 1.0f);
-  r = __fmaf_rn(r, t, r);
-  float q = __fmaf_rn(xs, r, 0.0f);
-  const float e = __fmaf_rn(-d, q, xs);
-  q = __fmaf_rn(r, e, q);
-  return z ? x : q;
-}
-__device__ __forceinline__ float sqrt_fast(float x, bool &slow) {           // zero passes through, as in sqrt_z
-  const bool z = (x == 0.f);
-  const float xs = z ? 1.0f : x;
-  slow |= (unsigned)(__float_as_int(xs) - 0x0d000000) > 0x727fffffu;
-  const float y = mufu_rsq(xs);
-  float sq = __fmul_rn(xs, y);
-  const float h = __fmul_rn(y, 0.5f);
-  const float e = __fmaf_rn(-sq, sq, xs);
-  sq = __fmaf_rn(e, h, sq);
-  return z ? x : sq;
-}
-__device__ __forceinline__ cf s5_fast(cf o, bool isNew, cf r, float tRe, float tIm, float div, bool &slow) {
-  cf n; n.im = (o.im * r.re) + (o.re * r.im); n.re = (o.re * r.re) - (o.im * r.im);
-  if (isNew) o = n;
-  cf y;
-  y.im = div_fast((tIm * o.re) + (tRe * o.im), div, slow);
-  y.re = div_fast((tRe * o.re) - (tIm * o.im), div, slow);
-  return y;
-}
-__device__ __forceinline__ void make_output_fast(float energy, cf fb, float re, float im, cf &o, bool &slow) {
-  const float n2 = (im * im) + (re * re);
-  const bool big = n2 > 1e-15f;
-  const float divF = ((fb.re * fb.re) + 1e-15f) + (fb.im * fb.im);
-  const float re2 = big ? re : fb.re, im2 = big ? im : fb.im, div = big ? n2 : divF;
-  const float sc = sqrt_fast(div_fast(energy, div, slow), slow);
-  o.im = sc * im2; o.re = sc * re2;
-}
-// chain_bin (kernels.cuh) with selects instead of branches; same operations in the same order
-template <int C>
-__device__ __forceinline__ void chain_fast(const float *ra, int mc, int k, int B, int ls, cf oPrev, cf oLong, cf n1, cf nL, cf *out, bool &slow) {
-  float phIm = (ra[1] * oPrev.re) + (ra[0] * oPrev.im), phRe = (ra[0] * oPrev.re) - (ra[1] * oPrev.im);
-  if (!(k > 0)) { phIm = 0.f; phRe = 0.f; }
-  {
-    const float aIm = ((ra[2] * oLong.im) + phIm) + (ra[3] * oLong.re), aRe = ((ra[2] * oLong.re) + phRe) - (oLong.im * ra[3]);
-    if (k >= ls) { phIm = aIm; phRe = aRe; }
-  }
-  {
-    const float t4 = ra[4] * n1.re, t5 = ra[5] * n1.im, t8 = (ra[4] * n1.im) - (ra[5] * n1.re);
-    const float aIm = t8 + phIm, aRe = (t4 + phRe) + t5;
-    if (k < B - 1) { phIm = aIm; phRe = aRe; }
-  }
-  {
-    const float t6 = ra[6] * nL.re, t7 = ra[7] * nL.im, t9 = ra[6] * nL.im, t10 = nL.re * ra[7];
-    const float aIm = (t9 + phIm) - t10, aRe = (t6 + phRe) + t7;
-    if (k < B - ls) { phIm = aIm; phRe = aRe; }
-  }
-  float eMc = ra[9]; cf fbMc; fbMc.re = ra[10]; fbMc.im = ra[11];
-#pragma unroll
-  for (int c = 1; c < C; ++c) if (c == mc) { eMc = ra[9 + 5 * c]; fbMc.re = ra[9 + 5 * c + 1]; fbMc.im = ra[9 + 5 * c + 2]; }
-  cf om;
-  make_output_fast(eMc, fbMc, phRe, phIm, om, slow);
-  if (C == 2) {   // exactly one follower: pick its record fields by mc instead of computing both and discarding one
-    const bool m0 = (mc == 0);
-    const float tRe = m0 ? ra[9 + 5 + 3] : ra[9 + 3], tIm = m0 ? ra[9 + 5 + 4] : ra[9 + 4], eo = m0 ? ra[9 + 5] : ra[9];
-    cf fb; fb.re = m0 ? ra[9 + 5 + 1] : ra[9 + 1]; fb.im = m0 ? ra[9 + 5 + 2] : ra[9 + 2];
-    const float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
-    cf oo;
-    make_output_fast(eo, fb, qRe, qIm, oo, slow);
-    out[0] = m0 ? om : oo; out[C - 1] = m0 ? oo : om;
-    return;
-  }
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float tRe = ra[9 + 5 * c + 3], tIm = ra[9 + 5 * c + 4];
-    const float qIm = (tIm * om.re) + (tRe * om.im), qRe = (tRe * om.re) - (tIm * om.im);
-    cf fb; fb.re = ra[9 + 5 * c + 1]; fb.im = ra[9 + 5 * c + 2];
-    cf o;
-    bool slowF = false;
-    make_output_fast(ra[9 + 5 * c], fb, qRe, qIm, o, slowF);
-    if (c == mc) o = om; else slow |= slowF;
-    out[c] = o;
-  }
-}
-
-// self-test hook for the helpers above (tests/test_gpu_parity.py): q = x / d, r = sqrt(x), flags bit0/bit1 = slow
-__global__ void arith_selftest_kernel(const float *x, const float *d, float *q, float *r, int *flags, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  bool s1 = false, s2 = false;
-  q[i] = div_fast(x[i], d[i], s1);
-  r[i] = sqrt_fast(x[i], s2);
-  flags[i] = (s1 ? 1 : 0) | (s2 ? 2 : 0);
-}
-
-template <int C>
-__global__ void __launch_bounds__(32 * kChainWarps) chain_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                                 const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
-                                                                 cf *specOut, StateDev st) {
-  extern __shared__ float4 sm4[];
-  constexpr int NR = (9 + 8 * C + 3) & ~3, NRP = (C == 2) ? 24 : ((NR + 31) & ~31), SO = 9 + 5 * C, TL = kChainTile;
-  const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = blockDim.x >> 5, j = threadIdx.x;
-  const StreamDev sd = streams[s];
-  const int B = g.B, ls = g.longStep, D = ls + 2, OA = 1, R = chain_ring(ls), RM = R - 1;
-  const int rows = rec_rows(B, ls);
-  // per warp: ringN [R][C][32] (S5 prediction of the lane's block), ringO [R][C][32] (its new output)
-  cf *ringN = (cf *)sm4 + (size_t)warp * 2 * R * C * 32 + lane, *ringO = ringN + (size_t)R * C * 32;
-  cf *tile = (cf *)sm4 + (size_t)nW * 2 * R * C * 32;      // [2][C][TL]  carried state, the bins ahead of slot 0's S5 stage
-  cf *hand = tile + 2 * (size_t)C * TL;                    // [2][nW][C]  last lane of a warp -> lane 0 of the next
-  long long nv = sd.nBlocks - slot0; if (nv > nSlots) nv = nSlots;
-  if (nv <= 0) return;
-  const int nValid = (int)nv, perPass = 32 * nW;
-  cf *stOut = st.outSpec + (size_t)s * C * B;
-  const size_t CB = (size_t)C * B;
-  const cf *specRot = T.specRot;
-  const int handSrc = warp > 0 ? warp - 1 : 0;
-  // uninitialised ring entries are read (and discarded) by the select-based arithmetic: give them a defined value
-  for (int i = j; i < nW * 2 * R * C * 32; i += perPass) { cf z; z.re = z.im = 0.f; ((cf *)sm4)[i] = z; }
-  for (int i = j; i < 2 * C * TL + 2 * nW * C; i += perPass) { cf z; z.re = z.im = 0.f; tile[i] = z; }
-  __syncthreads();
-
-  for (int p0 = 0; p0 < nValid; p0 += perPass) {
-    const int slot = p0 + j;
-    const bool active = slot < nValid;
-    const int lastJ = min(perPass - 1, nValid - 1 - p0);
-    const bool isNew = active && (blocks[sd.blockBase + slot0 + slot].flags & kNew);
-    const bool isLast = (j == lastJ);
-    const size_t blk = (size_t)s * nSlots + (active ? slot : p0);
-    // this warp's record group (wavefront-major, see kernels.cuh): diagonal u holds row u - lane*D of lane's block
-    const float4 *grp4 = (const float4 *)(st.rec + ((size_t)s * ((nSlots + 31) / 32) + (p0 >> 5) + warp) * rec_group_floats(B, ls, C)) + (size_t)lane * (NRP / 4);
-    cf *so = specOut + blk * CB;
-    const int tEnd = (B - 1 + ls) + lastJ * D;
-
-    // stage tile `ti` of the carried state (bins [ti*TL, ti*TL+TL) of every channel), whole CTA, 16 bytes per thread
-    auto request_tile = [&](int ti) {
-      const int b0 = ti * TL;
-      if (b0 >= B) return;
-      cf *dst = tile + (size_t)(ti & 1) * C * TL;
-      for (int i = j; i < C * (TL / 2); i += perPass) {
-        const int c = i / (TL / 2), jj = (i - c * (TL / 2)) * 2;
-        if (b0 + jj < B) cp_async16(dst + (size_t)c * TL + jj, stOut + (size_t)c * B + b0 + jj);   // B is even
-      }
-    };
-    request_tile(0); request_tile(1);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-
-    cf last[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) last[c].re = last[c].im = 0.f;
-    // Record rows: the 32 rows a warp needs in one step are one contiguous run of 32 row pitches (wavefront-major
-    // storage).  The warp fetches the run of step t+1 with fully coalesced 16-byte loads while it computes step t, then
-    // parks it in its shared-memory stage (XOR-swizzled by row so that both the row-major writes and the row-per-lane
-    // reads are bank-conflict free); every lane then picks up its own row with a few LDS.128.
-    constexpr int RQ = NRP / 4;                               // float4 per row pitch
-    float4 *stage = (float4 *)(hand + 2 * (size_t)nW * C) + (size_t)warp * 32 * RQ;
-    const float4 *grpRun = grp4 - (size_t)lane * (NRP / 4);   // group base (grp4 carries this lane's row offset)
-    const int nDiag = rows + 31 * D;
-    const bool warpLive = p0 + 32 * warp < nValid;            // this warp's record group exists (it has at least one block)
-    float4 ld[RQ];
-    cf rotNxt; rotNxt.re = rotNxt.im = 0.f;
-    auto fetch = [&](int t) {     // diagonal of step t: u = t + OA - 32*warp*D; lane l's row there is u - l*D
-      const int u = t + OA - 32 * warp * D;
-      if (warpLive && u >= 0 && u < nDiag) {
-        const float4 *src = grpRun + (size_t)u * (32 * RQ) + lane;
-#pragma unroll
-        for (int i = 0; i < RQ; ++i) ld[i] = __ldcs(src + i * 32);
-      }
-      const int r = u - lane * D;
-      if (r >= 1 && r < B) rotNxt = specRot[r];
-    };
-    auto park = [&]() {           // element i*32+lane of the run = row (i*32+lane)/RQ, chunk (i*32+lane)%RQ
-#pragma unroll
-      for (int i = 0; i < RQ; ++i) {
-        const int e = i * 32 + lane, rr = e / RQ, cc = e % RQ;
-        stage[rr * RQ + ((RQ % 8) ? cc : (cc ^ (rr & 7)))] = ld[i];   // XOR swizzle where the row is a multiple of 8 pieces
-      }
-    };
-    fetch(0); park(); __syncwarp();
-    cf rot = rotNxt;
-    auto step = [&](int t) {
-      // slot 0's S5 stage reads bin t+OA this step.  The buffer of tile i-1 was last read one step BEFORE the step with
-      // (t+OA) % TL == 0; threads that are ahead may only overwrite it once everybody has passed the barrier after that
-      // read, i.e. from the step with (t+OA) % TL == 1 on.  The tile is complete long before it is needed; the wait
-      // only formalises that, one step ahead of its first use.
-      const int q0 = t + OA;
-      if (q0 > TL && (q0 % TL) == 1) { request_tile(q0 / TL + 1); cp_async_commit(); }
-      if ((q0 % TL) == TL - 1) cp_async_wait<0>();
-      __syncthreads();
-      const int tau = t - j * D, q = tau + OA, k = tau - ls;
-      const bool validQ = active && q >= 1 && q < B, validK = active && k >= 0 && k < B;
-      if (!__any_sync(0xffffffffu, validQ || validK)) return;   // the whole warp is before its first or past its last bin
-      float row[NR];
-      {
-        constexpr int NP = (C == 2) ? 6 : NR / 4;             // stored 16-byte pieces that carry fields
-        float phys[4 * NP];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          const float4 v = stage[lane * RQ + ((RQ % 8) ? i : (i ^ (lane & 7)))];
-          phys[4 * i] = v.x; phys[4 * i + 1] = v.y; phys[4 * i + 2] = v.z; phys[4 * i + 3] = v.w;
-        }
-        if (C == 2) unpack2_row(phys, row);
-        else {
-#pragma unroll
-          for (int i = 0; i < NR; ++i) row[i] = phys[i];
-        }
-      }
-      const int qc = q & (2 * TL - 1);                      // position of bin q in the two-tile window (slot 0 only)
-      // S1 + S5 for bin q: previous block's output from the lane above (shuffle), the warp above (hand) or the state
-      cf n5[C];
-      bool slowQ = false;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        cf o;
-        o.re = __shfl_up_sync(0xffffffffu, last[c].re, 1);
-        o.im = __shfl_up_sync(0xffffffffu, last[c].im, 1);
-        const cf oT = tile[((size_t)(qc / TL) * C + c) * TL + (qc % TL)];
-        const cf oH = hand[((size_t)((t & 1) ^ 1) * nW + handSrc) * C + c];
-        if (lane == 0) o = (warp == 0) ? oT : oH;
-        n5[c] = s5_fast(o, isNew, rot, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2], slowQ);
-        if (validQ && slowQ) n5[c] = s5_bin(o, isNew, rot, row[SO + 3 * c], row[SO + 3 * c + 1], row[SO + 3 * c + 2]);
-        if (validQ) ringN[((size_t)(q & RM) * C + c) * 32] = n5[c];
-      }
-      // S6 for bin k
-      const int mc = validK ? __float_as_int(row[8]) : 0;
-      cf oPrev = last[0];
-#pragma unroll
-      for (int c = 1; c < C; ++c) if (c == mc) oPrev = last[c];
-      const cf oLong = ringO[((size_t)((k - ls) & RM) * C + mc) * 32];
-      const cf n1 = ringN[((size_t)((k + 1) & RM) * C + mc) * 32];
-      const cf nL = ringN[((size_t)((k + ls) & RM) * C + mc) * 32];
-      cf out[C];
-      bool slowK = false;
-      chain_fast<C>(row, mc, k, B, ls, oPrev, oLong, n1, nL, out, slowK);
-      if (validK && slowK) chain_bin<C>(row, mc, k, B, ls, oPrev, oLong, n1, nL, out);
-      if (validK) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          ringO[((size_t)(k & RM) * C + c) * 32] = out[c];
-          // two bins per 16-byte store: bin k-1 (still in `last`) and bin k, on odd k (B is even, so the last bin is odd)
-          if (k & 1) __stcs(reinterpret_cast<float4 *>(so + (size_t)c * B + k - 1), make_float4(last[c].re, last[c].im, out[c].re, out[c].im));
-          if (isLast) stOut[(size_t)c * B + k] = out[c];
-          if (lane == 31) hand[((size_t)(t & 1) * nW + warp) * C + c] = out[c];
-          last[c] = out[c];
-        }
-      }
-    };
-    for (int t = 0; t <= tEnd; ++t) {
-      fetch(t + 1);                 // in flight during the whole step
-      step(t);
-      __syncwarp();                 // every lane has read its row of step t
-      park(); rot = rotNxt;
-      __syncwarp();
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-  }
 }
 
 // carry: the last analysed spectrum of a stream survives the chunk if the next chunk starts with a block that has no
