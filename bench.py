@@ -183,6 +183,28 @@ def stage_bytes(name, g):
     return table.get(name)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers of the e2e leg
+    are allocated next to it (first touch).  Best effort: returns the node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def main_gpu(args):
     import numpy as np
     import torch
@@ -195,6 +217,7 @@ def main_gpu(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU engine)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)                  # pinned host buffers on the GPU's own memory node (best effort)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout: one JSON line only
@@ -330,7 +353,7 @@ def main_gpu(args):
                 "x_realtime_per_gpu": value / world, "plan_seconds": plan_s,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 4) * world, "d2h_bytes_per_step": int(h_out.numel() * 4) * world,
                         "ms_per_step": ms2 / e2e_steps},
-                "gpu_launches": int(launches_tot), "roofline": roofline, "cpu_baseline": cb, "clocks": clocks}
+                "gpu_launches": int(launches_tot), "numa_node_rank0": numa, "roofline": roofline, "cpu_baseline": cb, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
