@@ -82,29 +82,90 @@ __global__ void __launch_bounds__(256) map_energy_kernel(DevGeom g, const Stream
   else map_energy<0>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
 }
 
-// one thread per (stream, block): which = 0 band-energy smoothing (mapped blocks), 1 formant-envelope smoothing,
-// 2 formant auto-detect pick (each strictly serial over the bins of a block).
-// Launched over slices [t0, t0+nT) of the chunk's slots whose arrays fit the L2 together (four sweeps re-read them).
-__global__ void __launch_bounds__(32) map_smooth_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
-                                                        long long slot0, int nSlots, int S, int t0, int nT, StateDev st, int which) {
+// ---- the one-pole smoothers.  One lane per block (the recurrence s <- s + (v[i]-s)*slew is strictly serial over the
+// bins), 32 blocks per warp in lock step.  A lane reading its own row straight from global memory costs the load/store
+// unit one line per lane per instruction, and that -- not HBM and not the arithmetic -- was what the kernel waited on.
+// So a warp moves a tile (32 rows x 128 bytes) with coalesced 16-byte accesses (four whole lines per instruction) and
+// transposes it through an XOR-swizzled shared-memory stage; each lane then picks up its own 32 samples with
+// conflict-free LDS.128.  Four sweeps (backward, forward, backward, forward: smoothEnergy steps 1 and 2 / the two
+// formant-envelope passes, W#48 8420-8520), the carry running through all of them.  Same operations in the same order
+// as smooth_pass_g (kernels.cuh), which stays for odd row lengths and for the serial emulation.
+constexpr int kSmoothWarps = 4;
+__device__ __forceinline__ void smooth4_warp(float *v /* this lane's row, nullptr = none */, int n, float slew, float4 *stage /* [32][8] */) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, sub = lane >> 3, cc = lane & 7, nt = n >> 5;
+  if (!__any_sync(full, v != nullptr)) return;
+  float4 *rp[8];                       // the eight rows this lane moves in the coalesced phases: rows i*4 + sub, chunk cc
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rp[i] = (float4 *)__shfl_sync(full, (unsigned long long)v, i * 4 + sub);
+  int co[8], ow[8];                    // stage positions: coalesced phase (row i*4+sub, chunk cc), own row (chunk j)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int r = i * 4 + sub; co[i] = r * 8 + (cc ^ (r & 7)); ow[i] = lane * 8 + (i ^ (lane & 7)); }
+  float s = 0.f;
+  float4 nxt[8];
+  for (int sweep = 0; sweep < 4; ++sweep) {
+    const bool back = !(sweep & 1);
+    const int step = back ? -1 : 1;
+    int tile = back ? nt - 1 : 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (rp[i]) nxt[i] = rp[i][tile * 8 + cc];
+    for (int it = 0; it < nt; ++it, tile += step) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) stage[co[i]] = nxt[i];
+      __syncwarp();
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 q = stage[ow[j]]; x[4 * j] = q.x; x[4 * j + 1] = q.y; x[4 * j + 2] = q.z; x[4 * j + 3] = q.w; }
+      if (it + 1 < nt) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (rp[i]) nxt[i] = rp[i][(tile + step) * 8 + cc];
+      }
+      if (back) {
+#pragma unroll
+        for (int j = 31; j >= 0; --j) { s = ((x[j] - s) * slew) + s; x[j] = s; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s = ((x[j] - s) * slew) + s; x[j] = s; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) stage[ow[j]] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float4 q = stage[co[i]]; if (rp[i]) rp[i][tile * 8 + cc] = q; }
+      __syncwarp();
+    }
+  }
+}
+
+// one lane per (stream, block), consecutive blocks of a stream side by side: which = 0 band-energy smoothing (mapped
+// blocks), 1 formant-envelope smoothing, 2 formant auto-detect pick (each strictly serial over the bins of a block).
+__global__ void __launch_bounds__(32 * kSmoothWarps) map_smooth_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks,
+                                                                       const BlockRec2 *blocks2, long long slot0, int nSlots, int S, int t0,
+                                                                       int nT, StateDev st, int which) {
+  __shared__ float4 stageAll[kSmoothWarps][32 * 8];
+  const int nTp = (nT + 31) & ~31;                       // whole warps per stream
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S * nT) return;
-  const int t = t0 + i / S, s = i % S;
-  if (t >= nSlots) return;
-  const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
-  if (!c.valid) return;
+  const int s = i / nTp, t = t0 + i % nTp;
+  SlotCtx c; c.valid = false;
+  if (s < S && t < t0 + nT && t < nSlots) c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
+  float4 *stage = stageAll[threadIdx.x >> 5];
+  const bool tiled = (g.B % 32) == 0;                    // rows are whole, aligned 128-byte lines
   if (which == 0) {
-    if (!(c.rec.flags & kMapped)) return;
+    const bool act = c.valid && (c.rec.flags & kMapped);
     const float fN = (float)(uint32_t)g.N, fH = (float)(uint32_t)g.H, ratio = fN / fH;
     const float slew = 1.0f / ((ratio * 0.5f) + 1.0f);
-    float *v = st.smoothed + c.slot * g.B;
-    float carry = smooth_pass_g(v, g.B, slew, 0.f);   // smoothEnergy steps 1,2: the carry runs through both
-    smooth_pass_g(v, g.B, slew, carry);
+    float *v = act ? st.smoothed + c.slot * g.B : nullptr;
+    if (tiled) smooth4_warp(v, g.B, slew, stage);
+    else if (act) {
+      float carry = smooth_pass_g(v, g.B, slew, 0.f);   // smoothEnergy steps 1,2: the carry runs through both
+      smooth_pass_g(v, g.B, slew, carry);
+    }
   } else if (which == 1) {
-    if (!(c.rec.flags & kFormants)) return;
-    fm_smooth(g, c.rec, fm_auto(c.rec) ? st.fmBase[c.slot] : 0.f, st.fm + c.slot * fm_pitch(g.B));
+    const bool act = c.valid && (c.rec.flags & kFormants);
+    if (tiled) smooth4_warp(act ? st.fm + c.slot * fm_pitch(g.B) : nullptr, g.B, act ? fm_slew(g, c.rec, fm_auto(c.rec) ? st.fmBase[c.slot] : 0.f) : 0.f, stage);
+    else if (act) fm_smooth(g, c.rec, fm_auto(c.rec) ? st.fmBase[c.slot] : 0.f, st.fm + c.slot * fm_pitch(g.B));
   } else {
-    if (!fm_auto(c.rec)) return;
+    if (!c.valid || !fm_auto(c.rec)) return;
     fm_auto_pick(g, st.energy + c.slot * g.B, st.fmAuto + 2 * c.slot);
   }
 }
@@ -276,8 +337,10 @@ struct bsb_engine {
   struct KStat { const char *name; double ms; long long launches, units; };
   std::vector<KStat> kstat;
   bool profiling = false;
-  bool overlap = false;            // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1 (two CUDA
-                                   // streams); measured to gain nothing on B200 -- every kernel is occupancy bound -- so off
+  bool overlap = true;             // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1 (two CUDA
+                                   // streams).  Gains nothing while every stream is live (each kernel fills the GPU alone), but
+                                   // once the shorter streams of a batch have ended the chain runs on a fraction of the SMs and
+                                   // the next chunk's front half fills the rest: 334 -> 301 ms on 256 x 60 s of mixed rates
   float *recBuf[2] = {nullptr, nullptr};
 #ifndef BS_HOSTEMU
   cudaStream_t sFront = nullptr, sBack = nullptr, sIn = nullptr, sOut = nullptr;
@@ -527,7 +590,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
         bool any = false;
         for (int s = 0; s < S && !any; ++s) any = slot0 + t0 < e->hs[s].nBlocks;
         if (!any) break;
-        map_smooth_kernel<<<(unsigned)(((size_t)S * nT + 31) / 32), 32, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, t0, nT, st, which);
+        const size_t nThr = (size_t)S * ((nT + 31) & ~31);
+        map_smooth_kernel<<<(unsigned)((nThr + 32 * kSmoothWarps - 1) / (32 * kSmoothWarps)), 32 * kSmoothWarps, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, t0, nT, st, which);
       }
     };
     if (anyMapped) span("map_smooth_kernel", nBlk, [&] { smooth_all(0); });

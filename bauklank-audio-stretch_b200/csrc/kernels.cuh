@@ -804,10 +804,13 @@ BS_HD float freqest_step(float *freqEst, const float *fmAuto) {
 
 // formant envelope smoothing, one thread per block (W#48 8962-9040): fm = sqrt(channel-summed energy), written by the
 // energy stage; slew from the base bin (fixed, or the auto-detected estimate)
-BS_HD void fm_smooth(const DevGeom &g, const BlockRec rec, float baseBinAuto, float *fm) {
+BS_HD float fm_slew(const DevGeom &g, const BlockRec rec, float baseBinAuto) {
   const float fN = (float)(uint32_t)g.N, base = rec.fmBaseFreq;
   const float baseBin = (base > 0.f) ? ((base * fN) + -0.5f) : baseBinAuto;
-  const float slew = (float)(1.0 / (((double)baseBin * 0.5) + 1.0));
+  return (float)(1.0 / (((double)baseBin * 0.5) + 1.0));
+}
+BS_HD void fm_smooth(const DevGeom &g, const BlockRec rec, float baseBinAuto, float *fm) {
+  const float slew = fm_slew(g, rec, baseBinAuto);
   const float st = smooth_pass_g(fm, g.B, slew, 0.f);
   smooth_pass_g(fm, g.B, slew, st);
 }
