@@ -110,6 +110,9 @@ class Control {
         int f0 = s0 + (mapped ? 5 : 1);
         stepFm0_ = formants ? f0 : -1;
         stepFm2_ = formants ? f0 + 2 : -1;
+        stepS6_ = f0 + (formants ? 3 : 0) + C;   // after the C preliminary-prediction steps
+        stepSyn_ = analysisSteps + specSteps + 1;
+        curNew_ = isNew; curRean_ = rean;
         BlockRec rec{};
         rec.flags = kValid | (isNew ? kNew : 0u) | (mapped ? kMapped : 0u) | (formants ? kFormants : 0u);
         rec.timeFactor = tf;
@@ -141,6 +144,16 @@ class Control {
     }
   }
   void endCall(int nIn) { prevInputOffset_ -= nIn; }
+  // How far the block under way has got (split computation spreads its steps over the interval): vertical-prediction
+  // steps (of 8) and synthesis steps (of C) already executed.  Without split computation every step ran at once.
+  void progress(int &nS6, int &nSyn) const {
+    nS6 = std::min(8, std::max(0, step_ - stepS6_)); nSyn = std::min(g_.C, std::max(0, step_ - stepSyn_));
+  }
+  int stepsDone() const { return step_; }
+  int stepS6() const { return stepS6_; }
+  int stepFinal() const { return stepSyn_ - 2; }   // "prevInput = input" (only blocks with a new spectrum have it)
+  bool curIsNew() const { return curNew_; }
+  bool curReanalysesPrev() const { return curRean_; }
   // `blockProcess = {}` of the silence gate (W#48 7842-7845) and of reset() (W#59)
   void resetBlockProcess() { since_ = 0xffffffffu; steps_ = 0; step_ = 0; cur_ = -1; }
   void resetAll() { resetBlockProcess(); prevInputOffset_ = -1; didSeek_ = false; }
@@ -162,7 +175,8 @@ class Control {
   int prevInputOffset_ = -1;
   bool didSeek_ = false;
   float seekTF_ = 0.f;
-  int stepPeaks_ = -1, stepFm0_ = -1, stepFm2_ = -1;
+  int stepPeaks_ = -1, stepFm0_ = -1, stepFm2_ = -1, stepS6_ = 0, stepSyn_ = 0;
+  bool curNew_ = false, curRean_ = false;
   long long cur_ = -1;
   int lastNew_ = -1;
   uint32_t rngBlocks_ = 0;

@@ -531,7 +531,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
     st.parity ^= 1;
   }
   if (stages & 2) {
-    if (synthMode & kSynthAdd) {
+    if (synthMode & (kSynthAdd | kSynthFrames)) {
       account("isynth_kernel", nBlk * g.C);
       for (int s = 0; s < S; ++s)
         for (int t = 0; t < nSlots && slot0 + t < e->hs[s].nBlocks; ++t)
@@ -540,8 +540,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
             synth_frame(e->dg, e->dt, e->specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, sm, 0, 1);
           }
     }
-    account("ola_kernel", nBlk * g.C);
-    for (int s = 0; s < S; ++s) {
+    if (!(synthMode & kSynthFrames)) account("ola_kernel", nBlk * g.C);
+    for (int s = 0; s < S && !(synthMode & kSynthFrames); ++s) {
       const StreamDev &sd = e->hs[s];
       long long nvl = std::min<long long>(nSlots, sd.nBlocks - slot0);
       if (nvl <= 0) continue;
@@ -556,7 +556,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
             ola_sample(e->dg, e->dt, sd, c, x, o, st.frames + (size_t)s * nSlots * g.C * g.L, st.ring[st.ringPar] + rc, st.ring[st.ringPar ^ 1] + rc);
       }
     }
-    st.ringPar ^= 1;
+    if (!(synthMode & kSynthFrames)) st.ringPar ^= 1;
   }
 #else
   const size_t smA = 4 * (size_t)g.M * sizeof(float);
@@ -617,15 +617,17 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
   }
   q = qB;
   if (stages & 2) {
-    if (synthMode & kSynthAdd)
+    if (synthMode & (kSynthAdd | kSynthFrames))
       span("isynth_kernel", nBlk * g.C, [&] {
         isynth_kernel<<<(unsigned)((size_t)S * nSlots * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, e->specOut, st); });
     const long long span_n = (long long)std::min<long long>(nSlots, e->maxBlocksOr1(slot0)) * g.H + g.L;
-    span("ola_kernel", nBlk * g.C, [&] {
-      const int quad = ola_quad_ok(e->dg) ? 1 : 0;
-      const long long nThr = quad ? (span_n + 3) / 4 : span_n;
-      ola_kernel<<<dim3((unsigned)((nThr + 255) / 256), (unsigned)(S * g.C)), 256, 0, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, st, quad); });
-    st.ringPar ^= 1;
+    if (!(synthMode & kSynthFrames)) {
+      span("ola_kernel", nBlk * g.C, [&] {
+        const int quad = ola_quad_ok(e->dg) ? 1 : 0;
+        const long long nThr = quad ? (span_n + 3) / 4 : span_n;
+        ola_kernel<<<dim3((unsigned)((nThr + 255) / 256), (unsigned)(S * g.C)), 256, 0, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, synthMode, st, quad); });
+      st.ringPar ^= 1;
+    }
   }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
@@ -994,6 +996,51 @@ int bsb_block_info(const bsb_engine *e, int s, long long b, long long out[8]) {
 
 }  // extern "C"
 
+// ---- the reference's STFT output ring (W#22/23, the synthesis steps and the per-sample read of W#48), kept as such
+// for the compat shim: ring [C][L] + window products [L] in device memory, the position on the host.  Blocks may start
+// at any ring position (after the silence gate re-arms mid-interval they do), which the batched path's index-space
+// overlap-add does not model.
+BS_HD void shim_ring_add_one(int C /* channels to add */, int L, int i, int pos, float fN, const float *win, const float *frames, float *ring, float *wp) {
+  const int p = (pos + i) % L;
+  wp[p] = ((win[i] * fN) * win[i]) + wp[p];                               // synthesis step 0: addWindowProduct
+  for (int c = 0; c < C; ++c) ring[(size_t)c * L + p] = ring[(size_t)c * L + p] + frames[(size_t)c * L + i];
+}
+BS_HD void shim_ring_read_one(int C, int L, int i, int pos, int outStride, float *ring, float *wp, float *out, bool consume) {
+  const int p = (pos + i) % L;
+  const float w = wp[p];
+  for (int c = 0; c < C; ++c) {
+    if (out) out[(size_t)c * outStride + i] = ring[(size_t)c * L + p] / w;
+    if (consume) ring[(size_t)c * L + p] = 0.f;
+  }
+  if (consume) wp[p] = 1e-30f;                                            // moveOutput
+}
+#ifndef BS_HOSTEMU
+__global__ void shim_ring_add_kernel(int C, int L, int pos, float fN, const float *win, const float *frames, float *ring, float *wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) shim_ring_add_one(C, L, i, pos, fN, win, frames, ring, wp);
+}
+__global__ void shim_ring_read_kernel(int C, int L, int n, int pos, int outStride, float *ring, float *wp, float *out, int consume) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) shim_ring_read_one(C, L, i, pos, outStride, ring, wp, out, consume != 0);
+}
+#endif
+static void shim_ring_add(int C, int L, int pos, float fN, const float *win, const float *frames, float *ring, float *wp) {
+#ifdef BS_HOSTEMU
+  for (int i = 0; i < L; ++i) shim_ring_add_one(C, L, i, pos, fN, win, frames, ring, wp);
+#else
+  shim_ring_add_kernel<<<(L + 255) / 256, 256>>>(C, L, pos, fN, win, frames, ring, wp);
+#endif
+}
+// out == nullptr: moveOutput(n) only
+static void shim_ring_read(int C, int L, int n, int pos, int outStride, float *ring, float *wp, float *out, bool consume) {
+  if (n <= 0) return;
+#ifdef BS_HOSTEMU
+  for (int i = 0; i < n; ++i) shim_ring_read_one(C, L, i, pos, outStride, ring, wp, out, consume);
+#else
+  shim_ring_read_kernel<<<(n + 255) / 256, 256>>>(C, L, n, pos, outStride, ring, wp, out, consume ? 1 : 0);
+#endif
+}
+
 // =====================================================================================================================
 // Part 1 of the header: the reference's own 18 entry points for one "current" engine instance.
 // Host side keeps what the reference keeps in wasm linear memory (I/O buffer, input ring) and runs the same control
@@ -1008,6 +1055,12 @@ void d2h_sync(void *h, const void *d, size_t n) {
 }
 #endif
 
+#ifdef BS_HOSTEMU
+void d2d(void *dst, const void *src, size_t n) { std::memcpy(dst, src, n); }
+#else
+void d2d(void *dst, const void *src, size_t n) { cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, 0); }
+#endif
+
 struct Compat {
   bsb_engine *e = nullptr;
   Geometry g{};
@@ -1016,8 +1069,11 @@ struct Compat {
   uint32_t seed = 1, rngState = 1;
   std::vector<float> io; int ioCh = 0, ioLen = 0;
   std::vector<float> ring; int ringPos = 0, inLen = 0;   // stft input ring [C][L+H+1]
-  std::vector<float> lastCur, stage, pending;            // [C][L], [C][2L], [C][H]
+  std::vector<float> lastCur, stage;                     // [C][L], [C][2L]
   float *dStage = nullptr, *dOut = nullptr;
+  // the STFT output ring and its stashed copy (split computation reads the copy): [0] = live, [1] = stash
+  float *dRing[2] = {nullptr, nullptr}, *dWp[2] = {nullptr, nullptr};
+  int outPos[2] = {0, 0};
   StreamPlan plan;
   long long m = -1;            // block whose interval is being emitted
   bool deferred = false;       // split mode: block m's spectral work not launched yet
@@ -1033,6 +1089,31 @@ void compat_free(Compat *c) {
   if (c->dStage) dfree(c->dStage);
   if (c->dOut) dfree(c->dOut);
   c->dStage = c->dOut = nullptr;
+  for (int i = 0; i < 2; ++i) { if (c->dRing[i]) dfree(c->dRing[i]); if (c->dWp[i]) dfree(c->dWp[i]); c->dRing[i] = c->dWp[i] = nullptr; }
+}
+
+// W#22 stft.reset(weight) as far as the output ring goes: zero ring, window products of one frame folded over the
+// interval, weighted, then moveOutput(H)
+void compat_ring_reset(Compat *c, float weight) {
+  const Geometry &g = c->g; const int L = g.L, H = g.H;
+  const std::vector<float> &win = c->e->T.win;
+  std::vector<float> wp(L, 0.f);
+  const float fN = (float)(uint32_t)g.N;
+  for (int i = 0; i < L; ++i) wp[i] = ((win[i] * fN) * win[i]) + wp[i];
+  for (int i = L - H - 1; i >= 0; --i) wp[i] = wp[i] + wp[i + H];
+  for (int i = 0; i < L; ++i) wp[i] = (wp[i] * weight) + 1e-30f;
+  for (int i = 0; i < H && i < L; ++i) wp[i] = 1e-30f;   // moveOutput(H) from position 0 (the ring itself is all zero)
+  dzero(c->dRing[0], (size_t)g.C * L * sizeof(float), 0);
+  h2d(c->dWp[0], wp.data(), (size_t)L * sizeof(float), 0);
+#ifndef BS_HOSTEMU
+  cudaStreamSynchronize(0);   // wp is a local
+#endif
+  c->outPos[0] = H % L;
+}
+void compat_ring_stash(Compat *c) {   // stashedOutput = stft output (ring, window products, position)
+  const Geometry &g = c->g;
+  d2d(c->dRing[1], c->dRing[0], (size_t)g.C * g.L * sizeof(float)); d2d(c->dWp[1], c->dWp[0], (size_t)g.L * sizeof(float));
+  c->outPos[1] = c->outPos[0];
 }
 
 // stft.reset + stretch reset (W#22, W#59): host ring, device state, control
@@ -1040,8 +1121,8 @@ void compat_reset_state(Compat *c) {
   const Geometry &g = c->g;
   std::fill(c->ring.begin(), c->ring.end(), 0.f); c->ringPos = g.L;
   std::fill(c->lastCur.begin(), c->lastCur.end(), 0.f);
-  std::fill(c->pending.begin(), c->pending.end(), 0.f);
   reset_state(c->e, 0);
+  compat_ring_reset(c, 0.1f); compat_ring_stash(c);
   c->ctl->resetAll();
   c->m = -1; c->deferred = false; c->curLaunched = false;
   c->plan = StreamPlan();
@@ -1059,14 +1140,15 @@ void compat_configure(int ch, int L, int H, int split) {
   e->dg.incremental = 1;
   c->inLen = L + H + 1;
   c->ring.assign((size_t)ch * c->inLen, 0.f);
-  c->lastCur.assign((size_t)ch * L, 0.f); c->stage.assign((size_t)ch * 2 * L, 0.f); c->pending.assign((size_t)ch * H, 0.f);
+  c->lastCur.assign((size_t)ch * L, 0.f); c->stage.assign((size_t)ch * 2 * L, 0.f);
   c->dStage = (float *)dmalloc((size_t)ch * 2 * L * sizeof(float)); c->dOut = (float *)dmalloc((size_t)ch * H * sizeof(float));
+  for (int i = 0; i < 2; ++i) { c->dRing[i] = (float *)dmalloc((size_t)ch * L * sizeof(float)); c->dWp[i] = (float *)dmalloc((size_t)L * sizeof(float)); }
   // a one-stream, one-slot batch whose single table entry is rewritten for every block
   e->streams.assign(1, Stream()); e->streams[0].clip = c->dStage; e->streams[0].out = c->dOut; e->streams[0].clipLen = 2 * L;
   e->streams[0].seed = c->seed; e->streams[0].planned = true;
   e->streams[0].plan.blocks.assign(1, BlockRec{}); e->streams[0].plan.blocks2.assign(1, BlockRec2{}); e->streams[0].plan.windows.assign(2, Window{0, 0, 0});
   e->streams[0].plan.nOut = H;
-  if (!c->dStage || !c->dOut || bsb_commit(e, 1) != 0) bs::die("configure: device allocation failed");
+  if (!c->dStage || !c->dOut || !c->dRing[0] || !c->dRing[1] || !c->dWp[0] || !c->dWp[1] || bsb_commit(e, 1) != 0) bs::die("configure: device allocation failed");
   e->hs[0].nBlocks = (long long)1 << 60; e->hs[0].nOut = (long long)1 << 60; e->hs[0].outStride = H;
   c->ctl.reset(new Control(g));
   c->silenceFirst = true;
@@ -1117,6 +1199,30 @@ void compat_window(Compat *c, int samplesInPast, float *dst /* [C][2L] stride */
   }
 }
 
+// run every step of block m (analysis .. inverse FFT) and add its frames to the live output ring at the ring position
+void compat_block(Compat *c, long long m, int nSynth = -1 /* channels whose synthesis step ran; default all */) {
+  const Geometry &g = c->g;
+  compat_launch(c, m, c->plan.blocks[m], c->plan.blocks2[m], c->dWin, 1 | 2, kSynthFrames);
+  if (nSynth != 0)   // synthesis step 0 adds the window products, step c the frame of channel c
+    shim_ring_add(nSynth < 0 ? g.C : nSynth, g.L, c->outPos[0], (float)(uint32_t)g.N, c->e->dt.win, c->e->st.frames, c->dRing[0], c->dWp[0]);
+}
+// The silence gate re-arms blockProcess (W#48 7842-7845) while, with split computation, the block under way has only
+// run some of its steps.  What survives of it (every Band is cleared right after): the frames of the channels whose
+// synthesis step has run, and the random draws of the vertical-prediction steps that have run.
+void compat_abandon_block(Compat *c) {
+  if (!c->deferred) return;
+  const Geometry &g = c->g;
+  int nS6 = 0, nSyn = 0;
+  c->ctl->progress(nS6, nSyn);
+  if (nSyn > 0) compat_block(c, c->m, nSyn);
+  else {
+    const float tf = c->plan.blocks[c->m].timeFactor;
+    const uint32_t k1 = ((uint32_t)g.B * (uint32_t)nS6) >> 3;
+    if (!((tf < 0.5f ? 0.5f : tf) <= 2.0f) && k1 >= 1) c->rngState = minstd_jump(c->rngState, k1 < (uint32_t)g.B ? 2 * k1 - 1 : 2 * k1 - 2);
+  }
+  c->deferred = false;
+}
+
 void compat_process(int nIn, int nOut) {
   Compat *c = cc();
   if (!c->e) bs::die("process() before configure()/presetDefault()/presetCheaper()");
@@ -1132,9 +1238,13 @@ void compat_process(int nIn, int nOut) {
   if (!loud) {   // silence gate, W#48 7838-7943
     if (c->silenceCounter >= ((uint32_t)L << 1)) {
       if (c->silenceFirst) {
-        c->silenceFirst = false; c->ctl->resetBlockProcess();
+        c->silenceFirst = false;
+        compat_abandon_block(c);   // blockProcess = {}
+        c->ctl->resetBlockProcess();
         const size_t CB = (size_t)C * g.B;
+        // every Band cleared: input, prevInput, output (inputEnergy is rewritten by each block)
         dzero(c->e->st.outSpec, CB * sizeof(cf), 0); dzero(c->e->st.lastInput, CB * sizeof(cf), 0);
+        std::fill(c->lastCur.begin(), c->lastCur.end(), 0.f);
       }
       if (nIn > 0) {
         for (int i = 0, j = 0; i < nOut; ++i) { for (int ch = 0; ch < C; ++ch) outs[(size_t)c->ioLen * ch + i] = c->io[(size_t)c->ioLen * ch + j]; j = (j + 1 != nIn) ? j + 1 : 0; }
@@ -1152,7 +1262,7 @@ void compat_process(int nIn, int nOut) {
   auto onStart = [&](int, int inputOffset, int, bool rean, bool isNew, long long bi) {
     compat_copy_input(c, inputOffset);
     if (c->deferred) {   // split mode: every step of the previous block has run by now, its records are final
-      compat_launch(c, c->m, c->plan.blocks[c->m], c->plan.blocks2[c->m], c->dWin, 1 | 2, kSynthAdd);
+      compat_block(c, c->m);
       c->deferred = false;
     }
     c->m = bi; c->curLaunched = false;
@@ -1163,24 +1273,93 @@ void compat_process(int nIn, int nOut) {
       for (int ch = 0; ch < C; ++ch) std::memcpy(c->lastCur.data() + (size_t)ch * L, c->stage.data() + (size_t)ch * 2 * L, L * sizeof(float));
       h2d(c->dStage, c->stage.data(), c->stage.size() * sizeof(float), 0);
     }
-    if (g.split) {   // this interval's samples come from the blocks before; the block itself runs when its steps are done
-      compat_launch(c, c->m, BlockRec{}, BlockRec2{}, c->dWin, 2, kSynthEmit);
-      d2h_sync(c->pending.data(), c->dOut, c->pending.size() * sizeof(float));
+    if (g.split) {   // stash the output ring (this interval is read from the copy), make room for this block's frames
+      compat_ring_stash(c);
+      shim_ring_read(C, L, H, c->outPos[0], 0, c->dRing[0], c->dWp[0], nullptr, true);
+      c->outPos[0] = (c->outPos[0] + H) % L;
       c->deferred = true; c->curLaunched = true;
     }
   };
-  auto onSpan = [&](int idx, int span, uint32_t since) {
+  std::vector<float> got((size_t)C * H);
+  auto onSpan = [&](int idx, int span, uint32_t) {
     if (!c->curLaunched) {   // non-split: every step of the block ran at its first sample, with the current parameters
-      compat_launch(c, c->m, c->plan.blocks[c->m], c->plan.blocks2[c->m], c->dWin, 1 | 2, kSynthEmit | kSynthAdd);
-      d2h_sync(c->pending.data(), c->dOut, c->pending.size() * sizeof(float));
+      compat_block(c, c->m);
       c->curLaunched = true;
     }
-    for (int ch = 0; ch < C; ++ch)
-      std::memcpy(outs + (size_t)c->ioLen * ch + idx, c->pending.data() + (size_t)ch * H + since, (size_t)span * sizeof(float));
+    const int r = g.split ? 1 : 0;   // the per-sample read: ring / window products, then moveOutput(1)
+    for (int done = 0; done < span;) {   // (a span never exceeds H; the ring read is chunked to the H-sample staging buffer)
+      const int n = std::min(span - done, H);
+      shim_ring_read(C, L, n, c->outPos[r], H, c->dRing[r], c->dWp[r], c->dOut, true);
+      d2h_sync(got.data(), c->dOut, got.size() * sizeof(float));
+      for (int ch = 0; ch < C; ++ch) std::memcpy(outs + (size_t)c->ioLen * ch + idx + done, got.data() + (size_t)ch * H, (size_t)n * sizeof(float));
+      c->outPos[r] = (c->outPos[r] + n) % L;
+      done += n;
+    }
   };
   c->ctl->run(c->plan, 0, nOut, nIn, nOut, onStart, onSpan);
   compat_copy_input(c, nIn);
   c->ctl->endCall(nIn);
+}
+
+// W#46 flush(outputSamples) -- exported by the reference, never called by its JS.  Control operation on the output ring
+// (no DSP): the ring and its window products come down, the arithmetic below is the bytecode's, the state goes back up.
+// With split computation the block under way has run only some of its steps when flush() arrives and the reference runs
+// the rest afterwards, on the state flush() cleared.  Reproduced: flush before the vertical prediction has started
+// (the whole block then runs on the cleared state) and flush after it has finished (synthesised channels are in the old
+// ring, the rest add nothing but their window products to the new one).  A flush landing inside the eight
+// vertical-prediction steps is handled like one right after them (the reference would still synthesise the bins
+// predicted after the flush).
+void compat_flush(int nOut) {
+  Compat *c = cc();
+  if (!c->e) bs::die("flush() before configure()");
+  const Geometry &g = c->g; const int C = g.C, L = g.L;
+  if (nOut > c->ioLen) bs::die("flush(): sample count exceeds the setBuffers() length");
+  bool keepPrevInput = false, wpAfter = false;
+  if (c->deferred) {
+    int nS6 = 0, nSyn = 0;
+    c->ctl->progress(nS6, nSyn);
+    const int step = c->ctl->stepsDone();
+    if (step <= c->ctl->stepS6()) {   // runs after the flush, on Band.output = 0 and (unless its copy is still to come) prevInput = 0
+      // stft.reset also clears the spectrum scratch: a channel analysed before the flush whose copy into the Bands comes
+      // after it arrives as zeros; prevInput copied before the flush is cleared by the flush itself
+      const bool isNew = c->ctl->curIsNew(), rean = c->ctl->curReanalysesPrev();
+      const int aCur = (isNew && rean) ? C + 1 : 0;
+      for (int ch = 0; ch < C; ++ch) {
+        const bool prevOk = isNew && rean && step <= ch;
+        const bool curLost = isNew && step > aCur + ch && step <= aCur + C;
+        float *w = c->stage.data() + (size_t)ch * 2 * L;
+        if (!prevOk) std::fill(w + L, w + 2 * L, 0.f);
+        if (curLost) { std::fill(w, w + L, 0.f); std::fill(c->lastCur.begin() + (size_t)ch * L, c->lastCur.begin() + (size_t)(ch + 1) * L, 0.f); }
+      }
+      h2d(c->dStage, c->stage.data(), c->stage.size() * sizeof(float), 0);
+#ifndef BS_HOSTEMU
+      cudaStreamSynchronize(0);
+#endif
+      keepPrevInput = c->ctl->curIsNew();   // its last spectral step sets prevInput = input again
+    } else {
+      compat_block(c, c->m, nSyn);
+      c->deferred = false; c->curLaunched = true;
+      wpAfter = (nSyn == 0);              // synthesis step 0 is still to come: it adds the window products to the new ring
+      keepPrevInput = c->ctl->curIsNew() && step <= c->ctl->stepFinal();
+    }
+  }
+  std::vector<float> ring((size_t)C * L), wp(L);
+  d2h_sync(ring.data(), c->dRing[0], ring.size() * sizeof(float)); d2h_sync(wp.data(), c->dWp[0], wp.size() * sizeof(float));
+  const int pos = c->outPos[0];
+  float m = 0.f;
+  for (int i = 0; i < L; ++i) { const int p = (pos + i) % L; const float x = wp[p]; m = (m > x) ? m : x; wp[p] = m; }
+  const int n1 = (L < nOut) ? L : nOut, rest = L - n1, n2 = (rest < nOut) ? rest : nOut;
+  for (int ch = 0; ch < C; ++ch) {
+    const float *r = ring.data() + (size_t)ch * L; float *out = c->io.data() + (size_t)c->ioLen * (C + ch);
+    for (int i = 0; i < n1; ++i) { const int p = (pos + i) % L; out[i] = r[p] / wp[p]; }
+    for (int i = 0; i < n2; ++i) { const int p = (pos + n1 + i) % L; out[nOut - 1 - i] = out[nOut - 1 - i] - (r[p] / wp[p]); }
+  }
+  // stft.reset(0.1): input ring, output ring (the stashed copies stay); then Band.prevInput = Band.output = 0
+  std::fill(c->ring.begin(), c->ring.end(), 0.f); c->ringPos = L;
+  compat_ring_reset(c, 0.1f);
+  if (wpAfter) shim_ring_add(0, L, c->outPos[0], (float)(uint32_t)g.N, c->e->dt.win, c->e->st.frames, c->dRing[0], c->dWp[0]);
+  dzero(c->e->st.outSpec, (size_t)C * g.B * sizeof(cf), 0);
+  if (!keepPrevInput) std::fill(c->lastCur.begin(), c->lastCur.end(), 0.f);
 }
 
 void compat_seek(int n, double rate) {   // W#49
@@ -1225,7 +1404,7 @@ void setFormantSemitones(float st, int comp) { cc()->p.setFormantSemitones(st, c
 void setFormantBase(float f) { cc()->p.setFormantBase(f); }
 void seek(int n, double rate) { compat_seek(n, rate); }
 void process(int nIn, int nOut) { compat_process(nIn, nOut); }
-void flush(int) { bs::die("flush() is exported by the reference but never called by its JS (app/SignalsmithStretch.mjs:479); not implemented"); }
+void flush(int n) { compat_flush(n); }
 int stretch_main(int, char **) { return 0; }
 void stretch_set_seed(uint32_t seed) {
   Compat *c = cc(); c->seed = seed;

@@ -43,7 +43,7 @@ struct DevGeom {
   int incremental;  // blocks arrive one at a time (compat shim): always carry the input spectrum forward
   unsigned divMagic; int divShift;   // j / outer == (j * divMagic) >> divShift for every j < M (checked at create time)
 };
-enum : int { kSynthEmit = 1, kSynthAdd = 2 };
+enum : int { kSynthEmit = 1, kSynthAdd = 2, kSynthFrames = 4 };   // kSynthFrames: windowed frames only, no overlap-add (the compat shim keeps the reference's own output ring)
 struct DevTables {
   const float *win; const cf *tw; const float *otr, *oti; const cf *untangle, *rot, *specRot;
   const float *wpStart, *wpSteady;

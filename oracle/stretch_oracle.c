@@ -905,7 +905,29 @@ API void so_setFormantSemitones(float st, int comp) { so_setFormantFactor((float
 API void so_setFormantBase(float f) { cur->formantBaseFreq = f; }
 API void so_seek(int n, double rate) { engine_seek(cur, n, rate); }
 API void so_process(int nIn, int nOut) { engine_process(cur, nIn, nOut); }
-API void so_flush(int nOut) { (void)nOut; fprintf(stderr, "stretch_oracle: flush (W#46) is exported but never called by the reference JS; not restated\n"); abort(); }
+/* W#46 flush(outputSamples).  Exported, never called by the reference JS (app/SignalsmithStretch.mjs:479 is its only
+ * mention); restated from the bytecode: the window-product ring becomes its own running maximum (in ring order from the
+ * read position), up to L samples are read WITHOUT consuming them, what is left of the ring after those (at most
+ * outputSamples more) is folded back reversed and subtracted from the end of the output, then stft.reset(0.1) and every
+ * Band's prevInput and output are cleared (input and inputEnergy stay; blockProcess and prevInputOffset too). */
+static void engine_flush(Engine *e, int nOut) {
+  int C = e->channels, L = e->L;
+  OutState *o = &e->out;
+  float m = 0.0f;
+  for (int i = 0; i < L; ++i) { int p = (o->pos + i) % L; float x = o->wp[p]; m = (m > x) ? m : x; o->wp[p] = m; }
+  if (C > 0) {
+    int n1 = (L < nOut) ? L : nOut, rest = L - n1, n2 = (rest < nOut) ? rest : nOut;
+    for (int c = 0; c < C; ++c) {
+      const float *ring = o->ring + (size_t)c * L;
+      float *out = e->buffers + (size_t)e->bufLen * (C + c);
+      for (int i = 0; i < n1; ++i) { int p = (o->pos + i) % L; out[i] = ring[p] / o->wp[p]; }
+      for (int i = 0; i < n2; ++i) { int p = (o->pos + n1 + i) % L; out[nOut - 1 - i] = out[nOut - 1 - i] - (ring[p] / o->wp[p]); }
+    }
+  }
+  stft_reset(e, 0.1f);
+  for (size_t i = 0; i < (size_t)C * e->B; ++i) { e->bands[i].prevInput.re = e->bands[i].prevInput.im = 0.0f; e->bands[i].output.re = e->bands[i].output.im = 0.0f; }
+}
+API void so_flush(int nOut) { engine_flush(cur, nOut); }
 /* inspection helpers for the stage-by-stage tests */
 API const float *so_window(void) { return cur->win; }
 API const c32 *so_spectrum(void) { return cur->spectrum; }

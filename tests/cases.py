@@ -40,6 +40,11 @@ def make_clip(spec):
     kind = spec[0]
     if kind == "survey":
         return refdrive.survey_clip(spec[1])
+    if kind == "gated":     # (kind, n, ((start, stop), ...)): the survey clip with digital silence over the given spans
+        x = refdrive.survey_clip(spec[1]).copy()
+        for a, b in spec[2]:
+            x[:, a:b] = 0.0
+        return x
     if kind == "sweep":     # (kind, seconds, sr, channels)
         return refdrive.sweep_clip(spec[1], spec[2], spec[3])
     if kind == "noise":     # (kind, n, channels, seed, amplitude)
@@ -110,12 +115,19 @@ def stream_run(engine, clip, case):
     sr, n_in, n_out = case["sr"], case["n_in"], case["n_out"]
     ch = clip.shape[0]
     _setup(engine, case, ch)
-    engine.setBuffers(ch, max(n_in, n_out))
     calls = case.get("n_calls", clip.shape[1] // n_in)
+    flush_at, n_flush = case.get("flush", (None, 0))        # flush(n_flush) after that many calls; its samples are kept
+    engine.setBuffers(ch, max(n_in, n_out, n_flush))
     segs = case["segments"]
     si = 0
-    out = np.zeros((ch, calls * n_out), np.float32)
+    parts = []
     for k in range(calls):
+        if k == flush_at:
+            _, outs = engine.io_views()
+            outs[:] = 0.25                                      # flush subtracts from what the buffer holds
+            engine.flush(n_flush)
+            _, outs = engine.io_views()
+            parts.append(outs[:, :n_flush].copy())
         t = (k * n_out) / sr
         while si + 1 < len(segs) and segs[si + 1]["output"] <= t:
             si += 1
@@ -124,8 +136,8 @@ def stream_run(engine, clip, case):
         ins[:, :n_in] = clip[:, k * n_in:(k + 1) * n_in]
         engine.process(n_in, n_out)
         _, outs = engine.io_views()
-        out[:, k * n_out:(k + 1) * n_out] = outs[:, :n_out]
-    return out
+        parts.append(outs[:, :n_out].copy())
+    return np.concatenate(parts, axis=1)
 
 
 def run_case(engine, case, clip=None):
@@ -239,6 +251,25 @@ CASES = {
                                 segments=[seg(rate=0.8, semitones=-5.0, tonality_hz=16000.0)]),
     "stream_transpose_only_q96": dict(drive="kiosk", clip=("survey", 30000), sr=48000, n_out=30000, preset="default", quantum=96,
                                       segments=[seg(rate=1.0, semitones=12.0)]),
+}
+
+# Cases for the 18-call surface only (oracle engines and the compat shim): the silence gate of process() (W#48
+# 7838-7943; fires after 2L silent input samples, re-arms the block phase wherever it stands) and flush() (W#46).  The
+# batched path plans whole drives ahead of the data and does not model either.
+_GAPS = ((6000, 30000), (40000, 55000))
+SHIM_CASES = {
+    "gate_default": dict(drive="stream", clip=("gated", 60000, _GAPS), sr=48000, n_in=512, n_out=512, preset="default",
+                         segments=[seg(semitones=2.0)]),
+    "gate_cheaper_split": dict(drive="stream", clip=("gated", 60000, _GAPS), sr=48000, n_in=128, n_out=128, preset="cheaper",
+                               segments=[seg(semitones=2.0)]),
+    "gate_cheaper_random_tf": dict(drive="stream", clip=("gated", 60000, _GAPS), sr=48000, n_in=300, n_out=700, preset="cheaper",
+                                   seed=5, segments=[seg(semitones=2.0)]),
+    "flush_default": dict(drive="stream", clip=("survey", 24000), sr=48000, n_in=300, n_out=700, preset="default", seed=5,
+                          flush=(30, 3000), segments=[seg(semitones=3.0)]),
+    "flush_cheaper_before_prediction": dict(drive="stream", clip=("survey", 24000), sr=48000, n_in=480, n_out=512, preset="cheaper",
+                                            flush=(27, 7000), segments=[seg(semitones=3.0)]),
+    "flush_cheaper_during_synthesis": dict(drive="stream", clip=("survey", 24000), sr=48000, n_in=480, n_out=512, preset="cheaper",
+                                           flush=(22, 1440), segments=[seg(semitones=3.0)]),
 }
 
 # small subset used by the CPU suite for the (slower) serial emulation of the kernels

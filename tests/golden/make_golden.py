@@ -34,7 +34,7 @@ def main():
     assert os.path.exists(refdrive.REF_SO), "build oracle/_ref first: make -C oracle ref"
     meta = {}
     sub = {}
-    for name, case in cases.CASES.items():
+    for name, case in list(cases.CASES.items()) + list(cases.SHIM_CASES.items()):
         eng = refdrive.RefEngine(seed=case.get("seed", 1))
         y = cases.run_case(eng, case)
         eng.close()

@@ -71,6 +71,14 @@ def test_compat_shim_on_gpu(name, bs, golden):
     assert_matches_golden(name, y, golden)
 
 
+@pytest.mark.parametrize("name", list(cases.SHIM_CASES))
+def test_compat_shim_gate_and_flush_on_gpu(name, bs, golden):
+    """The silence gate of process() and flush() through the reference's own entry points (W#48 7838-7943, W#46)."""
+    e = bs.StretchEngine(seed=cases.SHIM_CASES[name].get("seed", 1))
+    y = cases.run_case(e, cases.SHIM_CASES[name])
+    assert_matches_golden(name, y, golden)
+
+
 def test_block_schedule_bit_exact(bs):
     """frame/hop indexing: the device-side block table equals the one derived from the worklet arithmetic."""
     import torch

@@ -68,6 +68,15 @@ def test_compat_shim_bit_exact(name, emu, golden):
     assert_matches_golden(name, y, golden)
 
 
+@pytest.mark.parametrize("name", list(cases.SHIM_CASES))
+def test_compat_shim_gate_and_flush(name, emu, golden):
+    """process()'s silence gate (re-arming the block phase mid-interval, with and without split computation, with random
+    time factors) and flush(): the shim keeps the reference's own output ring, so both are bit-exact."""
+    e = bs.StretchEngine(seed=cases.SHIM_CASES[name].get("seed", 1), lib=emu)
+    y = cases.run_case(e, cases.SHIM_CASES[name])
+    assert_matches_golden(name, y, golden)
+
+
 def test_shim_parameter_changes_every_quantum(emu):
     """Q4: with splitComputation the steps of a block see the parameters current when they run."""
     x = refdrive.survey_clip(20000)

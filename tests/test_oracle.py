@@ -30,6 +30,28 @@ def test_port_reproduces_golden(name, golden):
     assert_matches_golden(name, y, golden)
 
 
+@pytest.mark.parametrize("name", list(cases.SHIM_CASES))
+def test_port_reproduces_golden_gate_and_flush(name, golden):
+    """Silence gate (W#48 7838-7943) and flush (W#46, restated from the bytecode) against vectors minted from the blob."""
+    eng = refdrive.PortEngine(seed=cases.SHIM_CASES[name].get("seed", 1))
+    y = cases.run_case(eng, cases.SHIM_CASES[name])
+    eng.close()
+    assert_matches_golden(name, y, golden)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="translated reference blob not built (oracle/_ref)")
+def test_port_flush_equals_translated_blob_live():
+    """flush() at many positions of the block cycle, then more processing: port == blob bit for bit."""
+    for preset, n_in, n_out in (("default", 300, 700), ("cheaper", 200, 200)):
+        for calls in (20, 23, 26, 29):
+            case = dict(drive="stream", clip=("survey", 16000), sr=48000, n_in=n_in, n_out=n_out, preset=preset, seed=5,
+                        flush=(calls, 2000), segments=[cases.seg(semitones=3.0)])
+            a = refdrive.RefEngine(seed=5); b = refdrive.PortEngine(seed=5)
+            ya, yb = cases.run_case(a, case), cases.run_case(b, case)
+            assert cases.compare(ya, yb)[0], (preset, calls)
+            a.close(); b.close()
+
+
 SURVEY_PREFIX = dict(KA1="83b7dd548f69c080", KA2="4b020352d89f76a1", KA3="75865524063b07dc", KA4="2d2d72427453da4e",
                      KA5="18e7b06e2a8eb64e", KA6="05a59d3d8ea0ae29")
 
