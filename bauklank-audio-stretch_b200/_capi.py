@@ -54,6 +54,7 @@ _BATCH_SIG = {
     "bsb_stream_blocks": (C.c_longlong, [C.c_void_p, C.c_int]),
     "bsb_chunk_blocks": (C.c_int, [C.c_void_p]),
     "bsb_launch_count": (C.c_longlong, [C.c_void_p]),
+    "bsb_gate_events": (C.c_longlong, [C.c_void_p]),
     "bsb_block_info": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_longlong)]),
     "bsb_selftest_arith": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bsb_set_profiling": (None, [C.c_void_p, C.c_int]),

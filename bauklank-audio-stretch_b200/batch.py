@@ -186,6 +186,13 @@ class BatchStretch:
     def chunk_blocks(self): return self.lib.bsb_chunk_blocks(self.h)
     def launch_count(self): return self.lib.bsb_launch_count(self.h)
 
+    def gate_events(self):
+        """Streaming drives: number of process() calls of the last run that the reference's silence gate would have
+        short-circuited (2 * blockSamples of silent input, app-side ``_process(q, q)`` on silence).  The batched path
+        does not model that branch; a non-zero count means the result differs from the reference there -- drive such
+        material through ``StretchEngine`` instead.  Synchronises with the device."""
+        return int(self.lib.bsb_gate_events(self.h))
+
     def set_profiling(self, on=True):
         """Bracket every kernel launch of the following runs with CUDA events (on the run's stream)."""
         self.lib.bsb_set_profiling(self.h, 1 if on else 0)

@@ -310,7 +310,40 @@ __global__ void __launch_bounds__(256) ola_kernel(DevGeom g, DevTables T, const 
 struct Stream {
   const float *clip = nullptr; float *out = nullptr; long long clipLen = 0; uint32_t seed = 1;
   StreamPlan plan; bool planned = false;
+  int gateIn = 0; long long gateCalls = 0;   // streaming drive: process(gateIn, .) x gateCalls (0 = kiosk drive, no gate)
 };
+
+// ---- silence-gate watch for streaming drives.  process() stops running blocks once 2L consecutive input samples were
+// silent (sum of squares of a call's input below 1e-15, W#48 7838-7943); the batched path plans every block ahead of the
+// data and does not follow the reference through that branch, so it at least says when the branch would have been
+// taken: one thread per call sums its input exactly like the reference (channel by channel, sample by sample), one
+// thread per stream then runs the counter.  bsb_gate_events() returns the number of calls the reference would have gated.
+struct GateDev { const float *clip; long long clipLen, nCalls, callBase; int nIn, pad; };
+BS_HD uint8_t gate_call_loud(const GateDev &gd, int C, long long k) {
+  float total = 0.f;
+  for (int c = 0; c < C; ++c) { const float *x = gd.clip + (size_t)c * gd.clipLen + k * gd.nIn; for (int i = 0; i < gd.nIn; ++i) total = (x[i] * x[i]) + total; }
+  return total >= 1e-15f ? 1 : 0;
+}
+BS_HD int gate_count(const GateDev &gd, int L, const uint8_t *loud) {
+  unsigned counter = 0; int fired = 0;
+  for (long long k = 0; k < gd.nCalls; ++k) {
+    if (loud[gd.callBase + k]) counter = 0;
+    else if (counter >= ((unsigned)L << 1)) ++fired;
+    else counter += (unsigned)gd.nIn;
+  }
+  return fired;
+}
+#ifndef BS_HOSTEMU
+__global__ void gate_energy_kernel(const GateDev *gds, int C, uint8_t *loud) {
+  const GateDev gd = gds[blockIdx.y];
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < gd.nCalls) loud[gd.callBase + k] = gate_call_loud(gd, C, k);
+}
+__global__ void gate_count_kernel(const GateDev *gds, int n, int L, const uint8_t *loud, int *fired) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) fired[s] = gate_count(gds[s], L, loud);
+}
+#endif
 
 }  // namespace bs
 
@@ -342,6 +375,8 @@ struct bsb_engine {
                                    // once the shorter streams of a batch have ended the chain runs on a fraction of the SMs and
                                    // the next chunk's front half fills the rest: 334 -> 301 ms on 256 x 60 s of mixed rates
   float *recBuf[2] = {nullptr, nullptr};
+  std::vector<GateDev> gate; std::vector<int> gateStream; GateDev *dGate = nullptr; uint8_t *dLoud = nullptr; int *dFired = nullptr;
+  long long gateCallsTotal = 0, gateMaxCalls = 0;
 #ifndef BS_HOSTEMU
   cudaStream_t sFront = nullptr, sBack = nullptr, sIn = nullptr, sOut = nullptr;
   cudaEvent_t evFront[2] = {nullptr, nullptr}, evBack[2] = {nullptr, nullptr}, evFork = nullptr, evJoin[2] = {nullptr, nullptr};
@@ -718,6 +753,19 @@ long long bsb_total_blocks(const bsb_engine *e) { return e->totalBlocks; }
 long long bsb_stream_blocks(const bsb_engine *e, int s) { return (s >= 0 && s < (int)e->streams.size()) ? (long long)e->streams[s].plan.blocks.size() : -1; }
 int bsb_chunk_blocks(const bsb_engine *e) { return e->chunk; }
 long long bsb_launch_count(const bsb_engine *e) { return e->launches; }
+long long bsb_gate_events(bsb_engine *e) {
+  if (!e->committed) return -1;
+  if (e->gate.empty()) return 0;
+  std::vector<int> fired(e->gate.size());
+#ifdef BS_HOSTEMU
+  std::memcpy(fired.data(), e->dFired, fired.size() * sizeof(int));
+#else
+  if (cudaMemcpy(fired.data(), e->dFired, fired.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+#endif
+  long long n = 0;
+  for (int v : fired) n += v;
+  return n;
+}
 void bsb_set_profiling(bsb_engine *e, int on) { e->profiling = on != 0; }
 int bsb_kernel_count(const bsb_engine *e) { return (int)e->kstat.size(); }
 int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units) {
@@ -808,6 +856,7 @@ int bsb_add_streaming(bsb_engine *e, int si, const float *dClip, long long clipL
   s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
   auto v = to_segments(segs, nSegs);
   plan_stream(e->g, e->sampleRate, nIn, nOut, nCalls, clipLen, v.data(), nSegs, s.plan);
+  s.gateIn = nIn; s.gateCalls = nCalls;
   s.planned = true; e->committed = false;
   return 0;
 }
@@ -817,6 +866,8 @@ int bsb_rebind(bsb_engine *e, int si, const float *dClip, float *dOut) {
   e->streams[si].clip = dClip; e->streams[si].out = dOut;
   e->hs[si].clip = dClip; e->hs[si].out = dOut;
   h2d(e->dStreams + si, &e->hs[si], sizeof(StreamDev), 0);
+  for (size_t i = 0; i < e->gate.size(); ++i)
+    if (e->gateStream[i] == si) { e->gate[i].clip = dClip; h2d(e->dGate + i, &e->gate[i], sizeof(GateDev), 0); }
   return 0;
 }
 
@@ -892,6 +943,19 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
     free_batch(e);
     return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);
   }
+  e->gate.clear(); e->gateStream.clear(); e->gateCallsTotal = 0; e->gateMaxCalls = 0;
+  for (int s = 0; s < S; ++s) {
+    const Stream &x = e->streams[s];
+    if (x.gateIn < 1 || x.gateCalls < 1) continue;
+    e->gate.push_back(GateDev{x.clip, x.clipLen, x.gateCalls, e->gateCallsTotal, x.gateIn, 0}); e->gateStream.push_back(s);
+    e->gateCallsTotal += x.gateCalls; e->gateMaxCalls = std::max(e->gateMaxCalls, x.gateCalls);
+  }
+  e->dGate = nullptr; e->dLoud = nullptr; e->dFired = nullptr;
+  if (!e->gate.empty()) {
+    e->dGate = upload(e, e->gate, own); e->dLoud = dalloc<uint8_t>((size_t)e->gateCallsTotal, own); e->dFired = dalloc<int>(e->gate.size(), own);
+    if (!e->dGate || !e->dLoud || !e->dFired) { free_batch(e); return e->fail("device allocation failed (gate watch)"); }
+    dzero(e->dFired, e->gate.size() * sizeof(int), 0);
+  }
   e->committed = true;
   return 0;
 }
@@ -913,6 +977,10 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     if (launch_chunk(e, slot0, e->chunk, q, q, 0, 3, kSynthEmit | kSynthAdd)) return -1;
   for (int s = 0; s < S && hOuts; ++s)
     std::memcpy(hOuts[s], e->streams[s].out, (size_t)g.C * e->hs[s].nOut * sizeof(float));
+  for (size_t i = 0; i < e->gate.size(); ++i) {
+    for (long long k = 0; k < e->gate[i].nCalls; ++k) e->dLoud[e->gate[i].callBase + k] = gate_call_loud(e->gate[i], g.C, k);
+    e->dFired[i] = gate_count(e->gate[i], g.L, e->dLoud);
+  }
 #else
   e->spans.clear(); e->evUsed = 0;
   const bool two = e->overlap && e->recBuf[1] != nullptr && e->maxBlocks > e->chunk;
@@ -960,6 +1028,10 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     cudaEvent_t a = e->get_event(), b = e->get_event();
     cudaEventRecord(a, e->sIn); cudaEventRecord(b, e->sOut);
     cudaStreamWaitEvent(q, a, 0); cudaStreamWaitEvent(q, b, 0);
+  }
+  if (!e->gate.empty()) {   // every clip sample is on the device by now
+    gate_energy_kernel<<<dim3((unsigned)((e->gateMaxCalls + 127) / 128), (unsigned)e->gate.size()), 128, 0, q>>>(e->dGate, g.C, e->dLoud);
+    gate_count_kernel<<<(unsigned)((e->gate.size() + 63) / 64), 64, 0, q>>>(e->dGate, (int)e->gate.size(), g.L, e->dLoud, e->dFired);
   }
   if (cudaGetLastError() != cudaSuccess) return e->fail("copy or launch failed");
 #endif

@@ -324,7 +324,8 @@ def main_gpu(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         timed = {k: v for k, v in stats.items() if v["ms"] > 0}
-        dom = max(timed, key=lambda k: timed[k]["ms"])
+        timed_iso = {k: v for k, v in stats_iso.items() if v["ms"] > 0}
+        dom = max(timed_iso or timed, key=lambda k: (timed_iso or timed)[k]["ms"])   # dominant = most device time when run alone
         kernels = {}
         for k, v in stats.items():
             bpu = stage_bytes(k, geom)
@@ -342,6 +343,7 @@ def main_gpu(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
+                    "achieved_isolated": iso.get(dom, {}).get("achieved_gbs"), "frac_isolated": iso.get(dom, {}).get("frac"),
                     "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_launch": d["bytes_per_unit"] * d["units"] / max(1, d["launches"]) if d["bytes_per_unit"] else None,
                     "avg_launch_ms": d["ms_per_step"] / max(1, d["launches"]), "kernels": kernels, "kernels_isolated": iso,

@@ -108,6 +108,11 @@ int bsb_chunk_blocks(const bsb_engine *e);
 /* kernel launches issued by the last bsb_run, and a read-out of one block record (for the indexing tests):
  * out[0]=flags out[1]=timeFactor bits, out[2..4]=cur window {start lo hi}, out[5..7]=prev window */
 long long bsb_launch_count(const bsb_engine *e);
+/* Streaming drives only (bsb_add_streaming): the reference's process() stops running blocks after 2*blockSamples
+ * silent input samples (its "silence gate", W#48 7838-7943 -- data dependent, so the ahead-of-time block plan of the
+ * batched path does not follow it).  Every run re-derives, from the clips as they are on the device, how many
+ * process() calls the reference would have gated; 0 = the batch result is the reference's.  Synchronises. */
+long long bsb_gate_events(bsb_engine *e);
 int bsb_block_info(const bsb_engine *e, int stream, long long block, long long out[8]);
 /* Per-kernel accounting of the last bsb_run.  launches and units (analysis: window x channel transforms actually
  * computed; other kernels: channel-blocks) are always counted; device milliseconds only while profiling is on (one

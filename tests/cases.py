@@ -184,6 +184,27 @@ def run_cases_batch(bs, cases, lib=None, device=None, chunk_blocks=0):
     return res
 
 
+def expected_gate_events(clip, n_in, n_calls, block_samples):
+    """How many process(n_in, .) calls the reference short-circuits (W#48 7838-7943): a call is silent when the f32 sum
+    of squares of its input, accumulated channel by channel in sample order, is below 1e-15; once 2L silent samples
+    have been counted every further silent call is gated."""
+    counter = fired = 0
+    for k in range(n_calls):
+        total = np.float32(0.0)
+        for c in range(clip.shape[0]):
+            x = clip[c, k * n_in:(k + 1) * n_in]
+            if np.any(x):
+                for v in x:
+                    total = np.float32(np.float32(v * v) + total)
+        if total >= np.float32(1e-15):
+            counter = 0
+        elif counter >= 2 * block_samples:
+            fired += 1
+        else:
+            counter += n_in
+    return fired
+
+
 def config_key(case):
     return (case.get("preset", "default"), tuple(case["block"]) if case.get("block") else None, case["sr"],
             case["clip"][2] if case["clip"][0] in ("noise", "tones") else (case["clip"][3] if case["clip"][0] == "sweep" else 2))

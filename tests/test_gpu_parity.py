@@ -79,6 +79,20 @@ def test_compat_shim_gate_and_flush_on_gpu(name, bs, golden):
     assert_matches_golden(name, y, golden)
 
 
+def test_batch_reports_when_the_silence_gate_would_fire(bs):
+    import torch
+    case = cases.SHIM_CASES["gate_default"]
+    loud = dict(case); loud["clip"] = ("survey", 20000)
+    for c in (case, loud):
+        clip = cases.make_clip(c["clip"])
+        eng = cases.make_batch(bs, c, 2)
+        eng.plan([torch.from_numpy(clip).cuda().contiguous()], [cases.batch_drive(bs, c, clip.shape[1])])
+        eng.run()
+        want = cases.expected_gate_events(clip, c["n_in"], clip.shape[1] // c["n_in"], eng.blockSamples())
+        assert eng.gate_events() == want
+        eng.close()
+
+
 def test_block_schedule_bit_exact(bs):
     """frame/hop indexing: the device-side block table equals the one derived from the worklet arithmetic."""
     import torch

@@ -137,3 +137,17 @@ def test_edge_cases_empty_tiny_and_ragged(emu):
     eng = bs.BatchStretch(2, 48000.0, lib=emu)
     outs = eng.plan([clips[0]], [bs.KioskDrive(0, [bs.segment()])]); eng.run(); eng.close()
     assert outs[0].shape == (2, 0)
+
+
+def test_batch_reports_when_the_silence_gate_would_fire(emu):
+    """The batched path does not model process()'s silence gate; it counts the calls the reference would have gated."""
+    case = cases.SHIM_CASES["gate_default"]
+    loud = dict(case); loud["clip"] = ("survey", 20000)
+    for c, want_some in ((case, True), (loud, False)):
+        clip = cases.make_clip(c["clip"])
+        eng = cases.make_batch(bs, c, 2, lib=emu)
+        eng.plan([np.ascontiguousarray(clip)], [cases.batch_drive(bs, c, clip.shape[1])])
+        eng.run()
+        want = cases.expected_gate_events(clip, c["n_in"], clip.shape[1] // c["n_in"], eng.blockSamples())
+        assert eng.gate_events() == want and (want > 0) == want_some
+        eng.close()
