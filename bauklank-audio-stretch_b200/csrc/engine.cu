@@ -257,15 +257,30 @@ static int chain_warps(int C, int longStep, int nSlots) {
 
 template <int C>
 static void launch_chain(int S, int warps, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
-                         const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st) {
-  chain_kernel<C><<<S, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st);
+                         const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st, int ctas, int *prog) {
+  chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog);
 }
 typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
-                                long long, int, const cf *, cf *, const StateDev &);
+                                long long, int, const cf *, cf *, const StateDev &, int, int *);
 static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>, launch_chain<3>, launch_chain<4>,
                                                 launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
 template <int C> static cudaError_t chain_attr(size_t smem) {
   return cudaFuncSetAttribute(chain_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int C> static int chain_occ(int threads, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_kernel<C>, threads, smem) != cudaSuccess) n = 1;
+  return n < 1 ? 1 : n;
+}
+static int chain_resident_ctas(int C, int threads, size_t smem) {   // chain CTAs the whole GPU holds at once
+  int dev = 0, sms = 1; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int occ;
+  switch (C) {
+    case 1: occ = chain_occ<1>(threads, smem); break; case 2: occ = chain_occ<2>(threads, smem); break; case 3: occ = chain_occ<3>(threads, smem); break;
+    case 4: occ = chain_occ<4>(threads, smem); break; case 5: occ = chain_occ<5>(threads, smem); break; case 6: occ = chain_occ<6>(threads, smem); break;
+    case 7: occ = chain_occ<7>(threads, smem); break; default: occ = chain_occ<8>(threads, smem); break;
+  }
+  return sms * occ;
 }
 static cudaError_t chain_set_smem(int C, size_t smem) {
   switch (C) {
@@ -360,6 +375,14 @@ struct bsb_engine {
   uint32_t *dSeeds = nullptr;
   StateDev st{}; cf *specIn = nullptr, *specOut = nullptr;
   int chunk = 0; long long maxBlocks = 0, totalBlocks = 0, launches = 0;
+  // the run as a list of time chunks.  All streams advance together; they are kept longest first, so the streams with
+  // blocks left are always a prefix.  Once few enough are left, a chunk covers `ctas` x 256 blocks per stream and the
+  // chain wavefront of a stream is relayed across `ctas` CTAs (chain.cuh): the SMs the finished streams freed shorten the
+  // remaining streams' critical path instead of idling.
+  struct Chunk { long long slot0; int nSlots, nLive, ctas; };
+  std::vector<Chunk> chunks;
+  std::vector<int> order, posOf;   // hs[pos] describes streams[order[pos]]
+  int *dChainProg = nullptr;
   std::vector<long long> blockBase;
   std::vector<BlockRec> hostBlocks;
   std::vector<long long> needEnd;   // [chunk][stream]: clip samples (per channel) the chunk's analysis windows reach
@@ -440,9 +463,9 @@ static void reset_state(bsb_engine *e, stream_t q) {
 // one time-chunk: stages bit0 = analysis + map + terms + chain, bit1 = synthesis (with `synthMode`)
 // Front half (analysis, map, terms, carry) goes to qF, back half (chain, synthesis) to qB; with two different streams
 // the back half of chunk i runs beside the front half of chunk i+1, handing the term records over in buffer `buf`.
-static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF, stream_t qB, int buf, int stages, int synthMode) {
+static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, int ctas, stream_t qF, stream_t qB, int buf, int stages, int synthMode) {
   const Geometry &g = e->g;
-  const int S = (int)e->hs.size();
+  const int S = nLive;   // streams are kept longest first: the ones with blocks left at slot0 are the first nLive
   const size_t CB = (size_t)g.C * g.B;
   e->st.rec = e->recBuf[buf];
   StateDev &st = e->st;
@@ -595,7 +618,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
   }
 #else
   const size_t smA = 4 * (size_t)g.M * sizeof(float);
-  const int chainWarps = chain_warps(g.C, g.longStep, nSlots);
+  const int chainWarps = chain_warps(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots);
   const size_t smT = preterms_smem_floats(g.C, g.longStep) * sizeof(float);
   const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
   const bool twoStreams = (qF != qB);
@@ -645,8 +668,9 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, stream_t qF,
       carry_kernel<<<S, 256, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     if (twoStreams) { cudaEventRecord(e->evFront[buf], qF); cudaStreamWaitEvent(qB, e->evFront[buf], 0); }
     q = qB;
+    if (ctas > 1) cudaMemsetAsync(e->dChainProg, 0, (size_t)S * ctas * sizeof(int), q);
     span("chain_kernel", nBlk * g.C, [&] {
-      kChainLaunch[g.C - 1](S, chainWarps, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st); });
+      kChainLaunch[g.C - 1](S, chainWarps, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st, ctas, e->dChainProg); });
     if (twoStreams) { cudaEventRecord(e->evBack[buf], qB); e->backUsed[buf] = true; }
     st.parity ^= 1;
   }
@@ -864,11 +888,23 @@ int bsb_add_streaming(bsb_engine *e, int si, const float *dClip, long long clipL
 int bsb_rebind(bsb_engine *e, int si, const float *dClip, float *dOut) {
   if (!e->committed || si < 0 || si >= (int)e->streams.size()) return e->fail("rebind needs a committed batch and a valid stream");
   e->streams[si].clip = dClip; e->streams[si].out = dOut;
-  e->hs[si].clip = dClip; e->hs[si].out = dOut;
-  h2d(e->dStreams + si, &e->hs[si], sizeof(StreamDev), 0);
+  const int pos = e->posOf[si];
+  e->hs[pos].clip = dClip; e->hs[pos].out = dOut;
+  h2d(e->dStreams + pos, &e->hs[pos], sizeof(StreamDev), 0);
   for (size_t i = 0; i < e->gate.size(); ++i)
     if (e->gateStream[i] == si) { e->gate[i].clip = dClip; h2d(e->dGate + i, &e->gate[i], sizeof(GateDev), 0); }
   return 0;
+}
+
+#ifdef BS_HOSTEMU
+static int chain_warps(int, int, int nSlots) { return std::max(1, std::min(8, (nSlots + 31) / 32)); }   // (planning only)
+#endif
+static int chain_capacity(bsb_engine *e, int threads) {   // chain CTAs resident at once on this GPU
+#ifdef BS_HOSTEMU
+  (void)e; (void)threads; return 296;
+#else
+  return std::max(1, chain_resident_ctas(e->g.C, threads, chain_smem_bytes(e->g.C, e->g.longStep, threads / 32)));
+#endif
 }
 
 int bsb_commit(bsb_engine *e, int chunkBlocks) {
@@ -878,9 +914,14 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   free_batch(e);
   std::vector<BlockRec> blocks; std::vector<BlockRec2> blocks2; std::vector<Window> windows; std::vector<uint32_t> seeds(S);
   e->hs.assign(S, StreamDev{}); e->blockBase.assign(S, 0); e->maxBlocks = 0;
+  for (int s = 0; s < S; ++s) if (!e->streams[s].planned) return e->fail("stream %d was not added", s);
+  // longest stream first (stable): the streams that still have blocks at any point of the run are a prefix
+  e->order.resize(S); e->posOf.resize(S);
+  for (int s = 0; s < S; ++s) e->order[s] = s;
+  std::stable_sort(e->order.begin(), e->order.end(), [&](int a, int b) { return e->streams[a].plan.blocks.size() > e->streams[b].plan.blocks.size(); });
   for (int s = 0; s < S; ++s) {
-    Stream &st = e->streams[s];
-    if (!st.planned) return e->fail("stream %d was not added", s);
+    Stream &st = e->streams[e->order[s]];
+    e->posOf[e->order[s]] = s;
     e->blockBase[s] = (long long)blocks.size();
     blocks.insert(blocks.end(), st.plan.blocks.begin(), st.plan.blocks.end());
     blocks2.insert(blocks2.end(), st.plan.blocks2.begin(), st.plan.blocks2.end());
@@ -897,19 +938,45 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   const size_t CB = (size_t)g.C * g.B;
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
   const size_t perSlot = (size_t)S * ((size_t)g.C * g.L * 4 + (size_t)g.B * 12 + CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (e->overlap ? 2 : 1) * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
-  if (chunkBlocks <= 0) {
+  const bool autoChunk = chunkBlocks <= 0;
+  if (autoChunk) {
     const size_t budget = (size_t)56 << 30;
     chunkBlocks = (int)std::min<size_t>(256, std::max<size_t>(1, budget / perSlot));
     if (chunkBlocks > 32) chunkBlocks &= ~31;   // whole warps of the chain wavefront
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
   e->chunk = chunkBlocks;
-  e->nChunks = (int)((e->maxBlocks + chunkBlocks - 1) / chunkBlocks);
+  // slots allocated in all: S x chunk, or -- a small batch of long streams -- as many as the chain kernel can work on at
+  // once when every stream's wavefront is relayed across several CTAs
+  const int perPass = 32 * chain_warps(g.C, g.longStep, 1 << 20);
+  const int cap = chain_capacity(e, perPass);
+  size_t allocSlots = (size_t)S * chunkBlocks;
+  const bool relayOk = autoChunk && chunkBlocks >= perPass && !e->dg.incremental;
+  if (relayOk) {
+    const size_t want = (size_t)S * (size_t)((e->maxBlocks + perPass - 1) / perPass) * perPass;
+    const size_t room = std::min<size_t>(((size_t)56 << 30) / (perSlot / S), (size_t)cap * perPass);
+    allocSlots = std::max(allocSlots, std::min(want, room));
+  }
+  e->chunks.clear();
+  for (long long pos = 0; pos < std::max<long long>(e->maxBlocks, 1);) {
+    int nLive = 0;
+    while (nLive < S && e->hs[nLive].nBlocks > pos) ++nLive;
+    if (nLive < 1) nLive = 1;
+    bsb_engine::Chunk c{pos, chunkBlocks, nLive, 1};
+    if (relayOk) {
+      long long k = std::min<long long>(cap / nLive, (long long)(allocSlots / ((size_t)nLive * perPass)));
+      k = std::min<long long>(k, (e->maxBlocks - pos + perPass - 1) / perPass);
+      if (k > 1) { c.ctas = (int)k; c.nSlots = (int)k * perPass; }
+    }
+    e->chunks.push_back(c);
+    pos += c.nSlots;
+  }
+  e->nChunks = (int)e->chunks.size();
   e->needEnd.assign((size_t)std::max(1, e->nChunks) * S, 0);
   for (int s = 0; s < S; ++s) {   // running maximum of the analysis windows' reach, chunk by chunk (for bsb_run_host)
     long long reach = 0;
     for (int i = 0; i < e->nChunks; ++i) {
-      const long long m0 = (long long)i * chunkBlocks, m1 = std::min<long long>(m0 + chunkBlocks, e->hs[s].nBlocks);
+      const long long m0 = e->chunks[i].slot0, m1 = std::min<long long>(m0 + e->chunks[i].nSlots, e->hs[s].nBlocks);
       for (long long m = m0; m < m1; ++m)
         for (int w = 0; w < 2; ++w) {
           const Window &x = windows[2 * (e->blockBase[s] + m) + w];
@@ -921,10 +988,11 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   auto &own = e->batchOwned;
   e->dStreams = upload(e, e->hs, own); e->dBlocks = upload(e, blocks, own); e->dBlocks2 = upload(e, blocks2, own);
   e->dWindows = upload(e, windows, own); e->dSeeds = upload(e, seeds, own);
-  e->specIn = dalloc<cf>((size_t)S * chunkBlocks * 2 * CB, own);
-  e->specOut = dalloc<cf>((size_t)S * chunkBlocks * CB, own);
+  e->specIn = dalloc<cf>(allocSlots * 2 * CB, own);
+  e->specOut = dalloc<cf>(allocSlots * CB, own);
+  e->dChainProg = dalloc<int>((size_t)std::max(cap, S) + 64, own);
   StateDev &st = e->st;
-  const size_t nSlotTot = (size_t)S * chunkBlocks;
+  const size_t nSlotTot = allocSlots;
   st.outSpec = dalloc<cf>(S * CB, own); st.predE[0] = dalloc<float>(S * CB, own); st.predE[1] = dalloc<float>(S * CB, own);
   st.lastInput = dalloc<cf>(S * CB, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
   st.ring[0] = dalloc<float>((size_t)S * g.C * g.L, own); st.ring[1] = dalloc<float>((size_t)S * g.C * g.L, own);
@@ -932,12 +1000,12 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
   st.energy = dalloc<float>(nSlotTot * g.B, own); st.smoothed = dalloc<float>(nSlotTot * g.B, own); st.fm = dalloc<float>(nSlotTot * fm_pitch(g.B), own);
-  const size_t recFloats = (size_t)S * ((chunkBlocks + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
+  const size_t recFloats = ((allocSlots + 31) / 32 + S) * rec_group_floats(g.B, g.longStep, g.C);
   e->recBuf[0] = dalloc<float>(recFloats, own);
-  e->recBuf[1] = (e->overlap && e->maxBlocks > chunkBlocks) ? dalloc<float>(recFloats, own) : nullptr;   // only for chunk pipelining
+  e->recBuf[1] = (e->overlap && e->chunks.size() > 1) ? dalloc<float>(recFloats, own) : nullptr;   // only for chunk pipelining
   st.rec = e->recBuf[0];
   st.seeds = e->dSeeds; st.parity = 0;
-  if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !st.outSpec ||
+  if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !e->dChainProg || !st.outSpec ||
       !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring[0] || !st.ring[1] || !st.frames || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase || !st.energy || !st.smoothed || !st.fm ||
       !st.rec) {
     free_batch(e);
@@ -972,18 +1040,18 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
   for (auto &k : e->kstat) { k.ms = 0.0; k.launches = 0; k.units = 0; }
 #ifdef BS_HOSTEMU
   for (int s = 0; s < S && hClips; ++s)
-    std::memcpy((void *)e->streams[s].clip, hClips[s], (size_t)g.C * e->hs[s].clipLen * sizeof(float));
-  for (long long slot0 = 0, i = 0; slot0 < e->maxBlocks; slot0 += e->chunk, ++i)
-    if (launch_chunk(e, slot0, e->chunk, q, q, 0, 3, kSynthEmit | kSynthAdd)) return -1;
+    std::memcpy((void *)e->streams[s].clip, hClips[s], (size_t)g.C * e->streams[s].clipLen * sizeof(float));
+  for (const bsb_engine::Chunk &c : e->chunks)
+    if (e->maxBlocks > 0 && launch_chunk(e, c.slot0, c.nSlots, c.nLive, c.ctas, q, q, 0, 3, kSynthEmit | kSynthAdd)) return -1;
   for (int s = 0; s < S && hOuts; ++s)
-    std::memcpy(hOuts[s], e->streams[s].out, (size_t)g.C * e->hs[s].nOut * sizeof(float));
+    std::memcpy(hOuts[s], e->streams[s].out, (size_t)g.C * e->streams[s].plan.nOut * sizeof(float));
   for (size_t i = 0; i < e->gate.size(); ++i) {
     for (long long k = 0; k < e->gate[i].nCalls; ++k) e->dLoud[e->gate[i].callBase + k] = gate_call_loud(e->gate[i], g.C, k);
     e->dFired[i] = gate_count(e->gate[i], g.L, e->dLoud);
   }
 #else
   e->spans.clear(); e->evUsed = 0;
-  const bool two = e->overlap && e->recBuf[1] != nullptr && e->maxBlocks > e->chunk;
+  const bool two = e->overlap && e->recBuf[1] != nullptr && e->chunks.size() > 1;
   const bool host = hClips != nullptr && hOuts != nullptr;
   if (two || host) {   // fork: the internal streams start after everything already queued on the caller's stream
     cudaEventRecord(e->evFork, q);
@@ -993,32 +1061,35 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
   }
   std::vector<long long> copied(host ? S : 0, 0);
   long long i = 0;
-  for (long long slot0 = 0; slot0 < e->maxBlocks; slot0 += e->chunk, ++i) {
+  for (const bsb_engine::Chunk &ck : e->chunks) {
+    if (e->maxBlocks <= 0) break;
+    const long long slot0 = ck.slot0;
     stream_t qF = two ? e->sFront : q, qB = two ? e->sBack : q;
     if (host) {   // clip samples first needed by this chunk, all channels of a stream in one strided copy
       for (int s = 0; s < S; ++s) {
         const long long need = e->needEnd[(size_t)i * S + s], have = copied[s];
         if (need > have) {
           const StreamDev &d = e->hs[s];
-          cudaMemcpy2DAsync((void *)(d.clip + have), (size_t)d.clipLen * sizeof(float), hClips[s] + have, (size_t)d.clipLen * sizeof(float),
+          cudaMemcpy2DAsync((void *)(d.clip + have), (size_t)d.clipLen * sizeof(float), hClips[e->order[s]] + have, (size_t)d.clipLen * sizeof(float),
                             (size_t)(need - have) * sizeof(float), (size_t)g.C, cudaMemcpyHostToDevice, e->sIn);
           copied[s] = need;
         }
       }
       cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, e->sIn); cudaStreamWaitEvent(qF, ev, 0);
     }
-    if (launch_chunk(e, slot0, e->chunk, qF, qB, two ? (int)(i & 1) : 0, 3, kSynthEmit | kSynthAdd)) return -1;
+    if (launch_chunk(e, slot0, ck.nSlots, ck.nLive, ck.ctas, qF, qB, two ? (int)(i & 1) : 0, 3, kSynthEmit | kSynthAdd)) return -1;
     if (host) {   // the output samples this chunk emitted
       cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, qB); cudaStreamWaitEvent(e->sOut, ev, 0);
       for (int s = 0; s < S; ++s) {
         const StreamDev &d = e->hs[s];
         const long long n0 = std::min<long long>(slot0 * g.H, d.nOut);
-        const long long n1 = std::min<long long>(std::min<long long>(slot0 + e->chunk, d.nBlocks) * (long long)g.H, d.nOut);
+        const long long n1 = std::min<long long>(std::min<long long>(slot0 + ck.nSlots, d.nBlocks) * (long long)g.H, d.nOut);
         if (n1 > n0)
-          cudaMemcpy2DAsync(hOuts[s] + n0, (size_t)d.nOut * sizeof(float), d.out + n0, (size_t)d.outStride * sizeof(float),
+          cudaMemcpy2DAsync(hOuts[e->order[s]] + n0, (size_t)d.nOut * sizeof(float), d.out + n0, (size_t)d.outStride * sizeof(float),
                             (size_t)(n1 - n0) * sizeof(float), (size_t)g.C, cudaMemcpyDeviceToHost, e->sOut);
       }
     }
+    ++i;
   }
   if (two) {   // join
     cudaEventRecord(e->evJoin[0], e->sFront); cudaEventRecord(e->evJoin[1], e->sBack);
@@ -1239,7 +1310,7 @@ void compat_launch(Compat *c, long long m, const BlockRec &rec, BlockRec2 rec2, 
     h2d(e->dWindows, win, 2 * sizeof(Window), 0);
     h2d(e->dSeeds, &c->rngState, sizeof(uint32_t), 0);
   }
-  if (launch_chunk(e, m, 1, 0, 0, 0, stages, mode)) bs::die(e->err.c_str());
+  if (launch_chunk(e, m, 1, 1, 1, 0, 0, 0, stages, mode)) bs::die(e->err.c_str());
   if ((stages & 1) && !((rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor) <= 2.0f) && c->g.B >= 2)
     c->rngState = minstd_jump(c->rngState, (uint32_t)(2 * c->g.B - 2));
 }

@@ -63,6 +63,25 @@ def test_fresh_random_cases_against_live_oracle(seed, bs):
     assert same, "within tolerance but not bit-identical: err %.3g snr %.1f dB" % (err, snr)
 
 
+def test_relayed_wavefront_for_long_streams(bs):
+    """Few long streams: a chunk covers several hundred blocks per stream and each stream's chain wavefront is relayed
+    across several CTAs (chain.cuh).  Three streams of different lengths (the live prefix shrinks along the run), one of
+    them with random time factors; against the CPU oracle, and against the same batch run in plain 96-block chunks."""
+    specs = [dict(n=150000, rate=0.6, st=4.0, seed=3), dict(n=90000, rate=0.45, st=-3.0, seed=4), dict(n=60000, rate=1.3, st=7.0, seed=5)]
+    cs = []
+    for sp in specs:
+        cs.append(dict(drive="kiosk", clip=("noise", sp["n"], 2, sp["seed"], 0.2), sr=48000, n_out=int(sp["n"] / sp["rate"]), preset="default",
+                       seed=sp["seed"], segments=[cases.seg(rate=sp["rate"], semitones=sp["st"])]))
+    got = cases.run_cases_batch(bs, cs, device="cuda:0")
+    plain = cases.run_cases_batch(bs, cs, device="cuda:0", chunk_blocks=96)
+    for c, y, z in zip(cs, got, plain):
+        assert cases.compare(y, z)[0], "relayed and plain chunking differ"
+        eng = refdrive.PortEngine(seed=c["seed"])
+        ref = cases.run_case(eng, c); eng.close()
+        same, err, snr = cases.compare(y, ref)
+        assert same, "not bit-identical to the oracle: err %.3g snr %.1f dB" % (err, snr)
+
+
 @pytest.mark.parametrize("name", ["KA5", "stream_480_512_cheaper", "lowlat_8ch_formant_auto"])
 def test_compat_shim_on_gpu(name, bs, golden):
     """The reference's 18 entry points, host buffers in / host buffers out, one block per launch."""
