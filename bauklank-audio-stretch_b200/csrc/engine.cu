@@ -204,7 +204,7 @@ __global__ void freqest_kernel(int S, const StreamDev *streams, const BlockRec *
 }
 
 // preterms: one CTA per (stream, block): the per-bin coefficient records of the phase prediction
-__global__ void __launch_bounds__(256) preterms_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+__global__ void __launch_bounds__(256, 6) preterms_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
                                                        const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, StateDev st) {
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
   const StreamDev sd = streams[s];

@@ -854,7 +854,9 @@ BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
 // the max-channel index travels in the sign bit of channel 1's energy (energies are never negative) and the fields
 // behind it move up by one.  Other channel counts keep the logical row, padded to whole 128-byte lines.
 BS_HHD int nr_pitch(int C) { return C == 2 ? 24 : (nr_floats(C) + 31) & ~31; }
-BS_HHD int nr_stage(int C) { return C == 2 ? 29 : nr_pitch(C) + 4; }   // row stride of preterms' staging rows (odd for stereo: conflict-free scalar access)
+// row stride of preterms' staging rows.  Stereo rows are staged in their stored (packed) form, 24 floats in a 28-float
+// pitch: 16-byte stores by consecutive threads then fall into eight different bank groups.
+BS_HHD int nr_stage(int C) { return C == 2 ? 28 : nr_pitch(C) + 4; }
 BS_HD float pack2_field(const float *logical, int f) {                 // physical field f of a stereo row
   if (f < 8) return logical[f];
   float v = logical[f + 1];
@@ -919,6 +921,7 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
       }
       // S5 coefficients (W#48 9314-9455) and the maximum-energy channel
       int mc = 0; float me = 0.f, pRe = 0.f, pIm = 0.f;
+      float enC[2], inRe[2], inIm[2], s5[2][3];   // stereo: the row stays in registers
       for (int c = 0; c < C; ++c) {
         const float en = lerp_f(inEnergy + (size_t)c * B, B, low, fr) * gpos;
         const cf in = lerp_c(inp + (size_t)c * B, B, low, fr);
@@ -926,16 +929,22 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
         const float prevE = prevMap ? (lerp_f(prevInE + (size_t)c * B, B, lowP, frP) * gP) : prevEState[(size_t)c * B + k];
         if (predEOut) predEOut[(size_t)c * B + k] = en;
         const float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
-        rb[3 * c] = tRe; rb[3 * c + 1] = tIm; rb[3 * c + 2] = ((en > prevE) ? en : prevE) + 1e-15f;
-        ra[9 + 5 * c] = en; ra[9 + 5 * c + 1] = in.re; ra[9 + 5 * c + 2] = in.im;
+        const float dv = ((en > prevE) ? en : prevE) + 1e-15f;
+        if (CT == 2) { enC[c & 1] = en; inRe[c & 1] = in.re; inIm[c & 1] = in.im; s5[c & 1][0] = tRe; s5[c & 1][1] = tIm; s5[c & 1][2] = dv; }
+        else {
+          rb[3 * c] = tRe; rb[3 * c + 1] = tIm; rb[3 * c + 2] = dv;
+          ra[9 + 5 * c] = en; ra[9 + 5 * c + 1] = in.re; ra[9 + 5 * c + 2] = in.im;
+        }
         if (c == 0 || en > me) { me = en; mc = c; pRe = in.re; pIm = in.im; }
       }
+      float twRe[2], twIm[2];
       for (int c = 0; c < C; ++c) {   // channel twists: predIn[c] * conj(predIn[mc])
-        const float cRe = ra[9 + 5 * c + 1], cIm = ra[9 + 5 * c + 2];
-        ra[9 + 5 * c + 3] = (pIm * cIm) + (pRe * cRe);
-        ra[9 + 5 * c + 4] = (pRe * cIm) - (pIm * cRe);
+        const float cRe = CT == 2 ? inRe[c & 1] : ra[9 + 5 * c + 1], cIm = CT == 2 ? inIm[c & 1] : ra[9 + 5 * c + 2];
+        const float wRe = (pIm * cIm) + (pRe * cRe), wIm = (pRe * cIm) - (pIm * cRe);
+        if (CT == 2) { twRe[c & 1] = wRe; twIm[c & 1] = wIm; }
+        else { ra[9 + 5 * c + 3] = wRe; ra[9 + 5 * c + 4] = wIm; }
       }
-      ra[8] = __int_as_float_hd(mc);
+      if (CT != 2) ra[8] = __int_as_float_hd(mc);
       const cf *ic = inp + (size_t)mc * B;
       // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep and downward neighbours k+1,
       // k+longStep (whose predIn is re-interpolated here for channel mc).  With random time factors (timeFactor > 2)
@@ -960,7 +969,19 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
         d0 = (dD1.im * uN.im) + (dD1.re * uN.re); d1 = (dD1.re * uN.im) - (dD1.im * uN.re);
         if (k < B - longStep) { d2 = (dDL.im * uL.im) + (dDL.re * uL.re); d3 = (dDL.re * uL.im) - (dDL.im * uL.re); }
       }
-      ra[0] = u0; ra[1] = u1; ra[2] = u2; ra[3] = u3; ra[4] = d0; ra[5] = d1; ra[6] = d2; ra[7] = d3;
+      if (CT == 2) {   // the stored form (see unpack2_row): 24 floats, the max-channel index in the sign of channel 1's energy
+        f4 *pa = (f4 *)ra, *pb = (f4 *)(sm + (size_t)i * NR);
+        f4 v;
+        v.x = u0; v.y = u1; v.z = u2; v.w = u3; pa[0] = v;
+        v.x = d0; v.y = d1; v.z = d2; v.w = d3; pa[1] = v;
+        v.x = enC[0]; v.y = inRe[0]; v.z = inIm[0]; v.w = twRe[0]; pa[2] = v;
+        v.x = twIm[0]; v.y = (mc == 1) ? -enC[1] : enC[1]; v.z = inRe[1]; v.w = inIm[1]; pa[3] = v;
+        f2 w; w.x = twRe[1]; w.y = twIm[1]; *(f2 *)(ra + 16) = w;
+        w.x = s5[0][0]; w.y = s5[0][1]; *(f2 *)(sm + (size_t)i * NR + 18) = w;
+        v.x = s5[0][2]; v.y = s5[1][0]; v.z = s5[1][1]; v.w = s5[1][2]; pb[5] = v;
+      } else {
+        ra[0] = u0; ra[1] = u1; ra[2] = u2; ra[3] = u3; ra[4] = d0; ra[5] = d1; ra[6] = d2; ra[7] = d3;
+      }
     }
     BS_SYNC();
     // local rows [0, nOut) are complete: global rows k0 .. k0+nOut-1 (the last tile also flushes the R0 trailing rows)
@@ -968,15 +989,13 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
     const int nOut = lastTile ? nb + R0 : TB;
     for (int i = tid; i < nOut * (NRP / 4); i += nt) {   // whole sectors / lines, one 16-byte piece per thread
       const int r = i / (NRP / 4), f = i - r * (NRP / 4);
-      const float *lg = sm + (size_t)r * NR;
-      f4 v;
-      if (CT == 2) { v.x = pack2_field(lg, 4 * f); v.y = pack2_field(lg, 4 * f + 1); v.z = pack2_field(lg, 4 * f + 2); v.w = pack2_field(lg, 4 * f + 3); }
-      else v = ((const f4 *)lg)[f];
+      const f4 v = ((const f4 *)(sm + (size_t)r * NR))[f];   // staged in stored form: a plain copy
       ((f4 *)(recRows + (size_t)(k0 + r) * rowStride))[f] = v;
     }
     BS_SYNC();
+    const int SC = (CT == 2) ? SO - 1 : SO;   // floats of a staged row that belong to the chain part
     if (!lastTile)   // chain parts of this tile's last R0 bins belong to the first R0 rows of the next tile
-      for (int i = tid; i < R0 * SO; i += nt) { const int r = i / SO, f = i - r * SO; sm[(size_t)r * NR + f] = sm[(size_t)(TB + r) * NR + f]; }
+      for (int i = tid; i < R0 * SC; i += nt) { const int r = i / SC, f = i - r * SC; sm[(size_t)r * NR + f] = sm[(size_t)(TB + r) * NR + f]; }
     BS_SYNC();
   }
 }
