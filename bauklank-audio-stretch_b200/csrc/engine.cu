@@ -380,7 +380,8 @@ struct bsb_engine {
   // chain wavefront of a stream is relayed across `ctas` CTAs (chain.cuh): the SMs the finished streams freed shorten the
   // remaining streams' critical path instead of idling.
   struct Chunk { long long slot0; int nSlots, nLive, ctas; };
-  std::vector<Chunk> chunks;
+  std::vector<Chunk> chunks, chunksHost;     // device-resident audio / host audio (short first chunk)
+  std::vector<long long> needEndHost;
   std::vector<int> order, posOf;   // hs[pos] describes streams[order[pos]]
   int *dChainProg = nullptr;
   std::vector<long long> blockBase;
@@ -957,34 +958,41 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
     const size_t room = std::min<size_t>(((size_t)56 << 30) / (perSlot / S), (size_t)cap * perPass);
     allocSlots = std::max(allocSlots, std::min(want, room));
   }
-  e->chunks.clear();
-  for (long long pos = 0; pos < std::max<long long>(e->maxBlocks, 1);) {
-    int nLive = 0;
-    while (nLive < S && e->hs[nLive].nBlocks > pos) ++nLive;
-    if (nLive < 1) nLive = 1;
-    bsb_engine::Chunk c{pos, chunkBlocks, nLive, 1};
-    if (relayOk) {
-      long long k = std::min<long long>(cap / nLive, (long long)(allocSlots / ((size_t)nLive * perPass)));
-      k = std::min<long long>(k, (e->maxBlocks - pos + perPass - 1) / perPass);
-      if (k > 1) { c.ctas = (int)k; c.nSlots = (int)k * perPass; }
+  // `lead` > 0: a short first chunk, for bsb_run_host -- nothing can be computed before the first chunk's clip samples
+  // have crossed the bus, so the first chunk is kept small and the rest of the upload hides behind its kernels
+  auto build_chunks = [&](int lead, std::vector<bsb_engine::Chunk> &list, std::vector<long long> &need) {
+    list.clear();
+    for (long long pos = 0; pos < std::max<long long>(e->maxBlocks, 1);) {
+      int nLive = 0;
+      while (nLive < S && e->hs[nLive].nBlocks > pos) ++nLive;
+      if (nLive < 1) nLive = 1;
+      bsb_engine::Chunk c{pos, chunkBlocks, nLive, 1};
+      if (pos == 0 && lead > 0 && lead < chunkBlocks) c.nSlots = lead;
+      else if (relayOk) {
+        long long k = std::min<long long>(cap / nLive, (long long)(allocSlots / ((size_t)nLive * perPass)));
+        k = std::min<long long>(k, (e->maxBlocks - pos + perPass - 1) / perPass);
+        if (k > 1) { c.ctas = (int)k; c.nSlots = (int)k * perPass; }
+      }
+      list.push_back(c);
+      pos += c.nSlots;
     }
-    e->chunks.push_back(c);
-    pos += c.nSlots;
-  }
+    need.assign(std::max<size_t>(1, list.size()) * S, 0);
+    for (int s = 0; s < S; ++s) {   // running maximum of the analysis windows' reach, chunk by chunk (for bsb_run_host)
+      long long reach = 0;
+      for (size_t i = 0; i < list.size(); ++i) {
+        const long long m0 = list[i].slot0, m1 = std::min<long long>(m0 + list[i].nSlots, e->hs[s].nBlocks);
+        for (long long m = m0; m < m1; ++m)
+          for (int w = 0; w < 2; ++w) {
+            const Window &x = windows[2 * (e->blockBase[s] + m) + w];
+            if (x.hi > x.lo) reach = std::max(reach, x.start + x.hi);
+          }
+        need[i * S + s] = std::min<long long>(reach, e->hs[s].clipLen);
+      }
+    }
+  };
+  build_chunks(0, e->chunks, e->needEnd);
+  build_chunks(autoChunk && !e->dg.incremental ? 32 : 0, e->chunksHost, e->needEndHost);
   e->nChunks = (int)e->chunks.size();
-  e->needEnd.assign((size_t)std::max(1, e->nChunks) * S, 0);
-  for (int s = 0; s < S; ++s) {   // running maximum of the analysis windows' reach, chunk by chunk (for bsb_run_host)
-    long long reach = 0;
-    for (int i = 0; i < e->nChunks; ++i) {
-      const long long m0 = e->chunks[i].slot0, m1 = std::min<long long>(m0 + e->chunks[i].nSlots, e->hs[s].nBlocks);
-      for (long long m = m0; m < m1; ++m)
-        for (int w = 0; w < 2; ++w) {
-          const Window &x = windows[2 * (e->blockBase[s] + m) + w];
-          if (x.hi > x.lo) reach = std::max(reach, x.start + x.hi);
-        }
-      e->needEnd[(size_t)i * S + s] = std::min<long long>(reach, e->hs[s].clipLen);
-    }
-  }
   auto &own = e->batchOwned;
   e->dStreams = upload(e, e->hs, own); e->dBlocks = upload(e, blocks, own); e->dBlocks2 = upload(e, blocks2, own);
   e->dWindows = upload(e, windows, own); e->dSeeds = upload(e, seeds, own);
@@ -1002,7 +1010,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.energy = dalloc<float>(nSlotTot * g.B, own); st.smoothed = dalloc<float>(nSlotTot * g.B, own); st.fm = dalloc<float>(nSlotTot * fm_pitch(g.B), own);
   const size_t recFloats = ((allocSlots + 31) / 32 + S) * rec_group_floats(g.B, g.longStep, g.C);
   e->recBuf[0] = dalloc<float>(recFloats, own);
-  e->recBuf[1] = (e->overlap && e->chunks.size() > 1) ? dalloc<float>(recFloats, own) : nullptr;   // only for chunk pipelining
+  e->recBuf[1] = (e->overlap && e->chunksHost.size() > 1) ? dalloc<float>(recFloats, own) : nullptr;   // only for chunk pipelining
   st.rec = e->recBuf[0];
   st.seeds = e->dSeeds; st.parity = 0;
   if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !e->dChainProg || !st.outSpec ||
@@ -1051,8 +1059,10 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
   }
 #else
   e->spans.clear(); e->evUsed = 0;
-  const bool two = e->overlap && e->recBuf[1] != nullptr && e->chunks.size() > 1;
   const bool host = hClips != nullptr && hOuts != nullptr;
+  const std::vector<bsb_engine::Chunk> &chunks = host ? e->chunksHost : e->chunks;
+  const std::vector<long long> &needEnd = host ? e->needEndHost : e->needEnd;
+  const bool two = e->overlap && e->recBuf[1] != nullptr && chunks.size() > 1;
   if (two || host) {   // fork: the internal streams start after everything already queued on the caller's stream
     cudaEventRecord(e->evFork, q);
     if (two) { cudaStreamWaitEvent(e->sFront, e->evFork, 0); cudaStreamWaitEvent(e->sBack, e->evFork, 0); }
@@ -1061,13 +1071,13 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
   }
   std::vector<long long> copied(host ? S : 0, 0);
   long long i = 0;
-  for (const bsb_engine::Chunk &ck : e->chunks) {
+  for (const bsb_engine::Chunk &ck : chunks) {
     if (e->maxBlocks <= 0) break;
     const long long slot0 = ck.slot0;
     stream_t qF = two ? e->sFront : q, qB = two ? e->sBack : q;
     if (host) {   // clip samples first needed by this chunk, all channels of a stream in one strided copy
       for (int s = 0; s < S; ++s) {
-        const long long need = e->needEnd[(size_t)i * S + s], have = copied[s];
+        const long long need = needEnd[(size_t)i * S + s], have = copied[s];
         if (need > have) {
           const StreamDev &d = e->hs[s];
           cudaMemcpy2DAsync((void *)(d.clip + have), (size_t)d.clipLen * sizeof(float), hClips[e->order[s]] + have, (size_t)d.clipLen * sizeof(float),
