@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(32 * kSmoothWarps) map_smooth_kernel(DevGeom g
   }
 }
 
-__global__ void __launch_bounds__(128) map_peaks_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
+__global__ void __launch_bounds__(256) map_peaks_kernel(DevGeom g, const StreamDev *streams, const BlockRec *blocks, const BlockRec2 *blocks2,
                                                         long long slot0, int nSlots, StateDev st) {
   extern __shared__ float4 sm4[];
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
@@ -655,7 +655,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     };
     if (anyMapped) span("map_smooth_kernel", nBlk, [&] { smooth_all(0); });
     if (anyMapped) span("map_peaks_kernel", nBlk, [&] {
-      map_peaks_kernel<<<nCta, 128, smM, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
+      map_peaks_kernel<<<nCta, 256, smM, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
     if (anyAuto) span("map_smooth_kernel", 0, [&] { smooth_all(2); });
     if (anyAuto) span("freqest_kernel", nBlk, [&] { freqest_kernel<<<(S + 63) / 64, 64, 0, q>>>(S, e->dStreams, e->dBlocks, slot0, nSlots, st); });
     if (anyFormants) {

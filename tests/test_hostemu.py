@@ -151,3 +151,28 @@ def test_batch_reports_when_the_silence_gate_would_fire(emu):
         want = cases.expected_gate_events(clip, c["n_in"], clip.shape[1] // c["n_in"], eng.blockSamples())
         assert eng.gate_events() == want and (want > 0) == want_some
         eng.close()
+
+
+def test_longest_first_ordering_relay_chunks_and_host_audio(emu):
+    """Streams are kept longest first inside the engine and the tail of the run uses chunks of several hundred blocks per
+    stream (the relayed chain wavefront on the GPU); results and the stream <-> buffer association must not change.
+    Three mono streams of very different lengths in a small-block geometry, given shortest first; device-style run and
+    host-audio run (short first chunk) against the oracle."""
+    specs = [dict(n=9000, rate=1.4, st=5.0, seed=7), dict(n=60000, rate=0.55, st=-2.0, seed=8), dict(n=30000, rate=0.9, st=3.0, seed=9)]
+    cs = [dict(drive="kiosk", clip=("noise", sp["n"], 1, sp["seed"], 0.2), sr=44100, n_out=int(sp["n"] / sp["rate"]), block=(512, 128, 0),
+               seed=sp["seed"], segments=[cases.seg(rate=sp["rate"], semitones=sp["st"])]) for sp in specs]
+    refs = []
+    for c in cs:
+        eng = refdrive.PortEngine(seed=c["seed"]); refs.append(cases.run_case(eng, c)); eng.close()
+    got = cases.run_cases_batch(bs, cs, lib=emu)
+    for y, r in zip(got, refs):
+        assert cases.compare(y, r)[0]
+    clips = [np.ascontiguousarray(cases.make_clip(c["clip"])) for c in cs]
+    eng = cases.make_batch(bs, cs[0], 1, lib=emu)
+    outs = eng.plan([np.zeros_like(x) for x in clips], [cases.batch_drive(bs, c, x.shape[1]) for c, x in zip(cs, clips)])
+    assert eng.stream_blocks(1) > 256 > eng.stream_blocks(0)          # long enough for a relay chunk; given shortest first
+    host_outs = [np.zeros_like(o) for o in outs]
+    eng.run_host(clips, host_outs)
+    for y, r in zip(host_outs, refs):
+        assert cases.compare(y, r)[0]
+    eng.close()
