@@ -204,7 +204,7 @@ __global__ void freqest_kernel(int S, const StreamDev *streams, const BlockRec *
 }
 
 // preterms: one CTA per (stream, block): the per-bin coefficient records of the phase prediction
-__global__ void __launch_bounds__(256, 6) preterms_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+__global__ void __launch_bounds__(kTermTile, BS_TERM_CTAS) preterms_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
                                                        const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, StateDev st) {
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
   const StreamDev sd = streams[s];
@@ -664,7 +664,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
         map_fmapply_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, st); });
     }
     span("preterms_kernel", nBlk * g.C, [&] {
-      preterms_kernel<<<nCta, nt, smT, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
+      preterms_kernel<<<nCta, kTermTile, smT, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     if (needCarry) span("carry_kernel", 0, [&] {
       carry_kernel<<<S, 256, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     if (twoStreams) { cudaEventRecord(e->evFront[buf], qF); cudaStreamWaitEvent(qB, e->evFront[buf], 0); }

@@ -882,7 +882,13 @@ BS_HHD size_t rec_slot_offset(int slot, int B, int longStep, int C) {
 
 // Rows are produced in tiles of kTermTile bins staged in shared memory, so that every record row leaves the SM as part
 // of one contiguous, 16-byte-vectorised burst (a row mixes two bins R0 apart, hence the R0 rows carried tile to tile).
-constexpr int kTermTile = 256;
+#ifndef BS_TERM_TILE
+#define BS_TERM_TILE 128
+#endif
+#ifndef BS_TERM_CTAS
+#define BS_TERM_CTAS 10
+#endif
+constexpr int kTermTile = BS_TERM_TILE;
 BS_HHD size_t preterms_smem_floats(int C, int longStep) { return (size_t)(kTermTile + longStep + 1) * nr_stage(C); }
 
 template <int CT>

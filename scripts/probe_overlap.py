@@ -20,7 +20,7 @@ out_sec = sum(d.n_out for d in drives) / sr
 ref = None
 for v in variants.split(","):
     ov, chunk = (int(x) for x in v.split(":"))
-    eng = bs.BatchStretch(2, sr, preset="default")
+    eng = bs.BatchStretch(2, sr, preset="default", lib=bs.load_library(os.environ["BSLIB"]) if os.environ.get("BSLIB") else None)
     eng.set_overlap(bool(ov))
     outs = eng.plan(clips, drives, chunk_blocks=chunk)
     best = 1e9
