@@ -211,17 +211,18 @@ def test_run_host_pipelined_copies(bs, golden):
     names = ["KA6", "stream_100_900", "sweep_default"]
     cs = [cases.CASES[n] for n in names]
     clips = [cases.make_clip(c["clip"]) for c in cs]
-    eng = cases.make_batch(bs, cs[0], 2)
-    dclips = [torch.zeros(x.shape, dtype=torch.float32, device="cuda") for x in clips]
-    outs = eng.plan(dclips, [cases.batch_drive(bs, c, x.shape[1]) for c, x in zip(cs, clips)], chunk_blocks=24)
-    hin = [torch.from_numpy(x).pin_memory() for x in clips]
-    hout = [torch.zeros(tuple(o.shape), dtype=torch.float32).pin_memory() for o in outs]
-    for _ in range(2):
-        eng.run_host(hin, hout)
-        torch.cuda.synchronize()
-        for n, y in zip(names, hout):
-            assert_matches_golden(n, y.numpy(), golden)
-    eng.close()
+    for chunk in (24, 0):          # explicit small chunks; automatic (short first chunk for the upload, longest stream first)
+        eng = cases.make_batch(bs, cs[0], 2)
+        dclips = [torch.zeros(x.shape, dtype=torch.float32, device="cuda") for x in clips]
+        outs = eng.plan(dclips, [cases.batch_drive(bs, c, x.shape[1]) for c, x in zip(cs, clips)], chunk_blocks=chunk)
+        hin = [torch.from_numpy(x).pin_memory() for x in clips]
+        hout = [torch.zeros(tuple(o.shape), dtype=torch.float32).pin_memory() for o in outs]
+        for _ in range(2):
+            eng.run_host(hin, hout)
+            torch.cuda.synchronize()
+            for n, y in zip(names, hout):
+                assert_matches_golden(n, y.numpy(), golden)
+        eng.close()
 
 
 def test_control_trace_through_the_quantum_table(bs):
