@@ -467,7 +467,9 @@ static void reset_state(bsb_engine *e, stream_t q) {
 static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, int ctas, stream_t qF, stream_t qB, int buf, int stages, int synthMode) {
   const Geometry &g = e->g;
   const int S = nLive;   // streams are kept longest first: the ones with blocks left at slot0 are the first nLive
+#ifdef BS_HOSTEMU
   const size_t CB = (size_t)g.C * g.B;
+#endif
   e->st.rec = e->recBuf[buf];
   StateDev &st = e->st;
   const int nt = 256;
@@ -639,19 +641,11 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
       analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
     span("map_energy_kernel", nBlk * g.C, [&] {
       map_energy_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
-    // slices of slots whose smoother arrays (S * slice * B floats) stay L2 resident across the four sweeps
-    // (measured: slicing to keep the arrays L2 resident leaves too few threads in flight to cover the load latency, so
-    // one launch covers the whole chunk and the sweeps stream through HBM)
-    const int smSlice = nSlots;
+    // the smoothers: one launch over the whole chunk, one lane per (stream, block) (slicing the chunk so that the arrays stay
+    // L2 resident across the four sweeps was measured slower: too few threads left in flight)
     auto smooth_all = [&](int which) {
-      for (int t0 = 0; t0 < nSlots; t0 += smSlice) {
-        const int nT = std::min(smSlice, nSlots - t0);
-        bool any = false;
-        for (int s = 0; s < S && !any; ++s) any = slot0 + t0 < e->hs[s].nBlocks;
-        if (!any) break;
-        const size_t nThr = (size_t)S * ((nT + 31) & ~31);
-        map_smooth_kernel<<<(unsigned)((nThr + 32 * kSmoothWarps - 1) / (32 * kSmoothWarps)), 32 * kSmoothWarps, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, t0, nT, st, which);
-      }
+      const size_t nThr = (size_t)S * ((nSlots + 31) & ~31);
+      map_smooth_kernel<<<(unsigned)((nThr + 32 * kSmoothWarps - 1) / (32 * kSmoothWarps)), 32 * kSmoothWarps, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, S, 0, nSlots, st, which);
     };
     if (anyMapped) span("map_smooth_kernel", nBlk, [&] { smooth_all(0); });
     if (anyMapped) span("map_peaks_kernel", nBlk, [&] {
