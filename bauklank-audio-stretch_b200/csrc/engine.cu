@@ -44,7 +44,7 @@ static void h2d(void *d, const void *h, size_t n, stream_t s) { cudaMemcpyAsync(
 
 __global__ void __launch_bounds__(256, 4) analysis_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
                                                        const Window *windows, long long slot0, int nSlots, cf *specIn) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   int idx = blockIdx.x;
   const int c = idx % g.C; idx /= g.C;
   const int which = idx & 1; idx >>= 1;
@@ -291,7 +291,7 @@ static cudaError_t chain_set_smem(int C, size_t smem) {
 
 __global__ void __launch_bounds__(256, 4) isynth_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
                                                      const cf *specOut, StateDev st) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   int idx = blockIdx.x;
   const int c = idx % g.C; idx /= g.C;
   const int slot = idx % nSlots; const int s = idx / nSlots;

@@ -144,10 +144,19 @@ BS_HD int pow2_ffts_t(const DevGeom &g, const cf *tw, float *ar, float *ai, floa
         const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), iA = r >> lgStrideB, sB = r & (strideB - 1);
         const int base = sub * inner + (iA << (lgStrideA + 2)) + sB;
         float vr[4][4], vi[4][4];   // [a][j]
+        if (LG && lgStrideB == 0) {   // the four `a` inputs of a `j` are contiguous: one 16-byte load each (and no bank conflicts)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int j = 0; j < 4; ++j) {
+            const f4 qr = *(const f4 *)(sr + base + (j << lgStrideA)), qi = *(const f4 *)(si + base + (j << lgStrideA));
+            vr[0][j] = qr.x; vr[1][j] = qr.y; vr[2][j] = qr.z; vr[3][j] = qr.w;
+            vi[0][j] = qi.x; vi[1][j] = qi.y; vi[2][j] = qi.z; vi[3][j] = qi.w;
+          }
+        } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const int p = base + (j << lgStrideA) + (a << lgStrideB); vr[a][j] = sr[p]; vi[a][j] = si[p]; }
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int p = base + (j << lgStrideA) + (a << lgStrideB); vr[a][j] = sr[p]; vi[a][j] = si[p]; }
+        }
         {
           const cf tB = tw[iA << lgStrideA], tC = tw[(2 * iA) << lgStrideA], tD = tw[(3 * iA) << lgStrideA];
 #pragma unroll
@@ -171,8 +180,14 @@ BS_HD int pow2_ffts_t(const DevGeom &g, const cf *tw, float *ar, float *ai, floa
         const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), i = r >> lgStride, s = r & (stride - 1), base = sub * inner;
         const cf tB = tw[i << lgStride], tC = tw[(2 * i) << lgStride], tD = tw[(3 * i) << lgStride];
         const int pa = base + ((4 * i) << lgStride) + s;
-        float Ar = sr[pa], Ai = si[pa], Br = sr[pa + stride], Bi = si[pa + stride];
-        float Cr = sr[pa + 2 * stride], Ci = si[pa + 2 * stride], Dr = sr[pa + 3 * stride], Di = si[pa + 3 * stride];
+        float Ar, Ai, Br, Bi, Cr, Ci, Dr, Di;
+        if (LG && lgStride == 0) {   // the last pass: four contiguous inputs, one 16-byte load per array
+          const f4 qr = *(const f4 *)(sr + pa), qi = *(const f4 *)(si + pa);
+          Ar = qr.x; Br = qr.y; Cr = qr.z; Dr = qr.w; Ai = qi.x; Bi = qi.y; Ci = qi.z; Di = qi.w;
+        } else {
+          Ar = sr[pa]; Ai = si[pa]; Br = sr[pa + stride]; Bi = si[pa + stride];
+          Cr = sr[pa + 2 * stride]; Ci = si[pa + 2 * stride]; Dr = sr[pa + 3 * stride]; Di = si[pa + 3 * stride];
+        }
         bfly4<INV>(Ar, Ai, Br, Bi, Cr, Ci, Dr, Di, tB, tC, tD);
         const int po = base + (i << lgStride) + s, qs = 1 << (lgQ + lgStride);
         dr[po] = Ar;          di[po] = Ai;
