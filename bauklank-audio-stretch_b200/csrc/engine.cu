@@ -505,7 +505,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     return k;
   };
 #ifdef BS_HOSTEMU
-  std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)g.M + g.L + preterms_smem_floats(g.C, g.longStep) + 64) / 4 + 1);
+  std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)fft_pitch(g.M) + g.L + preterms_smem_floats(g.C, g.longStep) + 64) / 4 + 1);
   float *sm = (float *)smv.data();
   const size_t recPerStream = (size_t)((nSlots + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
   auto mapE = g.C == 2 ? map_energy<2> : (g.C == 1 ? map_energy<1> : map_energy<0>);
@@ -620,7 +620,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     if (!(synthMode & kSynthFrames)) st.ringPar ^= 1;
   }
 #else
-  const size_t smA = 4 * (size_t)g.M * sizeof(float);
+  const size_t smA = 4 * (size_t)fft_pitch(g.M) * sizeof(float);
   const int chainWarps = chain_warps(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots);
   const size_t smT = preterms_smem_floats(g.C, g.longStep) * sizeof(float);
   const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
@@ -726,7 +726,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
     cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
-  const size_t smA = 4 * (size_t)g.M * sizeof(float);
+  const size_t smA = 4 * (size_t)fft_pitch(g.M) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(isynth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(preterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||

@@ -142,7 +142,13 @@ BS_HD int pow2_ffts_t(const DevGeom &g, const cf *tw, float *ar, float *ai, floa
       const int lgPer = lg - 4, total = outer << lgPer;            // items per sub-transform: qA * strideB = inner/16
       for (int idx = tid; idx < total; idx += nt) {
         const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), iA = r >> lgStrideB, sB = r & (strideB - 1);
-        const int base = sub * inner + (iA << (lgStrideA + 2)) + sB;
+        // padIn: this pass reads with a 4-element inner stride -- eight of a warp's lanes per bank unless every 64-float
+        // group of the array is shifted by 4 floats; the pass before (padOut) wrote it that way.  Offsets within a group
+        // and whole-group offsets are compile-time constants either way.
+        constexpr bool kSpec = LG != 0;
+        const bool padIn = kSpec && lgStrideB == 2, padOut = kSpec && (lg - lgSize == 10);
+        int base = sub * inner + (iA << (lgStrideA + 2)) + sB;
+        if (padIn) base += (base >> 6) << 2;
         float vr[4][4], vi[4][4];   // [a][j]
         if (LG && lgStrideB == 0) {   // the four `a` inputs of a `j` are contiguous: one 16-byte load each (and no bank conflicts)
 #pragma unroll
@@ -162,14 +168,19 @@ BS_HD int pow2_ffts_t(const DevGeom &g, const cf *tw, float *ar, float *ai, floa
 #pragma unroll
           for (int a = 0; a < 4; ++a) bfly4<INV>(vr[a][0], vi[a][0], vr[a][1], vi[a][1], vr[a][2], vi[a][2], vr[a][3], vi[a][3], tB, tC, tD);
         }
-        const int obase = sub * inner + (iA << lgStrideB) + sB;
+        int obase = sub * inner + (iA << lgStrideB) + sB;
+        if (padOut) obase += (obase >> 6) << 2;      // (lgStrideB == 6 here: sB < 64, the offsets below are whole groups)
 #pragma unroll
         for (int jA = 0; jA < 4; ++jA) {
           const int iB = iA + (jA << lgQA);
           const cf tB = tw[iB << lgStrideB], tC = tw[(2 * iB) << lgStrideB], tD = tw[(3 * iB) << lgStrideB];
           bfly4<INV>(vr[0][jA], vi[0][jA], vr[1][jA], vi[1][jA], vr[2][jA], vi[2][jA], vr[3][jA], vi[3][jA], tB, tC, tD);
 #pragma unroll
-          for (int jB = 0; jB < 4; ++jB) { const int p = obase + (jA << (lgQA + lgStrideB)) + (jB << (lgQB + lgStrideB)); dr[p] = vr[jB][jA]; di[p] = vi[jB][jA]; }
+          for (int jB = 0; jB < 4; ++jB) {
+            const int o = (jA << (lgQA + lgStrideB)) + (jB << (lgQB + lgStrideB));
+            const int p = obase + o + (padOut ? (o >> 6) << 2 : 0);
+            dr[p] = vr[jB][jA]; di[p] = vi[jB][jA];
+          }
         }
       }
       lgSize += 4;
@@ -275,6 +286,10 @@ BS_HD void outer_stage(const DevGeom &g, const DevTables &T, float *dr, float *d
   else outer_stage_t<INV, 0>(g, T, dr, di, tid, nt);
 }
 
+// Pitch of the four FFT work arrays in shared memory: room for 4 padding floats per 64 (pow2_ffts_t pads the one array
+// whose next reader would otherwise hit eight-way bank conflicts), rounded to whole 16-byte pieces.
+BS_HHD int fft_pitch(int M) { return (M + (M >> 4) + 3) & ~3; }
+
 // position of packed sample j after the interleave step of the split FFT (plan types 1-5): j = i*outer + s -> s*inner + i
 BS_HD int deint(const DevGeom &g, int j) {
   const int q = (int)(((unsigned)j * g.divMagic) >> g.divShift);   // j / outer without a division or a branch
@@ -283,10 +298,10 @@ BS_HD int deint(const DevGeom &g, int j) {
 
 // ------------------------------------------------------------------------------------------------------------
 // analysis of one window of one channel (W#35): window, zero-phase rotate, zero-pad, modified real FFT.
-// smem: 4*M floats.  `x` = channel base of the clip.
+// smem: 4*fft_pitch(M) floats.  `x` = channel base of the clip.
 BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, int tid, int nt) {
-  const int M = g.M, N = g.N, L = g.L, off = g.off;
-  float *ar = sm, *ai = sm + M, *br = sm + 2 * M, *bi = sm + 3 * M;
+  const int M = g.M, N = g.N, L = g.L, off = g.off, MP = fft_pitch(M);
+  float *ar = sm, *ai = sm + MP, *br = sm + 2 * MP, *bi = sm + 3 * MP;
   // window * sample for the packed pair (2j, 2j+1): second half of the window first (zero-phase rotation), the first
   // half at the end with the half-bin shift's sign flip, zeros between.
   const int nA = L - off, cStart = N - off;
@@ -358,10 +373,10 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
 
 // inverse modified real FFT of one channel's output spectrum, synthesis window applied: the block's contribution to
 // the output, frame[i] for output sample frameStart + i (W#48 9986-10932; the first half of the window carries the
-// half-bin shift's sign flip, `ring -= t*w` there = adding -(t*w)).  smem: 4*M floats.
+// half-bin shift's sign flip, `ring -= t*w` there = adding -(t*w)).  smem: 4*fft_pitch(M) floats.
 BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float *frame, float *sm, int tid, int nt) {
-  const int M = g.M, N = g.N, L = g.L, off = g.off;
-  float *ar = sm, *ai = sm + M, *br = sm + 2 * M, *bi = sm + 3 * M;
+  const int M = g.M, N = g.N, L = g.L, off = g.off, MP = fft_pitch(M);
+  float *ar = sm, *ai = sm + MP, *br = sm + 2 * MP, *bi = sm + 3 * MP;
   const int half = M >> 1;
   constexpr int UN = 4;   // four bin pairs per trip, their global loads issued together
   for (int i0 = tid; i0 <= half; i0 += nt * UN) {
