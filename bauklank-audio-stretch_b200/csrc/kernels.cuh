@@ -404,14 +404,41 @@ BS_HD void synth_frame(const DevGeom &g, const DevTables &T, const cf *X, float 
   outer_stage<true>(g, T, rr, ri, tid, nt);
   const int nA = L - off, cStart = N - off;
   const bool evenCuts = ((nA | cStart | off) & 1) == 0;
+  if (evenCuts) {
+    // both samples of a pair fall in the same half of the window (one 8-byte coefficient load, one 8-byte store); four
+    // pairs per trip, all their table loads issued before the first one is used
+    constexpr int UO = 4;
+    const int jA = nA >> 1, jC = cStart >> 1;
+    for (int j0 = tid; j0 < M; j0 += nt * UO) {
+      cf rt[UO]; f2 wv[UO]; int ii[UO];
+#pragma unroll
+      for (int u = 0; u < UO; ++u) {
+        const int j = j0 + u * nt;
+        const bool inA = j < jA, live = j < M && (inA || j >= jC);
+        ii[u] = live ? (inA ? 2 * j + off : 2 * j - cStart) : -1;
+        if (live) { rt[u] = T.rot[j]; wv[u] = *(const f2 *)(T.win + ii[u]); }
+      }
+#pragma unroll
+      for (int u = 0; u < UO; ++u) {
+        const int j = j0 + u * nt;
+        if (ii[u] < 0) continue;
+        const cf r = rt[u];
+        const float t1 = (r.re * ri[j]) - (r.im * rr[j]);
+        const float t0 = (r.im * ri[j]) + (r.re * rr[j]);
+        f2 o;
+        if (j < jA) { o.x = t0 * wv[u].x; o.y = t1 * wv[u].y; }
+        else { o.x = -(t0 * wv[u].x); o.y = -(t1 * wv[u].y); }
+        *(f2 *)(frame + ii[u]) = o;
+      }
+    }
+    BS_SYNC();
+    return;
+  }
   for (int j = tid; j < M; j += nt) {
     const cf r = T.rot[j];
     const float t1 = (r.re * ri[j]) - (r.im * rr[j]);
     const float t0 = (r.im * ri[j]) + (r.re * rr[j]);
-    if (evenCuts) {   // both samples of the pair in the same half of the window: one 8-byte coefficient load, one 8-byte store
-      if (j < (nA >> 1)) { const int i = 2 * j + off; const f2 wv = *(const f2 *)(T.win + i); f2 o; o.x = t0 * wv.x; o.y = t1 * wv.y; *(f2 *)(frame + i) = o; }
-      else if (j >= (cStart >> 1)) { const int i = 2 * j - cStart; const f2 wv = *(const f2 *)(T.win + i); f2 o; o.x = -(t0 * wv.x); o.y = -(t1 * wv.y); *(f2 *)(frame + i) = o; }
-    } else {
+    {
       const float tv[2] = {t0, t1};
       for (int e = 0; e < 2; ++e) {
         const int n = 2 * j + e;
