@@ -358,15 +358,23 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
   float *rr = which ? br : ar, *ri = which ? bi : ai;
   outer_stage<false>(g, T, rr, ri, tid, nt);
   const int half = M >> 1;
-  for (int i = tid; i <= half; i += nt) {
-    if (i == half - 1 && !(M & 1)) continue;  // iteration i = M/2 rewrites this pair last in the reference loop
-    int j = M - 1 - i; cf u = T.untangle[i];
-    float sI = (ri[j] + ri[i]) * 0.5f, dR = (rr[i] - rr[j]) * 0.5f;
-    float p = (sI * u.re) + (dR * u.im), dI = (ri[i] - ri[j]) * 0.5f;
-    float q = (dR * u.re) - (sI * u.im), sR = (rr[j] + rr[i]) * 0.5f;
-    cf xi_, xj_;
-    xi_.im = p + dI; xi_.re = q + sR; xj_.im = p - dI; xj_.re = sR - q;
-    X[i] = xi_; X[j] = xj_;
+  constexpr int UT = 4;   // four bin pairs per trip, their twiddle loads issued together
+  for (int i0 = tid; i0 <= half; i0 += nt * UT) {
+    cf uu[UT];
+#pragma unroll
+    for (int t = 0; t < UT; ++t) { const int i = i0 + t * nt; if (i <= half) uu[t] = T.untangle[i]; }
+#pragma unroll
+    for (int t = 0; t < UT; ++t) {
+      const int i = i0 + t * nt;
+      if (i > half || (i == half - 1 && !(M & 1))) continue;  // iteration i = M/2 rewrites pair half-1 last in the reference loop
+      const int j = M - 1 - i; const cf u = uu[t];
+      float sI = (ri[j] + ri[i]) * 0.5f, dR = (rr[i] - rr[j]) * 0.5f;
+      float p = (sI * u.re) + (dR * u.im), dI = (ri[i] - ri[j]) * 0.5f;
+      float q = (dR * u.re) - (sI * u.im), sR = (rr[j] + rr[i]) * 0.5f;
+      cf xi_, xj_;
+      xi_.im = p + dI; xi_.re = q + sR; xj_.im = p - dI; xj_.re = sR - q;
+      X[i] = xi_; X[j] = xj_;
+    }
   }
   BS_SYNC();
 }
