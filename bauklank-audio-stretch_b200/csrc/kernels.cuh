@@ -233,14 +233,29 @@ template <bool INV, int OUTER>
 BS_HD void outer_stage_t(const DevGeom &g, const DevTables &T, float *dr, float *di, int tid, int nt) {
   const int inner = g.inner, outer = OUTER ? OUTER : g.outer;   // OUTER fixed: the per-sub-transform arrays stay in registers
   if (outer < 2) return;
-  for (int i = tid; i < inner; i += nt) {
+  constexpr int OB = OUTER == 3 ? 4 : (OUTER == 5 ? 2 : 1);   // bins per trip whose twiddles are fetched together
+  for (int i0 = tid; i0 < inner; i0 += nt * OB) {
+   float twr[OB][4], twi[OB][4];
+#pragma unroll
+   for (int b = 0; b < OB; ++b) {
+     const int i = i0 + b * nt;
+#pragma unroll
+     for (int s = 1; s < (OUTER ? OUTER : 5); ++s) {
+       if (s >= outer || i >= inner) break;
+       twr[b][s - 1] = T.otr[i + inner * (s - 1)]; twi[b][s - 1] = T.oti[i + inner * (s - 1)];
+     }
+   }
+#pragma unroll
+   for (int b = 0; b < OB; ++b) {
+    const int i = i0 + b * nt;
+    if (i >= inner) break;
     float xr[5], xi[5];
     xr[0] = dr[i]; xi[0] = di[i];
 #pragma unroll
     for (int s = 1; s < (OUTER ? OUTER : 5); ++s) {
       if (s >= outer) break;
       float vr = dr[i + s * inner], vi = di[i + s * inner];
-      float wr = T.otr[i + inner * (s - 1)], wi = T.oti[i + inner * (s - 1)];
+      float wr = twr[b][s - 1], wi = twi[b][s - 1];
       if (!INV) { xr[s] = (wr * vr) - (wi * vi); xi[s] = (wi * vr) + (vi * wr); }
       else { xr[s] = (vi * wi) + (vr * wr); xi[s] = (vi * wr) - (wi * vr); }
     }
@@ -275,6 +290,7 @@ BS_HD void outer_stage_t(const DevGeom &g, const DevTables &T, float *dr, float 
       dr[i + 3 * inner] = p2r - q2r; di[i + 3 * inner] = p2i - q2i;
       dr[i + 4 * inner] = p1r - q1r; di[i + 4 * inner] = p1i - q1i;
     }
+   }
   }
   BS_SYNC();
 }
