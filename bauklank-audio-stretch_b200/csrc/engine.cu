@@ -42,7 +42,7 @@ static void dfree(void *p) { if (p) cudaFree(p); }
 static void dzero(void *p, size_t n, stream_t s) { cudaMemsetAsync(p, 0, n, s); }
 static void h2d(void *d, const void *h, size_t n, stream_t s) { cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s); }
 
-__global__ void __launch_bounds__(256, 4) analysis_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+__global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
                                                        const Window *windows, long long slot0, int nSlots, cf *specIn) {
   extern __shared__ __align__(16) float sm[];
   int idx = blockIdx.x;
@@ -289,7 +289,7 @@ static cudaError_t chain_set_smem(int C, size_t smem) {
   }
 }
 
-__global__ void __launch_bounds__(256, 4) isynth_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
+__global__ void __launch_bounds__(256, 3) isynth_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
                                                      const cf *specOut, StateDev st) {
   extern __shared__ __align__(16) float sm[];
   int idx = blockIdx.x;
