@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T
   if (!(blocks[sd.blockBase + m].flags & kNew)) return;
   const Window w = windows[2 * (sd.blockBase + m) + which];
   cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * g.B;
-  analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x);
+  analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x, which == 1);
 }
 
 // ---- map stage kernels (see kernels.cuh "map stage")
@@ -521,7 +521,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
         for (int which = 0; which < 2; ++which)
           for (int c = 0; c < g.C; ++c)
             analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
-                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1);
+                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1, which == 1);
       }
     }
     account("map_energy_kernel", nBlk * g.C);

@@ -312,10 +312,14 @@ BS_HD int deint(const DevGeom &g, int j) {
   return (j - q * g.outer) * g.inner + q;
 }
 
+// S1 (W#48 8238-8300): prevInput *= rot, the per-bin rotation table
+BS_HD cf rot_prev(cf v, cf r) { cf o; o.re = (v.re * r.re) - (v.im * r.im); o.im = (v.im * r.re) + (v.re * r.im); return o; }
+
 // ------------------------------------------------------------------------------------------------------------
 // analysis of one window of one channel (W#35): window, zero-phase rotate, zero-pad, modified real FFT.
 // smem: 4*fft_pitch(M) floats.  `x` = channel base of the clip.
-BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, int tid, int nt) {
+BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, int tid, int nt,
+                          bool rotate = false /* store X[k] * specRot[k]: the S1 rotation of a "previous" spectrum, applied once here */) {
   const int M = g.M, N = g.N, L = g.L, off = g.off, MP = fft_pitch(M);
   float *ar = sm, *ai = sm + MP, *br = sm + 2 * MP, *bi = sm + 3 * MP;
   // window * sample for the packed pair (2j, 2j+1): second half of the window first (zero-phase rotation), the first
@@ -389,6 +393,7 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
       float q = (dR * u.re) - (sI * u.im), sR = (rr[j] + rr[i]) * 0.5f;
       cf xi_, xj_;
       xi_.im = p + dI; xi_.re = q + sR; xj_.im = p - dI; xj_.re = sR - q;
+      if (rotate) { xi_ = rot_prev(xi_, T.specRot[i]); xj_ = rot_prev(xj_, T.specRot[j]); }
       X[i] = xi_; X[j] = xj_;
     }
   }
@@ -596,7 +601,6 @@ BS_HD cf lerp_c(const cf *a, int B, int low, float fr) {
   r.re = ((hi.re - lo.re) * fr) + lo.re; r.im = ((hi.im - lo.im) * fr) + lo.im;
   return r;
 }
-BS_HD cf rot_prev(cf v, cf r) { cf o; o.re = (v.re * r.re) - (v.im * r.im); o.im = (v.im * r.re) + (v.re * r.im); return o; }
 BS_HD cf lerp_prev(const cf *a, const cf *rot, int B, int low, float fr) {  // rot == nullptr: no rotation
   cf lo = {0.f, 0.f}, hi = {0.f, 0.f}, r;
   if (low >= 0 && low < B) lo = rot ? rot_prev(a[low], rot[low]) : a[low];
@@ -984,7 +988,7 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
   const size_t rowStride = rec_row_stride(C);
   const bool isNew = rec.flags & kNew;
   const cf *prv = isNew ? inPrev : inp;
-  const cf *prvRot = isNew ? T.specRot : nullptr;
+  const cf *prvRot = nullptr;   // a new block's previous spectrum was rotated (S1) by the analysis kernel when it was stored
   const int longStep = g.longStep;
   const float tf = rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor;
   const float rlo = ((tf > 2.0f) ? 4.0f : 0.0f) - tf, rscale = (tf - rlo) * 0x1p-31f, fLong = (float)longStep;
