@@ -29,7 +29,7 @@ struct BlockRec2 {
   float fmLimit;
   int lastNew;        // stream-relative index of the block whose "current" spectrum is this block's input (-1: none yet)
   uint32_t rngSkip;   // blocks before this one that drew from the RNG (timeFactor > 2): each consumed 2*bands-2 draws
-  uint32_t pad;
+  uint32_t zeroBelow; // compat shim only (flush inside the vertical-prediction steps): Band.output of the bins below reads as 0
 };
 // sample i (0 <= i < L) of a window = (lo <= i < hi) ? clip[ch][start + i] : 0
 struct Window { long long start; int lo, hi; };

@@ -574,13 +574,14 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
       if (nv <= 0) continue;
       const size_t slot = (size_t)s * nSlots;
       const BlockRec *bl = e->dBlocks + sd.blockBase + slot0;
+      const BlockRec2 *bl2 = e->dBlocks2 + sd.blockBase + slot0;
       const float *rr = st.rec + (size_t)s * recPerStream;
       cf *so = e->specOut + slot * CB, *state = st.outSpec + (size_t)s * CB;
       switch (g.C) {
-        case 1: chain_host<1>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; case 2: chain_host<2>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
-        case 3: chain_host<3>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; case 4: chain_host<4>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
-        case 5: chain_host<5>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; case 6: chain_host<6>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
-        case 7: chain_host<7>(e->dg, e->dt, bl, (int)nv, rr, so, state); break; default: chain_host<8>(e->dg, e->dt, bl, (int)nv, rr, so, state); break;
+        case 1: chain_host<1>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break; case 2: chain_host<2>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break;
+        case 3: chain_host<3>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break; case 4: chain_host<4>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break;
+        case 5: chain_host<5>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break; case 6: chain_host<6>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break;
+        case 7: chain_host<7>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break; default: chain_host<8>(e->dg, e->dt, bl, (int)nv, rr, so, state, bl2); break;
       }
       const long long mLast = slot0 + nv - 1;
       if (e->dg.incremental || (mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew))) {
@@ -1466,7 +1467,13 @@ void compat_flush(int nOut) {
     int nS6 = 0, nSyn = 0;
     c->ctl->progress(nS6, nSyn);
     const int step = c->ctl->stepsDone();
-    if (step <= c->ctl->stepS6()) {   // runs after the flush, on Band.output = 0 and (unless its copy is still to come) prevInput = 0
+    if (nS6 >= 1 && nS6 <= 7) {
+      // inside the eight vertical-prediction steps: the bins predicted so far are cleared with everything else, the rest
+      // are predicted after the flush from cleared neighbours and cleared preliminary predictions -- the whole block run
+      // on Band.output = 0, with the output of the bins below the step boundary forced to 0
+      c->plan.blocks2[c->m].zeroBelow = ((uint32_t)g.B * (uint32_t)nS6) >> 3;
+      keepPrevInput = c->ctl->curIsNew();   // its last spectral step sets prevInput = input again
+    } else if (step <= c->ctl->stepS6()) {   // runs after the flush, on Band.output = 0 and (unless its copy is still to come) prevInput = 0
       // stft.reset also clears the spectrum scratch: a channel analysed before the flush whose copy into the Bands comes
       // after it arrives as zeros; prevInput copied before the flush is cleared by the flush itself
       const bool isNew = c->ctl->curIsNew(), rean = c->ctl->curReanalysesPrev();

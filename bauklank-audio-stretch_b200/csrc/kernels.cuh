@@ -1151,7 +1151,8 @@ BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, long l
 // block after the other (the wavefront order of the CUDA kernel computes exactly the same values)
 template <int C>
 inline void chain_host(const DevGeom &g, const DevTables &T, const BlockRec *blocks /* of this stream, at slot0 */, int nValid,
-                       const float *rec /* the stream's chunk records */, cf *specOut /* [slot][C][B] */, cf *stateOut /* [C][B] */) {
+                       const float *rec /* the stream's chunk records */, cf *specOut /* [slot][C][B] */, cf *stateOut /* [C][B] */,
+                       const BlockRec2 *blocks2 = nullptr) {
   const int B = g.B, ls = g.longStep, R0 = ls + 1, SO = 9 + 5 * C;
   const size_t NR = rec_row_stride(C);
   std::vector<cf> o5((size_t)C * B);
@@ -1178,6 +1179,7 @@ inline void chain_host(const DevGeom &g, const DevTables &T, const BlockRec *blo
       cf z = {0.f, 0.f}, out[C];
       chain_bin<C>(r, mc, k, B, ls, k > 0 ? so[(size_t)mc * B + k - 1] : z, k >= ls ? so[(size_t)mc * B + k - ls] : z,
                    k < B - 1 ? o5[(size_t)mc * B + k + 1] : z, k < B - ls ? o5[(size_t)mc * B + k + ls] : z, out);
+      if (g.incremental && blocks2 && k < (int)blocks2[t].zeroBelow) for (int c = 0; c < C; ++c) out[c].re = out[c].im = 0.f;
       for (int c = 0; c < C; ++c) so[(size_t)c * B + k] = out[c];
     }
     for (size_t i = 0; i < (size_t)C * B; ++i) stateOut[i] = so[i];

@@ -289,6 +289,8 @@ SHIM_CASES = {
                           flush=(30, 3000), segments=[seg(semitones=3.0)]),
     "flush_cheaper_before_prediction": dict(drive="stream", clip=("survey", 24000), sr=48000, n_in=480, n_out=512, preset="cheaper",
                                             flush=(27, 7000), segments=[seg(semitones=3.0)]),
+    "flush_cheaper_inside_prediction": dict(drive="stream", clip=("survey", 24000), sr=48000, n_in=480, n_out=512, preset="cheaper",
+                                            flush=(25, 2000), segments=[seg(semitones=3.0)]),
     "flush_cheaper_during_synthesis": dict(drive="stream", clip=("survey", 24000), sr=48000, n_in=480, n_out=512, preset="cheaper",
                                            flush=(22, 1440), segments=[seg(semitones=3.0)]),
 }
