@@ -176,3 +176,19 @@ def test_longest_first_ordering_relay_chunks_and_host_audio(emu):
     for y, r in zip(host_outs, refs):
         assert cases.compare(y, r)[0]
     eng.close()
+
+
+def test_shim_flush_at_many_positions_of_the_block_cycle(emu):
+    """flush() while a block's steps are spread over the interval (split computation): before, inside and after the
+    vertical prediction, during synthesis, on interval boundaries -- always the reference's bits, also for the
+    processing that follows."""
+    bad = []
+    for n_in, n_out, positions in ((480, 512, range(20, 32)), (300, 700, range(20, 30, 2)), (64, 64, range(30, 50, 3))):
+        for calls in positions:
+            case = dict(drive="stream", clip=("survey", 30000), sr=48000, n_in=n_in, n_out=n_out, preset="cheaper", seed=5,
+                        n_calls=calls + 14, flush=(calls, 2000), segments=[cases.seg(semitones=3.0)])
+            a = refdrive.PortEngine(seed=5); ya = cases.run_case(a, case); a.close()
+            yb = cases.run_case(bs.StretchEngine(seed=5, lib=emu), case)
+            if not cases.compare(ya, yb)[0]:
+                bad.append((n_in, n_out, calls))
+    assert not bad, bad
