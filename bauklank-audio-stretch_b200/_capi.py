@@ -16,7 +16,8 @@ class Segment(C.Structure):
     _fields_ = [("output", C.c_double), ("input", C.c_double), ("rate", C.c_double),
                 ("semitones", C.c_double), ("tonality_hz", C.c_double), ("formant_semitones", C.c_double),
                 ("formant_base_hz", C.c_double), ("loop_start", C.c_double), ("loop_end", C.c_double),
-                ("active", C.c_int32), ("formant_compensation", C.c_int32)]
+                ("active", C.c_int32), ("formant_compensation", C.c_int32),
+                ("transpose_factor", C.c_double), ("formant_factor", C.c_double)]
 
 
 class Quantum(C.Structure):
@@ -24,7 +25,7 @@ class Quantum(C.Structure):
     _fields_ = [("rate", C.c_double), ("input_samples_end", C.c_longlong), ("valid_start", C.c_longlong),
                 ("valid_end", C.c_longlong), ("semitones", C.c_float), ("tonality_limit", C.c_float),
                 ("formant_semitones", C.c_float), ("formant_base", C.c_float), ("formant_compensation", C.c_int32),
-                ("active", C.c_int32)]
+                ("active", C.c_int32), ("transpose_factor", C.c_float), ("formant_factor", C.c_float)]
 
 
 _BATCH_SIG = {
@@ -50,6 +51,7 @@ _BATCH_SIG = {
     "bsb_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bsb_run_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "bsb_rebind": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "bsb_synchronize": (C.c_int, [C.c_void_p]),
     "bsb_total_blocks": (C.c_longlong, [C.c_void_p]),
     "bsb_stream_blocks": (C.c_longlong, [C.c_void_p, C.c_int]),
     "bsb_chunk_blocks": (C.c_int, [C.c_void_p]),

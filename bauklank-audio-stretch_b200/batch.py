@@ -14,12 +14,18 @@ from . import _capi
 
 
 def segment(output=0.0, input=0.0, rate=1.0, semitones=0.0, tonality_hz=8000.0, formant_semitones=0.0,
-            formant_compensation=False, formant_base_hz=0.0, loop_start=0.0, loop_end=0.0, active=True):
+            formant_compensation=False, formant_base_hz=0.0, loop_start=0.0, loop_end=0.0, active=True,
+            transpose_factor=None, formant_factor=None):
     """One time-map entry; defaults are the worklet's initial segment (app/SignalsmithStretch.mjs:587-600),
-    except ``active`` (a playing stream)."""
+    except ``active`` (a playing stream).  ``transpose_factor`` / ``formant_factor``: drive the engine's
+    ``setTransposeFactor`` / ``setFormantFactor`` exports (:472, :474) with a frequency multiplier instead of the
+    semitone setters the worklet calls."""
+    nan = float("nan")
     return _capi.Segment(float(output), float(input), float(rate), float(semitones), float(tonality_hz),
                          float(formant_semitones), float(formant_base_hz), float(loop_start), float(loop_end),
-                         1 if active else 0, 1 if formant_compensation else 0)
+                         1 if active else 0, 1 if formant_compensation else 0,
+                         nan if transpose_factor is None else float(transpose_factor),
+                         nan if formant_factor is None else float(formant_factor))
 
 
 @dataclass
@@ -163,10 +169,12 @@ class BatchStretch:
         self._check(self.lib.bsb_run(self.h, C.c_void_p(cuda_stream)))
         return self.outputs
 
-    def run_host(self, host_clips, host_outs, cuda_stream=None):
+    def run_host(self, host_clips, host_outs, cuda_stream=None, sync=True):
         """Like run(), for audio in host memory: host_clips[i] / host_outs[i] are float32 [channels, n] arrays (pinned
         torch CPU tensors or numpy) matching the planned shapes.  The planned device tensors serve as staging; copies
-        and kernels are pipelined chunk by chunk inside the library."""
+        and kernels are pipelined chunk by chunk inside the library.  ``sync`` (default): return once the host outputs
+        are complete; with ``sync=False`` the copies may still be in flight -- call ``synchronize()`` (or synchronise
+        the stream) before reading ``host_outs``."""
         n = len(self._keep)
         assert len(host_clips) == n and len(host_outs) == n
         if cuda_stream is None:
@@ -179,7 +187,13 @@ class BatchStretch:
         ins = (C.c_void_p * n)(*[_ptr(x) for x in host_clips])
         outs = (C.c_void_p * n)(*[_ptr(x) for x in host_outs])
         self._check(self.lib.bsb_run_host(self.h, ins, outs, C.c_void_p(cuda_stream)))
+        if sync:
+            self.synchronize()
         return host_outs
+
+    def synchronize(self):
+        """Block until the last run()/run_host() has finished on the device."""
+        self._check(self.lib.bsb_synchronize(self.h))
 
     def total_blocks(self): return self.lib.bsb_total_blocks(self.h)
     def stream_blocks(self, i): return self.lib.bsb_stream_blocks(self.h, i)

@@ -49,13 +49,22 @@ struct Segment {
   double output, input, rate;
   double semitones, tonalityHz, formantSemitones, formantBaseHz, loopStart, loopEnd;
   int active, formantCompensation;
+  // not NaN: the driver calls setTransposeFactor / setFormantFactor (exports "q" / "s", app/SignalsmithStretch.mjs:472,474)
+  // with this multiplier instead of the semitone setters
+  double transposeFactor = NAN, formantFactor = NAN;
 };
 
+// A seek whose loudness the plan had to assume (see KioskPlanner): sum of squares over clip[c][start, start+count) of every
+// channel, accumulated like W#49 does, must be >= 1e-15 -- checked on the device after the run (bsb_gate_events).
+struct SeekWatch { long long start; int count; };
 struct StreamPlan {
   std::vector<BlockRec> blocks;
   std::vector<BlockRec2> blocks2;
   std::vector<Window> windows;  // 2 per block: cur, prev
   long long nOut = 0;
+  long long nLive = -1;         // output samples before the silence gate closed for good (the rest is zeros); -1: all of them
+  std::vector<SeekWatch> watch;
+  const char *error = nullptr;  // a drive the batched path cannot express
 };
 
 class Control {
@@ -184,27 +193,96 @@ class Control {
 
 inline void apply_segment_params(Params &p, const Segment &s, double sampleRate) {
   // WasmProcessor.process, app/SignalsmithStretch.mjs:847-849 (JS doubles -> f32 at the wasm call boundary)
-  p.setTransposeSemitones((float)s.semitones, (float)(s.tonalityHz / sampleRate));
-  p.setFormantSemitones((float)s.formantSemitones, s.formantCompensation ? 1 : 0);
+  if (std::isnan(s.transposeFactor)) p.setTransposeSemitones((float)s.semitones, (float)(s.tonalityHz / sampleRate));
+  else p.setTransposeFactor((float)s.transposeFactor, (float)(s.tonalityHz / sampleRate));
+  if (std::isnan(s.formantFactor)) p.setFormantSemitones((float)s.formantSemitones, s.formantCompensation ? 1 : 0);
+  else p.setFormantFactor((float)s.formantFactor, s.formantCompensation ? 1 : 0);
   p.setFormantBase((float)(s.formantBaseHz / sampleRate));
 }
 
-inline Window clip_window(long long start, int L, int validFrom, long long clipLen, long long clipFrom = 0) {
+inline Window clip_window(long long start, int L, int validFrom, long long clipLen, long long clipFrom = 0, int validTo = 1 << 30) {
   Window w; w.start = start;
-  long long lo = std::max<long long>(validFrom, clipFrom - start), hi = std::min<long long>(L, clipLen - start);
+  long long lo = std::max<long long>(validFrom, clipFrom - start), hi = std::min<long long>(std::min(L, validTo), clipLen - start);
   if (lo < 0) lo = 0;
   if (hi < lo) hi = lo;
   w.lo = (int)lo; w.hi = (int)hi;
   return w;
 }
 
+// One stream under the worklet's drive, quantum by quantum (app/SignalsmithStretch.mjs:840-943).  Two kinds of quantum:
+//   active    buffer playback (:883-943): `_seek(bufferLength, rate)` then `_process(0, q)`;
+//   inactive  (:861-869): the input buffer is zeroed and `_process(q, q)` runs on it.
+// The engine's STFT input ring is modelled by provenance: the most recent seek left clip[end-n, end) (zeros before it),
+// every inactive quantum appends zeros, and an analysis window is the L ring samples ending 0 (current) or H (previous)
+// samples before the write position -- always "a run of clip samples with zeros on either side", which is what a Window
+// says.  The silence gate of process() (W#48 7838-7943) is followed too: `silenceCounter` grows by q per inactive
+// quantum, a seek over audio resets it (W#49), and once it has reached 2L every further call without loud input returns
+// zeros without touching the output ring.  The batched path follows the reference up to that point and, if no seek re-opens the gate,
+// to the end (all zeros); a stream that is started again after the gate has closed re-arms its block phase at an
+// arbitrary output position and is left to the 18-call shim (`error` is set).
+// Data dependence: whether a seek is "loud" depends on the audio.  A seek whose buffer holds clip samples is planned as
+// loud; where that matters (the counter was not zero) the seek is put on the watch list and checked on the device.
+class KioskPlanner {
+ public:
+  KioskPlanner(const Geometry &g, StreamPlan &plan) : ctl(g), g_(g), plan_(plan) {}
+  Control ctl;   // the caller applies the quantum's setter values to ctl.p before each call of quantum()
+
+  // active quantum: `end` = Math.round(inputTime * sampleRate), the stored audio covers clip samples [validStart, validEnd)
+  // inactive quantum: rate / end / valid range unused
+  void quantum(int q, bool active, double rate, long long end, long long validStart, long long validEnd) {
+    if (plan_.error) return;
+    const int L = g_.L, H = g_.H, cap = L + H, bufLen = g_.inLat + g_.outLat;
+    if (active) {
+      const int n = std::min(bufLen, cap);   // samples of pre-roll that seek() keeps
+      const long long a0 = std::max<long long>(end - n, validStart), a1 = std::min<long long>(end, validEnd);
+      if (a1 > a0) {   // the buffer holds audio: planned as loud (silenceCounter = 0, W#49)
+        if (counter_ > 0) plan_.watch.push_back(SeekWatch{a0, (int)(a1 - a0)});
+        counter_ = 0;
+      }
+      ringEnd_ = end; ringN_ = n; ringLo_ = validStart; ringHi_ = validEnd; zeros_ = 0;
+      ctl.seek(rate);
+    }
+    const bool gated = counter_ >= ((uint32_t)L << 1);   // process(): no loud input (there is none, or it is zeros)
+    if (gated) {
+      if (plan_.nLive < 0) plan_.nLive = pos_;
+      if (!active) { pos_ += q; return; }
+      // (reached only if a silent seek follows a closed gate: stays closed)
+      pos_ += q; return;
+    }
+    if (plan_.nLive >= 0) { plan_.error = "a stream that plays again after the silence gate has closed (more than 2 blocks of inactive output) re-arms its block phase: drive it through the 18-call engine"; return; }
+    const int nIn = active ? 0 : q;
+    ctl.run(plan_, 0, q, nIn, q, [&](int idx, int, int, bool rean, bool isNew, long long bi) {
+      if (!isNew) return;  // spectra are carried over (flag kNew clear)
+      // zeros appended since the seek: the whole inactive quanta so far, plus copyInput(inputOffset) of this call (W#24)
+      const long long z = std::min<long long>(zeros_ + (active ? 0 : idx), (long long)cap + 1);
+      // a window ending p samples before the write position: sample i is ring history position i - p - L (0 = write position);
+      // history [-z, 0) is zeros, [-z-n, -z) is clip[ringEnd - n, ringEnd), older is zeros
+      auto win = [&](int p) { return clip_window(ringEnd_ + z - p - L, L, (int)std::max<long long>(0, (long long)p + L - z - ringN_), ringHi_, ringLo_, (int)std::max<long long>(0, (long long)p + L - z)); };
+      const Window cur = win(0);
+      plan_.windows[2 * bi + 0] = cur;
+      plan_.windows[2 * bi + 1] = rean ? win(H) : lastCur_;
+      lastCur_ = cur;
+    });
+    ctl.endCall(nIn);
+    if (!active) { counter_ += (uint32_t)q; zeros_ += q; }
+    pos_ += q;
+  }
+
+ private:
+  Geometry g_;
+  StreamPlan &plan_;
+  long long pos_ = 0;
+  uint32_t counter_ = 0;                 // silenceCounter
+  long long ringEnd_ = 0, ringLo_ = 0, ringHi_ = 0, zeros_ = 0; int ringN_ = 0;
+  Window lastCur_{0, 0, 0};
+};
+
 // Buffer-playback drive of the worklet (app/SignalsmithStretch.mjs:883-943): every quantum `_seek(bufferLength, rate)`
-// then `_process(0, q)`.  `segs` is the (already ordered) time map; currentTime = k*quantum/sampleRate.
+// then `_process(0, q)`; inactive segments run `_process(q, q)` on silence (:861-869).  `segs` is the (already ordered)
+// time map; currentTime = k*quantum/sampleRate.
 inline void plan_kiosk(const Geometry &g, double sampleRate, int quantum, long long nOut, long long clipLen,
                        const Segment *segs, int nSegs, StreamPlan &plan) {
-  Control ctl(g);
-  const int L = g.L, H = g.H, cap = L + H;
-  const int bufLen = g.inLat + g.outLat;
+  KioskPlanner kp(g, plan);
   const double inLatS = (double)g.inLat / sampleRate, outLatS = (double)g.outLat / sampleRate;
   std::vector<Segment> tm(segs, segs + nSegs);
   size_t si = 0;
@@ -216,21 +294,16 @@ inline void plan_kiosk(const Geometry &g, double sampleRate, int quantum, long l
     double outputTime = currentTime + outLatS;
     while (si + 1 < tm.size() && tm[si + 1].output <= outputTime) ++si;
     Segment &seg = tm[si];
-    apply_segment_params(ctl.p, seg, sampleRate);
-    double inputTime = seg.input + (outputTime - seg.output) * seg.rate;
-    double loopLength = seg.loopEnd - seg.loopStart;
-    if (loopLength > 0 && inputTime >= seg.loopEnd) { seg.input -= loopLength; inputTime -= loopLength; }
-    inputTime += inLatS;
-    long long end = (long long)std::floor(inputTime * sampleRate + 0.5);  // Math.round
-    ctl.seek(seg.rate);
-    int n = std::min(bufLen, cap);  // samples of pre-roll that seek() keeps
-    ctl.run(plan, 0, q, 0, q, [&](int, int, int, bool, bool isNew, long long bi) {
-      if (!isNew) return;  // spectra are carried over (flag kNew clear)
-      // ring after seek = [zeros(cap-n)][clip[end-n, end)]; cur = last L of it, prev = the L ending H earlier
-      plan.windows[2 * bi + 0] = clip_window(end - L, L, (cap - n) - H, clipLen);
-      plan.windows[2 * bi + 1] = clip_window(end - cap, L, cap - n, clipLen);
-    });
-    ctl.endCall(0);
+    apply_segment_params(kp.ctl.p, seg, sampleRate);
+    long long end = 0;
+    if (seg.active) {
+      double inputTime = seg.input + (outputTime - seg.output) * seg.rate;
+      double loopLength = seg.loopEnd - seg.loopStart;
+      if (loopLength > 0 && inputTime >= seg.loopEnd) { seg.input -= loopLength; inputTime -= loopLength; }
+      inputTime += inLatS;
+      end = (long long)std::floor(inputTime * sampleRate + 0.5);  // Math.round
+    }
+    kp.quantum(q, seg.active != 0, seg.rate, end, 0, clipLen);
     pos += q;
   }
 }
@@ -242,28 +315,21 @@ struct Quantum {
   double rate; long long inputSamplesEnd, validStart, validEnd;
   float semitones, tonalityLimit, formantSemitones, formantBase;
   int formantCompensation, active;
+  float transposeFactor = NAN, formantFactor = NAN;   // not NaN: setTransposeFactor / setFormantFactor instead of the semitone setters
 };
 inline void plan_kiosk_table(const Geometry &g, int quantum, long long nOut, const Quantum *qs, long long nQ, StreamPlan &plan) {
-  Control ctl(g);
-  const int L = g.L, H = g.H, cap = L + H;
-  const int bufLen = g.inLat + g.outLat;
+  KioskPlanner kp(g, plan);
   plan.nOut = nOut;
   long long pos = 0;
   for (long long k = 0; pos < nOut && k < nQ; ++k) {
     const Quantum &qq = qs[k];
     const int q = (int)std::min<long long>(quantum, nOut - pos);
-    ctl.p.setTransposeSemitones(qq.semitones, qq.tonalityLimit);
-    ctl.p.setFormantSemitones(qq.formantSemitones, qq.formantCompensation ? 1 : 0);
-    ctl.p.setFormantBase(qq.formantBase);
-    const long long end = qq.inputSamplesEnd;
-    ctl.seek(qq.rate);
-    const int n = std::min(bufLen, cap);
-    ctl.run(plan, 0, q, 0, q, [&](int, int, int, bool, bool isNew, long long bi) {
-      if (!isNew) return;
-      plan.windows[2 * bi + 0] = clip_window(end - L, L, (cap - n) - H, qq.validEnd, qq.validStart);
-      plan.windows[2 * bi + 1] = clip_window(end - cap, L, cap - n, qq.validEnd, qq.validStart);
-    });
-    ctl.endCall(0);
+    if (std::isnan(qq.transposeFactor)) kp.ctl.p.setTransposeSemitones(qq.semitones, qq.tonalityLimit);
+    else kp.ctl.p.setTransposeFactor(qq.transposeFactor, qq.tonalityLimit);
+    if (std::isnan(qq.formantFactor)) kp.ctl.p.setFormantSemitones(qq.formantSemitones, qq.formantCompensation ? 1 : 0);
+    else kp.ctl.p.setFormantFactor(qq.formantFactor, qq.formantCompensation ? 1 : 0);
+    kp.ctl.p.setFormantBase(qq.formantBase);
+    kp.quantum(q, qq.active != 0, qq.rate, qq.inputSamplesEnd, qq.validStart, qq.validEnd);
     pos += q;
   }
 }

@@ -348,7 +348,19 @@ BS_HD int gate_count(const GateDev &gd, int L, const uint8_t *loud) {
   }
   return fired;
 }
+// A seek the plan assumed loud (control.hpp KioskPlanner): W#49's energy sum over the buffer's clip samples, one accumulator
+// through all channels; the zeros around them add nothing.  1 = the assumption failed (the reference's counter kept running).
+struct SeekDev { const float *clip; long long clipLen, start; int count, pad; };
+BS_HD int seek_watch_failed(const SeekDev &w, int C) {
+  float energy = 0.f;
+  for (int c = 0; c < C; ++c) { const float *x = w.clip + (size_t)c * w.clipLen + w.start; for (int i = 0; i < w.count; ++i) energy = (x[i] * x[i]) + energy; }
+  return energy >= 1e-15f ? 0 : 1;
+}
 #ifndef BS_HOSTEMU
+__global__ void seek_watch_kernel(const SeekDev *ws, int n, int C, int *failed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) failed[i] = seek_watch_failed(ws[i], C);
+}
 __global__ void gate_energy_kernel(const GateDev *gds, int C, uint8_t *loud) {
   const GateDev gd = gds[blockIdx.y];
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,6 +412,8 @@ struct bsb_engine {
                                    // the next chunk's front half fills the rest: 334 -> 301 ms on 256 x 60 s of mixed rates
   float *recBuf[2] = {nullptr, nullptr};
   std::vector<GateDev> gate; std::vector<int> gateStream; GateDev *dGate = nullptr; uint8_t *dLoud = nullptr; int *dFired = nullptr;
+  std::vector<SeekDev> seekWatch; std::vector<int> seekStream; SeekDev *dSeek = nullptr; int *dSeekFailed = nullptr;
+  stream_t lastRunStream = 0;     // bsb_gate_events reads its counters behind whatever the last run queued there
   long long gateCallsTotal = 0, gateMaxCalls = 0;
 #ifndef BS_HOSTEMU
   cudaStream_t sFront = nullptr, sBack = nullptr, sIn = nullptr, sOut = nullptr;
@@ -720,6 +734,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   e->dt.specRot = upload(e, e->T.specRot, e->owned);
   e->dt.wpStart = upload(e, e->T.wpStart, e->owned); e->dt.wpSteady = upload(e, e->T.wpSteady, e->owned);
 #ifndef BS_HOSTEMU
+  cudaStreamSynchronize(0);   // table uploads done before any run can be queued on another stream
   cudaStreamCreateWithFlags(&e->sFront, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&e->sBack, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&e->sIn, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&e->sOut, cudaStreamNonBlocking);
   for (int i = 0; i < 2; ++i) {
@@ -775,15 +790,20 @@ int bsb_chunk_blocks(const bsb_engine *e) { return e->chunk; }
 long long bsb_launch_count(const bsb_engine *e) { return e->launches; }
 long long bsb_gate_events(bsb_engine *e) {
   if (!e->committed) return -1;
-  if (e->gate.empty()) return 0;
-  std::vector<int> fired(e->gate.size());
+  if (e->gate.empty() && e->seekWatch.empty()) return 0;
+  std::vector<int> fired(e->gate.size()), failed(e->seekWatch.size());
 #ifdef BS_HOSTEMU
-  std::memcpy(fired.data(), e->dFired, fired.size() * sizeof(int));
+  if (!fired.empty()) std::memcpy(fired.data(), e->dFired, fired.size() * sizeof(int));
+  if (!failed.empty()) std::memcpy(failed.data(), e->dSeekFailed, failed.size() * sizeof(int));
 #else
-  if (cudaMemcpy(fired.data(), e->dFired, fired.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  // the counters are written by kernels queued on the stream of the last run (possibly a non-blocking one): read behind them
+  if (!fired.empty() && cudaMemcpyAsync(fired.data(), e->dFired, fired.size() * sizeof(int), cudaMemcpyDeviceToHost, e->lastRunStream) != cudaSuccess) return -1;
+  if (!failed.empty() && cudaMemcpyAsync(failed.data(), e->dSeekFailed, failed.size() * sizeof(int), cudaMemcpyDeviceToHost, e->lastRunStream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(e->lastRunStream) != cudaSuccess) return -1;
 #endif
   long long n = 0;
   for (int v : fired) n += v;
+  for (int v : failed) n += v;
   return n;
 }
 void bsb_set_profiling(bsb_engine *e, int on) { e->profiling = on != 0; }
@@ -811,10 +831,10 @@ int bsb_begin(bsb_engine *e, int n) {
   return 0;
 }
 
-static int check_segments(bsb_engine *e, const bsb_segment *segs, int n) {
+static int check_segments(bsb_engine *e, const bsb_segment *segs, int n, bool allowInactive) {
   if (!segs || n < 1) return e->fail("at least one time-map segment is required");
   for (int i = 0; i < n; ++i) {
-    if (!segs[i].active) return e->fail("inactive time-map segments are not supported by the batched path");
+    if (!segs[i].active && !allowInactive) return e->fail("inactive time-map segments are not supported by the streaming drive (its silence gate depends on the audio)");
     if (i && segs[i].output < segs[i - 1].output) return e->fail("time-map segments must be ordered by output time");
   }
   return 0;
@@ -823,7 +843,8 @@ static std::vector<Segment> to_segments(const bsb_segment *s, int n) {
   std::vector<Segment> v(n);
   for (int i = 0; i < n; ++i)
     v[i] = Segment{s[i].output, s[i].input, s[i].rate, s[i].semitones, s[i].tonality_hz, s[i].formant_semitones,
-                   s[i].formant_base_hz, s[i].loop_start, s[i].loop_end, s[i].active, s[i].formant_compensation};
+                   s[i].formant_base_hz, s[i].loop_start, s[i].loop_end, s[i].active, s[i].formant_compensation,
+                   s[i].transpose_factor, s[i].formant_factor};
   return v;
 }
 
@@ -831,11 +852,12 @@ int bsb_add_kiosk(bsb_engine *e, int si, const float *dClip, long long clipLen, 
                   const bsb_segment *segs, int nSegs, uint32_t seed) {
   if (si < 0 || si >= (int)e->streams.size()) return e->fail("stream index out of range");
   if (quantum < 1 || nOut < 0 || clipLen < 0) return e->fail("bad sizes");
-  if (check_segments(e, segs, nSegs)) return -1;
+  if (check_segments(e, segs, nSegs, true)) return -1;
   Stream &s = e->streams[si];
   s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
   auto v = to_segments(segs, nSegs);
   plan_kiosk(e->g, e->sampleRate, quantum, nOut, clipLen, v.data(), nSegs, s.plan);
+  if (s.plan.error) return e->fail("stream %d: %s", si, s.plan.error);
   s.planned = true; e->committed = false;
   return 0;
 }
@@ -848,14 +870,14 @@ int bsb_add_kiosk_table(bsb_engine *e, int si, const float *dClip, long long cli
   std::vector<Quantum> qs((size_t)nQuanta);
   for (long long k = 0; k < nQuanta; ++k) {
     const bsb_quantum &t = table[k];
-    if (!t.active) return e->fail("inactive quanta (process(q,q) on silence) are not supported by the batched path");
     if (t.valid_start < 0 || t.valid_end > clipLen || t.valid_end < t.valid_start) return e->fail("quantum %lld: valid range outside the clip", k);
     qs[k] = Quantum{t.rate, t.input_samples_end, t.valid_start, t.valid_end, t.semitones, t.tonality_limit, t.formant_semitones,
-                    t.formant_base, t.formant_compensation, t.active};
+                    t.formant_base, t.formant_compensation, t.active, t.transpose_factor, t.formant_factor};
   }
   Stream &s = e->streams[si];
   s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
   plan_kiosk_table(e->g, quantum, nOut, qs.data(), nQuanta, s.plan);
+  if (s.plan.error) return e->fail("stream %d: %s", si, s.plan.error);
   s.planned = true; e->committed = false;
   return 0;
 }
@@ -871,7 +893,7 @@ int bsb_add_streaming(bsb_engine *e, int si, const float *dClip, long long clipL
                       const bsb_segment *segs, int nSegs, uint32_t seed) {
   if (si < 0 || si >= (int)e->streams.size()) return e->fail("stream index out of range");
   if (nIn < 1 || nOut < 1 || nCalls < 0 || nCalls * nIn > clipLen) return e->fail("bad sizes (n_calls*n_in must fit the clip)");
-  if (check_segments(e, segs, nSegs)) return -1;
+  if (check_segments(e, segs, nSegs, false)) return -1;
   Stream &s = e->streams[si];
   s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
   auto v = to_segments(segs, nSegs);
@@ -889,6 +911,11 @@ int bsb_rebind(bsb_engine *e, int si, const float *dClip, float *dOut) {
   h2d(e->dStreams + pos, &e->hs[pos], sizeof(StreamDev), 0);
   for (size_t i = 0; i < e->gate.size(); ++i)
     if (e->gateStream[i] == si) { e->gate[i].clip = dClip; h2d(e->dGate + i, &e->gate[i], sizeof(GateDev), 0); }
+  for (size_t i = 0; i < e->seekWatch.size(); ++i)
+    if (e->seekStream[i] == si) { e->seekWatch[i].clip = dClip; h2d(e->dSeek + i, &e->seekWatch[i], sizeof(SeekDev), 0); }
+#ifndef BS_HOSTEMU
+  cudaStreamSynchronize(0);   // (see bsb_commit: the next run may be queued on a stream that does not order against this one)
+#endif
   return 0;
 }
 
@@ -925,6 +952,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
     StreamDev &d = e->hs[s];
     d.clip = st.clip; d.out = st.out; d.clipLen = st.clipLen; d.nOut = st.plan.nOut; d.blockBase = e->blockBase[s];
     d.nBlocks = (long long)st.plan.blocks.size(); d.outStride = st.plan.nOut; d.outBase = 0;
+    d.nLive = st.plan.nLive >= 0 ? std::min(st.plan.nLive, st.plan.nOut) : st.plan.nOut;
     e->maxBlocks = std::max<long long>(e->maxBlocks, d.nBlocks);
     uint32_t sd = st.seed % 2147483647u; seeds[s] = sd <= 1u ? 1u : sd;   // W#26: minstd_rand seeding
   }
@@ -1021,12 +1049,27 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
     e->gate.push_back(GateDev{x.clip, x.clipLen, x.gateCalls, e->gateCallsTotal, x.gateIn, 0}); e->gateStream.push_back(s);
     e->gateCallsTotal += x.gateCalls; e->gateMaxCalls = std::max(e->gateMaxCalls, x.gateCalls);
   }
+  e->seekWatch.clear(); e->seekStream.clear(); e->dSeek = nullptr; e->dSeekFailed = nullptr;
+  for (int s = 0; s < S; ++s)
+    for (const SeekWatch &w : e->streams[s].plan.watch) {
+      e->seekWatch.push_back(SeekDev{e->streams[s].clip, e->streams[s].clipLen, w.start, w.count, 0}); e->seekStream.push_back(s);
+    }
+  if (!e->seekWatch.empty()) {
+    e->dSeek = upload(e, e->seekWatch, own); e->dSeekFailed = dalloc<int>(e->seekWatch.size(), own);
+    if (!e->dSeek || !e->dSeekFailed) { free_batch(e); return e->fail("device allocation failed (seek watch)"); }
+    dzero(e->dSeekFailed, e->seekWatch.size() * sizeof(int), 0);
+  }
   e->dGate = nullptr; e->dLoud = nullptr; e->dFired = nullptr;
   if (!e->gate.empty()) {
     e->dGate = upload(e, e->gate, own); e->dLoud = dalloc<uint8_t>((size_t)e->gateCallsTotal, own); e->dFired = dalloc<int>(e->gate.size(), own);
     if (!e->dGate || !e->dLoud || !e->dFired) { free_batch(e); return e->fail("device allocation failed (gate watch)"); }
     dzero(e->dFired, e->gate.size() * sizeof(int), 0);
   }
+#ifndef BS_HOSTEMU
+  // the uploads above went through the legacy default stream from pageable memory; the run may be queued on any stream,
+  // including non-blocking ones that do not order against it
+  if (cudaStreamSynchronize(0) != cudaSuccess) { free_batch(e); return e->fail("device error during the table upload"); }
+#endif
   e->committed = true;
   return 0;
 }
@@ -1040,7 +1083,18 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
   const int S = (int)e->streams.size();
   reset_state(e, q);
   e->launches = 0;
+  e->lastRunStream = q;
   for (auto &k : e->kstat) { k.ms = 0.0; k.launches = 0; k.units = 0; }
+  // streams whose silence gate closed for good (inactive time-map segments): the output from there on is zeros
+  for (int s = 0; s < S; ++s) {
+    const StreamDev &d = e->hs[s];
+    if (d.nLive >= d.nOut) continue;
+#ifdef BS_HOSTEMU
+    for (int c = 0; c < g.C; ++c) std::memset(d.out + (size_t)c * d.outStride + d.nLive, 0, (size_t)(d.nOut - d.nLive) * sizeof(float));
+#else
+    cudaMemset2DAsync(d.out + d.nLive, (size_t)d.outStride * sizeof(float), 0, (size_t)(d.nOut - d.nLive) * sizeof(float), (size_t)g.C, q);
+#endif
+  }
 #ifdef BS_HOSTEMU
   for (int s = 0; s < S && hClips; ++s)
     std::memcpy((void *)e->streams[s].clip, hClips[s], (size_t)g.C * e->streams[s].clipLen * sizeof(float));
@@ -1052,6 +1106,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     for (long long k = 0; k < e->gate[i].nCalls; ++k) e->dLoud[e->gate[i].callBase + k] = gate_call_loud(e->gate[i], g.C, k);
     e->dFired[i] = gate_count(e->gate[i], g.L, e->dLoud);
   }
+  for (size_t i = 0; i < e->seekWatch.size(); ++i) e->dSeekFailed[i] = seek_watch_failed(e->seekWatch[i], g.C);
 #else
   e->spans.clear(); e->evUsed = 0;
   const bool host = hClips != nullptr && hOuts != nullptr;
@@ -1064,7 +1119,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     if (host) { cudaStreamWaitEvent(e->sIn, e->evFork, 0); cudaStreamWaitEvent(e->sOut, e->evFork, 0); }
     e->backUsed[0] = e->backUsed[1] = false;
   }
-  std::vector<long long> copied(host ? S : 0, 0);
+  std::vector<long long> copied(host ? S : 0, 0), fetched(host ? S : 0, 0);
   long long i = 0;
   for (const bsb_engine::Chunk &ck : chunks) {
     if (e->maxBlocks <= 0) break;
@@ -1092,10 +1147,18 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
         if (n1 > n0)
           cudaMemcpy2DAsync(hOuts[e->order[s]] + n0, (size_t)d.nOut * sizeof(float), d.out + n0, (size_t)d.outStride * sizeof(float),
                             (size_t)(n1 - n0) * sizeof(float), (size_t)g.C, cudaMemcpyDeviceToHost, e->sOut);
+        fetched[s] = std::max(fetched[s], n1);
       }
     }
     ++i;
   }
+  if (host)   // what no block covers: the zeros behind a closed silence gate (written on `cudaStream` before the fork)
+    for (int s = 0; s < S; ++s) {
+      const StreamDev &d = e->hs[s];
+      if (d.nOut > fetched[s])
+        cudaMemcpy2DAsync(hOuts[e->order[s]] + fetched[s], (size_t)d.nOut * sizeof(float), d.out + fetched[s], (size_t)d.outStride * sizeof(float),
+                          (size_t)(d.nOut - fetched[s]) * sizeof(float), (size_t)g.C, cudaMemcpyDeviceToHost, e->sOut);
+    }
   if (two) {   // join
     cudaEventRecord(e->evJoin[0], e->sFront); cudaEventRecord(e->evJoin[1], e->sBack);
     cudaStreamWaitEvent(q, e->evJoin[0], 0); cudaStreamWaitEvent(q, e->evJoin[1], 0);
@@ -1109,6 +1172,8 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     gate_energy_kernel<<<dim3((unsigned)((e->gateMaxCalls + 127) / 128), (unsigned)e->gate.size()), 128, 0, q>>>(e->dGate, g.C, e->dLoud);
     gate_count_kernel<<<(unsigned)((e->gate.size() + 63) / 64), 64, 0, q>>>(e->dGate, (int)e->gate.size(), g.L, e->dLoud, e->dFired);
   }
+  if (!e->seekWatch.empty())
+    seek_watch_kernel<<<(unsigned)((e->seekWatch.size() + 63) / 64), 64, 0, q>>>(e->dSeek, (int)e->seekWatch.size(), g.C, e->dSeekFailed);
   if (cudaGetLastError() != cudaSuccess) return e->fail("copy or launch failed");
 #endif
   return 0;
@@ -1122,6 +1187,13 @@ int bsb_run_host(bsb_engine *e, const float *const *hClips, float *const *hOuts,
 }
 
 void bsb_set_overlap(bsb_engine *e, int on) { e->overlap = on != 0; }
+
+int bsb_synchronize(bsb_engine *e) {
+#ifndef BS_HOSTEMU
+  if (cudaStreamSynchronize(e->lastRunStream) != cudaSuccess) return e->fail("device error: %s", cudaGetErrorString(cudaGetLastError()));
+#endif
+  return 0;
+}
 
 int bsb_selftest_arith(const float *dX, const float *dD, float *dQ, float *dR, int *dFlags, int n) {
 #ifdef BS_HOSTEMU

@@ -57,6 +57,7 @@ struct StreamDev {
   long long outStride;    // channel stride of `out`
   long long outBase;      // output sample n is stored at out[c*outStride + n - outBase]
   long long nBlocks;
+  long long nLive;        // output samples [0, nLive) come from the blocks; [nLive, nOut) is where the silence gate had closed (zeros)
 };
 // persistent per-stream state + per-chunk scratch (all device pointers, stream-major)
 struct StateDev {
@@ -518,7 +519,7 @@ BS_HD void ola_quad(const DevGeom &g, const DevTables &T, const StreamDev &sd, i
   }
   if (x < o.xE1) {
     const long long n = o.ringBase + x;
-    if (n < sd.nOut) {
+    if (n < sd.nLive) {
       f4 wp;
       if (n + 3 < g.wpStartLen) wp = *(const f4 *)(T.wpStart + n);
       else if (n >= g.wpStartLen) { int q = o.wpPhase + x; q -= (q / H) * H; wp = *(const f4 *)(T.wpSteady + q); }
@@ -530,9 +531,9 @@ BS_HD void ola_quad(const DevGeom &g, const DevTables &T, const StreamDev &sd, i
       float *dst = sd.out + (size_t)c * sd.outStride + (n - sd.outBase);
       const float r0 = acc.x / wp.x, r1 = acc.y / wp.y, r2 = acc.z / wp.z, r3 = acc.w / wp.w;
       dst[0] = r0;
-      if (n + 1 < sd.nOut) dst[1] = r1;
-      if (n + 2 < sd.nOut) dst[2] = r2;
-      if (n + 3 < sd.nOut) dst[3] = r3;
+      if (n + 1 < sd.nLive) dst[1] = r1;
+      if (n + 2 < sd.nLive) dst[2] = r2;
+      if (n + 3 < sd.nLive) dst[3] = r3;
     }
   } else *(f4 *)(ringNew + p) = acc;
 }
@@ -551,7 +552,7 @@ BS_HD void ola_sample(const DevGeom &g, const DevTables &T, const StreamDev &sd,
   }
   if (x < o.xE1) {
     const long long n = o.ringBase + x;
-    if (n < sd.nOut) {
+    if (n < sd.nLive) {
       float wp;
       if (n < g.wpStartLen) wp = T.wpStart[n];
       else { int q = o.wpPhase + x; q -= (q / H) * H; wp = T.wpSteady[q]; }

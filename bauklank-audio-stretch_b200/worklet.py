@@ -232,6 +232,7 @@ class WorkletTimeline:
             q.semitones, q.tonality_limit = r["semitones"], r["tonality_limit"]
             q.formant_semitones, q.formant_base = r["formant_semitones"], r["formant_base"]
             q.formant_compensation, q.active = int(r["formant_compensation"]), int(r["active"])
+            q.transpose_factor = q.formant_factor = float("nan")
         return arr
 
     def render(self, engine, n_out, events=(), clip=None):

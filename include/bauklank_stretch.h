@@ -10,7 +10,7 @@
  *
  * Part 2 is the batched, handle-based form of the same operator for many independent streams with DEVICE-resident
  * audio: the worklet's per-quantum drive (app/SignalsmithStretch.mjs:826-954) is compiled on the host into a block
- * table and executed by three CUDA kernels per time chunk.  No torch types cross this boundary: plain pointers, sizes
+ * table and executed by a short pipeline of CUDA kernels per time chunk.  No torch types cross this boundary: plain pointers, sizes
  * and a cudaStream_t passed as void*.
  *
  * There is no CPU fallback: every entry point that computes requires a CUDA device.
@@ -41,7 +41,7 @@ void setFormantSemitones(float semitones, int compensatePitch);    /* "t" :475, 
 void setFormantBase(float baseFreq);                               /* "u" :476, used at :849 */
 void seek(int inputSamples, double playbackRate);                  /* "v" :477, used at :935 */
 void process(int inputSamples, int outputSamples);                 /* "w" :478, used at :869, :882, :936 */
-void flush(int outputSamples); /* "x" :479 -- bound but never called by the reference JS; aborts with a message */
+void flush(int outputSamples); /* "x" :479 -- bound but never called by the reference JS; implemented (W#46), bit-exact */
 int stretch_main(int argc, char **argv); /* "y" :480 `_main`, a no-op (a shared object cannot export `main`) */
 /* the reference seeds its RNG from crypto.getRandomValues (:382-394); a drop-in needs a way to pin it */
 void stretch_set_seed(uint32_t seed);
@@ -54,6 +54,9 @@ typedef struct bsb_segment {
   double output, input, rate;
   double semitones, tonality_hz, formant_semitones, formant_base_hz, loop_start, loop_end;
   int32_t active, formant_compensation;
+  /* not NaN: the driver calls setTransposeFactor / setFormantFactor (wasm exports "q" / "s", :472, :474) with this
+   * multiplier instead of the semitone setters the worklet uses; NaN = unset (the worklet's own behaviour) */
+  double transpose_factor, formant_factor;
 } bsb_segment;
 
 /* configure()/presetDefault()/presetCheaper() for a batch; all streams of one engine share the configuration */
@@ -71,7 +74,11 @@ const char *bsb_last_error(const bsb_engine *e);
 /* Start describing a batch of n_streams independent streams.  d_clip / d_out are DEVICE pointers to planar f32
  * [channels][len]. */
 int bsb_begin(bsb_engine *e, int n_streams);
-/* buffer-playback drive: per render quantum `seek(bufferLength, rate); process(0, quantum)` (:883-943) */
+/* buffer-playback drive: per render quantum `seek(bufferLength, rate); process(0, quantum)` (:883-943).  Inactive
+ * segments (stop(), :861-869) run `process(quantum, quantum)` on a zeroed input buffer like the worklet does, including
+ * the engine's silence gate: after 2*blockSamples of inactive output every call returns zeros.  A stream that is started
+ * again after the gate has closed re-arms its block phase at an arbitrary output sample -- that one case is refused here
+ * (bsb_last_error says so) and left to Part 1. */
 int bsb_add_kiosk(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, long long n_out,
                   int quantum, const bsb_segment *segments, int n_segments, uint32_t seed);
 /* The same drive, already resolved quantum by quantum (what a host-side mirror of the worklet's time map,
@@ -83,6 +90,7 @@ typedef struct bsb_quantum {
   long long input_samples_end, valid_start, valid_end;
   float semitones, tonality_limit, formant_semitones, formant_base;
   int32_t formant_compensation, active;
+  float transpose_factor, formant_factor;   /* NaN = unset, see bsb_segment */
 } bsb_quantum;
 int bsb_add_kiosk_table(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, long long n_out,
                         int quantum, const bsb_quantum *table, long long n_quanta, uint32_t seed);
@@ -100,6 +108,9 @@ int bsb_run(bsb_engine *e, void *cuda_stream);
  * copies are pipelined with the kernels time chunk by time chunk (input of chunk i+1 and output of chunk i-1 move
  * while chunk i computes).  Everything is ordered after, and joined back into, `cuda_stream`. */
 int bsb_run_host(bsb_engine *e, const float *const *h_clips, float *const *h_outs, void *cuda_stream);
+/* block until everything the last bsb_run / bsb_run_host queued has finished (the host outputs of bsb_run_host are only
+ * complete after this, or after the caller's own synchronisation of `cuda_stream`) */
+int bsb_synchronize(bsb_engine *e);
 /* rebind the device I/O pointers of an already planned batch (same shapes) without re-planning */
 int bsb_rebind(bsb_engine *e, int stream, const float *d_clip, float *d_out);
 long long bsb_total_blocks(const bsb_engine *e);
@@ -108,10 +119,12 @@ int bsb_chunk_blocks(const bsb_engine *e);
 /* kernel launches issued by the last bsb_run, and a read-out of one block record (for the indexing tests):
  * out[0]=flags out[1]=timeFactor bits, out[2..4]=cur window {start lo hi}, out[5..7]=prev window */
 long long bsb_launch_count(const bsb_engine *e);
-/* Streaming drives only (bsb_add_streaming): the reference's process() stops running blocks after 2*blockSamples
- * silent input samples (its "silence gate", W#48 7838-7943 -- data dependent, so the ahead-of-time block plan of the
- * batched path does not follow it).  Every run re-derives, from the clips as they are on the device, how many
- * process() calls the reference would have gated; 0 = the batch result is the reference's.  Synchronises. */
+/* The reference's process() stops running blocks after 2*blockSamples silent input samples (its "silence gate", W#48
+ * 7838-7943).  Where that depends on the audio the ahead-of-time block plan cannot follow it, so every run re-derives
+ * from the clips as they are on the device: (streaming drives) how many process() calls the reference would have
+ * gated; (kiosk drives with inactive segments) how many of the seeks the plan took for loud -- the buffer held clip
+ * samples -- were in fact digital silence, which would have left the gate's counter running.  0 = the batch result is
+ * the reference's.  Synchronises with the stream of the last run. */
 long long bsb_gate_events(bsb_engine *e);
 int bsb_block_info(const bsb_engine *e, int stream, long long block, long long out[8]);
 /* Per-kernel accounting of the last bsb_run.  launches and units (analysis: window x channel transforms actually

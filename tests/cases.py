@@ -17,10 +17,14 @@ T8 = 8000.0  # worklet default tonalityHz (app/SignalsmithStretch.mjs:594)
 
 
 def seg(output=0.0, input=0.0, rate=1.0, semitones=0.0, tonality_hz=T8, formant_semitones=0.0,
-        formant_compensation=False, formant_base_hz=0.0, loop_start=0.0, loop_end=0.0):
+        formant_compensation=False, formant_base_hz=0.0, loop_start=0.0, loop_end=0.0, active=True,
+        transpose_factor=None, formant_factor=None):
+    """One time-map entry.  ``transpose_factor`` / ``formant_factor``: the driver uses the engine's setTransposeFactor /
+    setFormantFactor exports (app/SignalsmithStretch.mjs:472,474) instead of the semitone setters."""
     return dict(output=output, input=input, rate=rate, semitones=semitones, tonality_hz=tonality_hz,
                 formant_semitones=formant_semitones, formant_compensation=formant_compensation,
-                formant_base_hz=formant_base_hz, loop_start=loop_start, loop_end=loop_end)
+                formant_base_hz=formant_base_hz, loop_start=loop_start, loop_end=loop_end, active=active,
+                transpose_factor=transpose_factor, formant_factor=formant_factor)
 
 
 def schedule(segments, output, **changes):
@@ -30,8 +34,8 @@ def schedule(segments, output, **changes):
     new = dict(last)
     new.update(changes)
     new["output"] = output
-    if "input" not in changes:
-        new["input"] = last["input"] + (output - last["output"]) * last["rate"]
+    if "input" not in changes:     # (:679-682: an inactive segment's input stands still)
+        new["input"] = last["input"] + (output - last["output"]) * (last["rate"] if last.get("active", True) else 0.0)
     segments.append(new)
     return segments
 
@@ -71,8 +75,14 @@ def _setup(engine, case, channels):
 
 
 def _apply(engine, s, sr):
-    engine.setTransposeSemitones(s["semitones"], s["tonality_hz"] / sr)
-    engine.setFormantSemitones(s["formant_semitones"], bool(s["formant_compensation"]))
+    if s.get("transpose_factor") is None:
+        engine.setTransposeSemitones(s["semitones"], s["tonality_hz"] / sr)
+    else:
+        engine.setTransposeFactor(s["transpose_factor"], s["tonality_hz"] / sr)
+    if s.get("formant_factor") is None:
+        engine.setFormantSemitones(s["formant_semitones"], bool(s["formant_compensation"]))
+    else:
+        engine.setFormantFactor(s["formant_factor"], bool(s["formant_compensation"]))
     engine.setFormantBase(s["formant_base_hz"] / sr)
 
 
@@ -92,6 +102,15 @@ def kiosk_run(engine, clip, case):
             tm.pop(0)
         s = tm[0]
         _apply(engine, s, sr)
+        if not s.get("active", True):        # :861-869: zeroed input, process(q, q)
+            ins, _ = engine.io_views()
+            ins[:, :q] = 0
+            engine.process(q, q)
+            _, outs = engine.io_views()
+            out[:, pos:pos + q] = outs[:, :q]
+            pos += q
+            k += 1
+            continue
         input_time = s["input"] + (output_time - s["output"]) * s["rate"]
         loop_len = s["loop_end"] - s["loop_start"]
         if loop_len > 0 and input_time >= s["loop_end"]:
@@ -272,6 +291,26 @@ CASES = {
                                 segments=[seg(rate=0.8, semitones=-5.0, tonality_hz=16000.0)]),
     "stream_transpose_only_q96": dict(drive="kiosk", clip=("survey", 30000), sr=48000, n_out=30000, preset="default", quantum=96,
                                       segments=[seg(rate=1.0, semitones=12.0)]),
+    # setTransposeFactor / setFormantFactor (exports "q" / "s"): multipliers instead of semitones
+    "factor_setters": dict(drive="kiosk", clip=("survey", 40000), sr=48000, n_out=40000, preset="default",
+                           segments=[seg(rate=0.8, transpose_factor=1.3348399, formant_factor=0.84, formant_compensation=True)]),
+    "factor_setters_stream": dict(drive="stream", clip=("survey", 30000), sr=48000, n_in=480, n_out=512, preset="cheaper",
+                                  segments=[seg(transpose_factor=0.75, tonality_hz=0.0, formant_factor=1.2)]),
+    # the kiosk's real operating range: rate 0.001 by default (app/multi/app.mjs:113), clamp floor 1e-5 (:483); rate*H <= 1
+    # takes the other branch of seekTimeFactor (W#49) and every block draws random time factors
+    "rate_1e-5": dict(drive="kiosk", clip=("survey", 20000), sr=48000, n_out=30000, preset="default", seed=7,
+                      segments=[seg(rate=1e-5, input=0.2, semitones=-3.0)]),
+    "rate_5e-4_cheaper": dict(drive="kiosk", clip=("survey", 20000), sr=48000, n_out=30000, preset="cheaper", seed=8,
+                              segments=[seg(rate=5e-4, input=0.1, semitones=4.0, tonality_hz=16000.0)]),
+    "rate_1e-3_shipped": dict(drive="kiosk", clip=("survey", 30000), sr=48000, n_out=40000, block=(9600, 2400, 1), seed=9,
+                              segments=[seg(rate=1e-3, input=0.3, semitones=0.0, tonality_hz=16000.0, formant_base_hz=200.0)]),
+    # stop() / start(): inactive segments run process(q, q) on a zeroed buffer (:861-869).  A short pause (the gate stays
+    # open), and a stop that lasts: after 2 * blockSamples of it the silence gate closes and the output is zeros
+    "pause_and_resume": dict(drive="kiosk", clip=("survey", 40000), sr=48000, n_out=40000, preset="default",
+                             segments=[seg(rate=1.2, semitones=2.0), seg(output=0.2, input=0.24, rate=1.2, semitones=2.0, active=False),
+                                       seg(output=0.33, input=0.24, rate=0.9, semitones=-1.0)]),
+    "stop_for_good_cheaper": dict(drive="kiosk", clip=("survey", 40000), sr=48000, n_out=50000, preset="cheaper",
+                                  segments=[seg(rate=1.0, semitones=3.0), seg(output=0.31, input=0.31, rate=1.0, semitones=3.0, active=False)]),
 }
 
 # Cases for the 18-call surface only (oracle engines and the compat shim): the silence gate of process() (W#48
@@ -297,7 +336,8 @@ SHIM_CASES = {
 
 # small subset used by the CPU suite for the (slower) serial emulation of the kernels
 FAST = ["KA5", "rng_low_rate", "stream_480_512_cheaper", "stream_100_900", "loop", "mono_custom_block",
-        "lowlat_8ch_formant_auto", "stream_transpose_only_q96"]
+        "lowlat_8ch_formant_auto", "stream_transpose_only_q96", "factor_setters", "factor_setters_stream", "rate_1e-5",
+        "rate_5e-4_cheaper", "rate_1e-3_shipped", "pause_and_resume", "stop_for_good_cheaper"]
 
 
 def sha_of(y):

@@ -243,6 +243,29 @@ def test_control_trace_through_the_quantum_table(bs):
     eng.close()
 
 
+@pytest.mark.parametrize("kind", ["pause", "late_start", "stop"])
+def test_stop_and_start_on_gpu(kind, bs):
+    """Inactive time-map segments (process(q, q) on a zeroed buffer, app/SignalsmithStretch.mjs:861-869) with the silence
+    gate, device path and host-audio path, against the oracle driven quantum by quantum."""
+    import torch
+    import test_worklet
+    clip = refdrive.survey_clip(30000)
+    n_out = 45000
+    ref = bs.WorkletTimeline(48000.0).render(refdrive.PortEngine(), n_out, events=test_worklet._stop_start_trace(kind), clip=clip)
+    tl = bs.WorkletTimeline(48000.0); tl.addBuffers(clip)
+    recs = tl.resolve(n_out, events=test_worklet._stop_start_trace(kind))
+    eng = bs.BatchStretch(2, 48000.0)
+    dclip = torch.from_numpy(clip).cuda()
+    outs = eng.plan([dclip], [bs.TableDrive(n_out, bs.WorkletTimeline.table(recs))], chunk_blocks=9)
+    outs[0].fill_(7.0)                       # stale device memory must not show through behind a closed gate
+    eng.run(); torch.cuda.synchronize()
+    assert cases.compare(outs[0].cpu().numpy(), ref)[0] and eng.gate_events() == 0
+    hin, hout = [torch.from_numpy(clip).pin_memory()], [torch.full((2, n_out), 7.0).pin_memory()]
+    eng.run_host(hin, hout)
+    assert cases.compare(hout[0].numpy(), ref)[0]
+    eng.close()
+
+
 def test_edge_cases_empty_tiny_and_ragged_on_gpu(bs):
     """Empty output, one output sample, a clip shorter than the block, ragged ends, playing past the clip's end --
     all in one batch, each equal to the oracle."""

@@ -92,10 +92,14 @@ def test_shim_parameter_changes_every_quantum(emu):
 def test_error_behaviour(emu):
     eng = bs.BatchStretch(2, 48000.0, lib=emu)
     x = np.zeros((2, 1000), np.float32)
-    with pytest.raises(RuntimeError):      # inactive segments are not supported by the batched path
-        eng.plan([x], [bs.KioskDrive(100, [bs.segment(active=False)])])
+    with pytest.raises(RuntimeError):      # the streaming drive's silence gate depends on the audio: no inactive segments there
+        eng.plan([x], [bs.StreamingDrive(100, 100, 5, [bs.segment(active=False)])])
     with pytest.raises(RuntimeError):      # n_calls * n_in must fit the clip
         eng.plan([x], [bs.StreamingDrive(512, 512, 10)])
+    # playing again after the silence gate has closed re-arms the block phase mid-interval: refused, with a reason
+    y = np.ones((2, 60000), np.float32)
+    with pytest.raises(RuntimeError, match="silence gate"):
+        eng.plan([y], [bs.KioskDrive(60000, [bs.segment(), bs.segment(output=0.1, input=0.1, active=False), bs.segment(output=0.6, input=0.1)])])
     eng.close()
     with pytest.raises(RuntimeError):      # block < 8
         bs.BatchStretch(2, 48000.0, block_samples=4, interval_samples=1, lib=emu)

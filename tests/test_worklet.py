@@ -123,7 +123,70 @@ def test_controller_messages_to_schedule(emu):
     eng.run()
     assert cases.compare(np.array(outs[0]), ref)[0] and np.abs(ref).max() > 1e-3
     eng.close()
-    # an idle worklet (nothing scheduled: the initial segment is inactive) is process(q,q) on silence: not batched
+    # an idle worklet (nothing scheduled: the initial segment is inactive) is process(q,q) on silence: zeros
     tl = bs.WorkletTimeline(48000.0, lib=emu); tl.addBuffers(clip)
-    with pytest.raises(RuntimeError):
-        bs.BatchStretch(2, 48000.0, lib=emu).plan([np.ascontiguousarray(clip)], [bs.TableDrive(1000, bs.WorkletTimeline.table(tl.resolve(1000)))])
+    eng = bs.BatchStretch(2, 48000.0, lib=emu)
+    outs = eng.plan([np.ascontiguousarray(clip)], [bs.TableDrive(1000, bs.WorkletTimeline.table(tl.resolve(1000)))])
+    eng.run()
+    assert np.array(outs[0]).shape == (2, 1000) and not np.array(outs[0]).any()
+    eng.close()
+
+
+def _stop_start_trace(kind):
+    """play, stop, play again -- what the kiosk's `active` control produces: controlsChanged re-schedules the whole parameter set
+    with active toggled (app/multi/app.mjs:495-507).  (remoteMethods.stop() itself, :625-630, schedules a segment without
+    tonalityHz & co. and hands NaN to the engine -- the quirk the mirror refuses, see worklet.py.)"""
+    def stop(k):
+        return (k, "schedule", (dict(active=False, outputTime=k * 128 / 48000, **FULL),))
+    ev = [(3, "schedule", (dict(active=True, input=0.05, rate=1.1, semitones=2, outputTime=3 * 128 / 48000, **FULL),))]
+    if kind == "pause":            # 0.1 s of inactivity: the silence gate stays open (2 * 5760 samples = 0.24 s)
+        ev += [stop(60), (98, "schedule", (dict(active=True, rate=0.8, semitones=-3, outputTime=98 * 128 / 48000, **FULL),))]
+    elif kind == "late_start":     # idle for 0.2 s before anything plays, then a stop that lasts to the end
+        ev = [(75, "schedule", (dict(active=True, input=0.0, rate=1.0, semitones=0, outputTime=75 * 128 / 48000, **FULL),)), stop(170)]
+    elif kind == "stop":           # stop for good
+        ev += [stop(90)]
+    elif kind == "restart":        # ... and start again long after the gate has closed
+        ev += [stop(60), (260, "schedule", (dict(active=True, rate=1.0, semitones=0, outputTime=260 * 128 / 48000, **FULL),))]
+    return ev
+
+
+@pytest.mark.parametrize("preset", ["default", "cheaper"])
+@pytest.mark.parametrize("kind", ["pause", "late_start", "stop"])
+def test_stop_and_start_run_on_the_batched_path(kind, preset, emu):
+    """Inactive segments are process(q, q) on a zeroed buffer (app/SignalsmithStretch.mjs:861-869), silence gate included:
+    the table-driven engine follows the oracle driven quantum by quantum, bit for bit."""
+    clip = refdrive.survey_clip(30000)
+    n_out = 45000
+    ref = bs.WorkletTimeline(48000.0, config=dict(preset=preset), lib=emu).render(refdrive.PortEngine(), n_out, events=_stop_start_trace(kind), clip=clip)
+    tl = bs.WorkletTimeline(48000.0, config=dict(preset=preset), lib=emu); tl.addBuffers(clip)
+    recs = tl.resolve(n_out, events=_stop_start_trace(kind))
+    assert any(not r["active"] for r in recs) and any(r["active"] for r in recs)
+    eng = bs.BatchStretch(2, 48000.0, preset=preset, lib=emu)
+    clips = [np.ascontiguousarray(clip)]
+    outs = eng.plan(clips, [bs.TableDrive(n_out, bs.WorkletTimeline.table(recs))], chunk_blocks=7)
+    eng.run()
+    assert cases.compare(np.array(outs[0]), ref)[0] and np.abs(ref).max() > 1e-2
+    assert eng.gate_events() == 0
+    if kind != "pause":
+        assert not ref[:, -4000:].any()                      # the gate closed: zeros to the end
+    host = [np.zeros_like(ref)]                                # ... and through the host-audio entry point (tail included)
+    eng.run_host(clips, host)
+    assert cases.compare(host[0], ref)[0]
+    eng.close()
+
+
+def test_restart_after_the_gate_closed_is_refused_and_a_silent_seek_is_reported(emu):
+    clip = refdrive.survey_clip(30000)
+    tl = bs.WorkletTimeline(48000.0, lib=emu); tl.addBuffers(clip)
+    recs = tl.resolve(45000, events=_stop_start_trace("restart"))
+    eng = bs.BatchStretch(2, 48000.0, lib=emu)
+    with pytest.raises(RuntimeError, match="silence gate"):
+        eng.plan([np.ascontiguousarray(clip)], [bs.TableDrive(45000, bs.WorkletTimeline.table(recs))])
+    # a pause whose first seek afterwards lands on digital silence inside the clip: the plan took it for loud, the run says so
+    quiet = clip.copy(); quiet[:, 4000:26000] = 0.0
+    tl = bs.WorkletTimeline(48000.0, lib=emu); tl.addBuffers(quiet)
+    recs = tl.resolve(30000, events=_stop_start_trace("pause"))
+    outs = eng.plan([np.ascontiguousarray(quiet)], [bs.TableDrive(30000, bs.WorkletTimeline.table(recs))])
+    eng.run()
+    assert eng.gate_events() == 1
+    eng.close()
