@@ -166,6 +166,16 @@ class Control {
   // `blockProcess = {}` of the silence gate (W#48 7842-7845) and of reset() (W#59)
   void resetBlockProcess() { since_ = 0xffffffffu; steps_ = 0; step_ = 0; cur_ = -1; }
   void resetAll() { resetBlockProcess(); prevInputOffset_ = -1; didSeek_ = false; }
+  // One-block-at-a-time callers (the 18-call shim runs for as long as the kiosk is up): drop the records of the blocks before
+  // the one under way; it becomes block 0 of the plan.  Call from onStart, where the current block is the plan's last.
+  void keepOnlyCurrent(StreamPlan &plan) {
+    if (cur_ <= 0) return;
+    plan.blocks.erase(plan.blocks.begin(), plan.blocks.begin() + cur_);
+    plan.blocks2.erase(plan.blocks2.begin(), plan.blocks2.begin() + cur_);
+    plan.windows.erase(plan.windows.begin(), plan.windows.begin() + 2 * cur_);
+    lastNew_ = lastNew_ >= cur_ ? (int)(lastNew_ - cur_) : -1;
+    cur_ = 0;
+  }
 
  private:
   void snapshot(StreamPlan &plan, int from, int to) {

@@ -257,11 +257,11 @@ static int chain_warps(int C, int longStep, int nSlots) {
 
 template <int C>
 static void launch_chain(int S, int warps, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
-                         const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st, int ctas, int *prog) {
-  chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog);
+                         const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st, int ctas, int *prog, int *err) {
+  chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
 }
 typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
-                                long long, int, const cf *, cf *, const StateDev &, int, int *);
+                                long long, int, const cf *, cf *, const StateDev &, int, int *, int *);
 static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>, launch_chain<3>, launch_chain<4>,
                                                 launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
 template <int C> static cudaError_t chain_attr(size_t smem) {
@@ -395,7 +395,8 @@ struct bsb_engine {
   std::vector<Chunk> chunks, chunksHost;     // device-resident audio / host audio (short first chunk)
   std::vector<long long> needEndHost;
   std::vector<int> order, posOf;   // hs[pos] describes streams[order[pos]]
-  int *dChainProg = nullptr;
+  int *dChainProg = nullptr, *dChainErr = nullptr;   // relay of the chain wavefront: ticket + progress words; time-out flag
+  int *hChainErr = nullptr;                           // pinned copy of the flag, refreshed behind every run
   std::vector<long long> blockBase;
   std::vector<BlockRec> hostBlocks;
   std::vector<long long> needEnd;   // [chunk][stream]: clip samples (per channel) the chunk's analysis windows reach
@@ -678,9 +679,9 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
       carry_kernel<<<S, 256, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     if (twoStreams) { cudaEventRecord(e->evFront[buf], qF); cudaStreamWaitEvent(qB, e->evFront[buf], 0); }
     q = qB;
-    if (ctas > 1) cudaMemsetAsync(e->dChainProg, 0, (size_t)S * ctas * sizeof(int), q);
+    if (ctas > 1) cudaMemsetAsync(e->dChainProg, 0, ((size_t)S * ctas + 1) * sizeof(int), q);   // the ticket counter + progress words
     span("chain_kernel", nBlk * g.C, [&] {
-      kChainLaunch[g.C - 1](S, chainWarps, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st, ctas, e->dChainProg); });
+      kChainLaunch[g.C - 1](S, chainWarps, smC, q, e->dg, e->dt, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, e->specOut, st, ctas, e->dChainProg, e->dChainErr); });
     if (twoStreams) { cudaEventRecord(e->evBack[buf], qB); e->backUsed[buf] = true; }
     st.parity ^= 1;
   }
@@ -742,6 +743,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
     cudaEventCreateWithFlags(&e->evJoin[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
+  if (cudaHostAlloc((void **)&e->hChainErr, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *e->hChainErr = 0; else e->hChainErr = nullptr;
   const size_t smA = 4 * (size_t)fft_pitch(g.M) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
       cudaFuncSetAttribute(isynth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
@@ -770,6 +772,7 @@ void bsb_destroy(bsb_engine *e) {
   for (auto &ev : e->evPool) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) { if (e->evFront[i]) cudaEventDestroy(e->evFront[i]); if (e->evBack[i]) cudaEventDestroy(e->evBack[i]); if (e->evJoin[i]) cudaEventDestroy(e->evJoin[i]); }
   if (e->evFork) cudaEventDestroy(e->evFork);
+  if (e->hChainErr) cudaFreeHost(e->hChainErr);
   if (e->sFront) cudaStreamDestroy(e->sFront);
   if (e->sBack) cudaStreamDestroy(e->sBack);
   if (e->sIn) cudaStreamDestroy(e->sIn);
@@ -963,8 +966,12 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
   const size_t perSlot = (size_t)S * ((size_t)g.C * g.L * 4 + (size_t)g.B * 12 + CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (e->overlap ? 2 : 1) * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
   const bool autoChunk = chunkBlocks <= 0;
+  // scratch budget: 56 GB of the 180, less on a device that has less to give (other engines of the process, other tenants)
+  size_t budget = (size_t)56 << 30;
+#ifndef BS_HOSTEMU
+  { size_t freeB = 0, totalB = 0; if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) budget = std::min(budget, freeB / 10 * 7); }
+#endif
   if (autoChunk) {
-    const size_t budget = (size_t)56 << 30;
     chunkBlocks = (int)std::min<size_t>(256, std::max<size_t>(1, budget / perSlot));
     if (chunkBlocks > 32) chunkBlocks &= ~31;   // whole warps of the chain wavefront
   }
@@ -978,7 +985,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   const bool relayOk = autoChunk && chunkBlocks >= perPass && !e->dg.incremental;
   if (relayOk) {
     const size_t want = (size_t)S * (size_t)((e->maxBlocks + perPass - 1) / perPass) * perPass;
-    const size_t room = std::min<size_t>(((size_t)56 << 30) / (perSlot / S), (size_t)cap * perPass);
+    const size_t room = std::min<size_t>(budget / (perSlot / S), (size_t)cap * perPass);
     allocSlots = std::max(allocSlots, std::min(want, room));
   }
   // `lead` > 0: a short first chunk, for bsb_run_host -- nothing can be computed before the first chunk's clip samples
@@ -1022,6 +1029,8 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->specIn = dalloc<cf>(allocSlots * 2 * CB, own);
   e->specOut = dalloc<cf>(allocSlots * CB, own);
   e->dChainProg = dalloc<int>((size_t)std::max(cap, S) + 64, own);
+  e->dChainErr = dalloc<int>(1, own);
+  if (e->dChainErr) dzero(e->dChainErr, sizeof(int), 0);
   StateDev &st = e->st;
   const size_t nSlotTot = allocSlots;
   st.outSpec = dalloc<cf>(S * CB, own); st.predE[0] = dalloc<float>(S * CB, own); st.predE[1] = dalloc<float>(S * CB, own);
@@ -1036,7 +1045,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->recBuf[1] = (e->overlap && e->chunksHost.size() > 1) ? dalloc<float>(recFloats, own) : nullptr;   // only for chunk pipelining
   st.rec = e->recBuf[0];
   st.seeds = e->dSeeds; st.parity = 0;
-  if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !e->dChainProg || !st.outSpec ||
+  if (!e->dStreams || !e->dBlocks || !e->dBlocks2 || !e->dWindows || !e->dSeeds || !e->specIn || !e->specOut || !e->dChainProg || !e->dChainErr || !st.outSpec ||
       !st.predE[0] || !st.predE[1] || !st.lastInput || !st.freqEst || !st.ring[0] || !st.ring[1] || !st.frames || !st.inEnergy || !st.map || !st.fmAuto || !st.fmBase || !st.energy || !st.smoothed || !st.fm ||
       !st.rec) {
     free_batch(e);
@@ -1069,6 +1078,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   // the uploads above went through the legacy default stream from pageable memory; the run may be queued on any stream,
   // including non-blocking ones that do not order against it
   if (cudaStreamSynchronize(0) != cudaSuccess) { free_batch(e); return e->fail("device error during the table upload"); }
+  if (e->hChainErr) *e->hChainErr = 0;
 #endif
   e->committed = true;
   return 0;
@@ -1079,6 +1089,9 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
 // down at the same time).
 static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float *const *hOuts) {
   if (!e->committed) return e->fail("bsb_run needs a committed batch");
+#ifndef BS_HOSTEMU
+  if (e->hChainErr && *e->hChainErr) return e->fail("chain relay timed out in an earlier run of this batch (results invalid); re-commit to clear");
+#endif
   const Geometry &g = e->g;
   const int S = (int)e->streams.size();
   reset_state(e, q);
@@ -1172,6 +1185,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     gate_energy_kernel<<<dim3((unsigned)((e->gateMaxCalls + 127) / 128), (unsigned)e->gate.size()), 128, 0, q>>>(e->dGate, g.C, e->dLoud);
     gate_count_kernel<<<(unsigned)((e->gate.size() + 63) / 64), 64, 0, q>>>(e->dGate, (int)e->gate.size(), g.L, e->dLoud, e->dFired);
   }
+  if (e->hChainErr) cudaMemcpyAsync(e->hChainErr, e->dChainErr, sizeof(int), cudaMemcpyDeviceToHost, q);
   if (!e->seekWatch.empty())
     seek_watch_kernel<<<(unsigned)((e->seekWatch.size() + 63) / 64), 64, 0, q>>>(e->dSeek, (int)e->seekWatch.size(), g.C, e->dSeekFailed);
   if (cudaGetLastError() != cudaSuccess) return e->fail("copy or launch failed");
@@ -1191,6 +1205,7 @@ void bsb_set_overlap(bsb_engine *e, int on) { e->overlap = on != 0; }
 int bsb_synchronize(bsb_engine *e) {
 #ifndef BS_HOSTEMU
   if (cudaStreamSynchronize(e->lastRunStream) != cudaSuccess) return e->fail("device error: %s", cudaGetErrorString(cudaGetLastError()));
+  if (e->hChainErr && *e->hChainErr) return e->fail("chain relay timed out: a CTA waited for its predecessor's spectrum for seconds (results of the last run are invalid)");
 #endif
   return 0;
 }
@@ -1448,6 +1463,7 @@ void compat_process(int nIn, int nOut) {
   if (!c->e) bs::die("process() before configure()/presetDefault()/presetCheaper()");
   const Geometry &g = c->g; const int C = g.C, L = g.L, H = g.H;
   if (std::max(nIn, nOut) > c->ioLen) bs::die("process(): sample count exceeds the setBuffers() length");
+  if (c->ioCh < g.C) bs::die("process(): setBuffers() was called with fewer channels than the engine is configured for");
   c->prevCopied = 0;
   float total = 0.f; bool loud = false;
   if (C > 0 && nIn > 0) {
@@ -1478,14 +1494,17 @@ void compat_process(int nIn, int nOut) {
   } else { c->silenceFirst = true; c->silenceCounter = 0; }
 
   c->ctl->p = c->p;
-  // c->plan keeps one record per block since the last reset (40 bytes per block); block m is plan.blocks[m]
+  // c->plan holds the record of the block under way only (plan.blocks[c->m], c->m == 0 once a second block has started):
+  // an always-on kiosk must not grow a table
   auto onStart = [&](int, int inputOffset, int, bool rean, bool isNew, long long bi) {
     compat_copy_input(c, inputOffset);
     if (c->deferred) {   // split mode: every step of the previous block has run by now, its records are final
       compat_block(c, c->m);
       c->deferred = false;
     }
-    c->m = bi; c->curLaunched = false;
+    (void)bi;
+    c->ctl->keepOnlyCurrent(c->plan);
+    c->m = (long long)c->plan.blocks.size() - 1; c->curLaunched = false;
     if (isNew) {
       compat_window(c, 0, c->stage.data(), 0);
       if (rean) compat_window(c, H, c->stage.data(), 1);
@@ -1534,6 +1553,7 @@ void compat_flush(int nOut) {
   if (!c->e) bs::die("flush() before configure()");
   const Geometry &g = c->g; const int C = g.C, L = g.L;
   if (nOut > c->ioLen) bs::die("flush(): sample count exceeds the setBuffers() length");
+  if (c->ioCh < g.C) bs::die("flush(): setBuffers() was called with fewer channels than the engine is configured for");
   bool keepPrevInput = false, wpAfter = false;
   if (c->deferred) {
     int nS6 = 0, nSyn = 0;
@@ -1593,6 +1613,7 @@ void compat_seek(int n, double rate) {   // W#49
   if (!c->e) bs::die("seek() before configure()");
   const Geometry &g = c->g; const int cap = g.L + g.H;
   if (n > c->ioLen) bs::die("seek(): sample count exceeds the setBuffers() length");
+  if (c->ioCh < g.C) bs::die("seek(): setBuffers() was called with fewer channels than the engine is configured for");
   std::vector<float> tmp(cap, 0.f);
   int start = n - cap; if (start < 0) start = 0;
   float energy = 0.f;
