@@ -61,6 +61,8 @@ _BATCH_SIG = {
     "bsb_selftest_arith": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "bsb_set_profiling": (None, [C.c_void_p, C.c_int]),
     "bsb_set_overlap": (None, [C.c_void_p, C.c_int]),
+    "bsb_set_fast_fft": (None, [C.c_void_p, C.c_int]),
+    "bsb_fast_fft_active": (C.c_int, [C.c_void_p]),
     "bsb_kernel_count": (C.c_int, [C.c_void_p]),
     "bsb_kernel_stat": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                   C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

@@ -215,6 +215,13 @@ class BatchStretch:
         """Chunk pipelining on two internal CUDA streams (default on); off = strictly serial kernels."""
         self.lib.bsb_set_overlap(self.h, 1 if on else 0)
 
+    def set_fast_fft(self, on=True):
+        """STFT kernels specialised for the preset geometries (default on); off = the run-time-geometry kernels."""
+        self.lib.bsb_set_fast_fft(self.h, 1 if on else 0)
+
+    def fast_fft_active(self):
+        return bool(self.lib.bsb_fast_fft_active(self.h))
+
     def kernel_stats(self):
         """{kernel name: dict(ms, launches, units)} of the last run; ``ms`` is 0 unless profiling was on."""
         out = {}

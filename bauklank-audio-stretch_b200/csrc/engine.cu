@@ -10,6 +10,7 @@
 
 #include "../../include/bauklank_stretch.h"
 #include "kernels.cuh"
+#include "fft_fast.cuh"
 
 #ifndef BS_HOSTEMU
 #include <cuda_runtime.h>
@@ -17,6 +18,32 @@
 #endif
 
 namespace bs {
+
+// the specialised transforms (fft_fast.cuh), by geometry
+#define BS_FAST_GEOMS(X) X(10, 3) X(9, 5) X(10, 5) X(11, 3) X(9, 1)
+#ifdef BS_HOSTEMU
+static bool fast_analyse_any(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, bool rotate) {
+  if (!fast_ok(g)) return false;
+#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { fast_analyse<LG, OUTER>(g, T, x, w, X, (cf *)sm, rotate); return true; }
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return false;
+}
+static bool fast_synth_any(const DevGeom &g, const DevTables &T, const cf *X, float *frame, float *sm) {
+  if (!fast_ok(g)) return false;
+#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { fast_synth<LG, OUTER>(g, T, X, frame, (cf *)sm); return true; }
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return false;
+}
+static size_t fast_smem_floats_max() {
+  size_t m = 0;
+#define X_(LG, OUTER) m = std::max(m, fast_smem_bytes<LG, OUTER>() / sizeof(float));
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return m;
+}
+#endif
 
 // ---------------------------------------------------------------------------------- memory / launch abstraction
 #ifdef BS_HOSTEMU
@@ -56,6 +83,58 @@ __global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T
   const Window w = windows[2 * (sd.blockBase + m) + which];
   cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * g.B;
   analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x, which == 1);
+}
+
+// the same two kernels for the preset geometries (fft_fast.cuh): grid (slot, stream, {cur,prev} x channel) -- no index division
+template <int LG, int OUTER>
+__global__ void __launch_bounds__(kFastNT, 3) analysis_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                                  const Window *windows, long long slot0, int nSlots, cf *specIn) {
+  extern __shared__ __align__(16) float sm[];
+  const int slot = blockIdx.x, s = blockIdx.y, which = blockIdx.z & 1, c = blockIdx.z >> 1;
+  const StreamDev sd = streams[s];
+  const long long m = slot0 + slot;
+  if (m >= sd.nBlocks) return;
+  if (!(blocks[sd.blockBase + m].flags & kNew)) return;
+  const Window w = windows[2 * (sd.blockBase + m) + which];
+  cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * g.B;
+  fast_analyse<LG, OUTER>(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, (cf *)sm, which == 1);
+}
+template <int LG, int OUTER>
+__global__ void __launch_bounds__(kFastNT, 3) isynth_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
+                                                                const cf *specOut, StateDev st) {
+  extern __shared__ __align__(16) float sm[];
+  const int slot = blockIdx.x, s = blockIdx.y, c = blockIdx.z;
+  const StreamDev sd = streams[s];
+  if (slot0 + slot >= sd.nBlocks) return;
+  const size_t blk = (size_t)s * nSlots + slot;
+  fast_synth<LG, OUTER>(g, T, specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, (cf *)sm);
+}
+// launchers: false = no specialised kernel for this geometry (or more streams than a grid dimension holds)
+static bool launch_analysis_fast(const DevGeom &g, const DevTables &T, int S, int nSlots, cudaStream_t q, const StreamDev *streams, const BlockRec *blocks,
+                                 const Window *windows, long long slot0, cf *specIn) {
+  if (!fast_ok(g) || S > 65535) return false;
+#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { \
+    analysis_fast_kernel<LG, OUTER><<<dim3((unsigned)nSlots, (unsigned)S, (unsigned)(2 * g.C)), kFastNT, fast_smem_bytes<LG, OUTER>(), q>>>(g, T, streams, blocks, windows, slot0, nSlots, specIn); return true; }
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return false;
+}
+static bool launch_isynth_fast(const DevGeom &g, const DevTables &T, int S, int nSlots, cudaStream_t q, const StreamDev *streams, long long slot0,
+                               const cf *specOut, const StateDev &st) {
+  if (!fast_ok(g) || S > 65535) return false;
+#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { \
+    isynth_fast_kernel<LG, OUTER><<<dim3((unsigned)nSlots, (unsigned)S, (unsigned)g.C), kFastNT, fast_smem_bytes<LG, OUTER>(), q>>>(g, T, streams, slot0, nSlots, specOut, st); return true; }
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return false;
+}
+static bool fast_set_smem() {
+  bool ok = true;
+#define X_(LG, OUTER) ok = ok && cudaFuncSetAttribute(analysis_fast_kernel<LG, OUTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<LG, OUTER>()) == cudaSuccess && \
+                       cudaFuncSetAttribute(isynth_fast_kernel<LG, OUTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<LG, OUTER>()) == cudaSuccess;
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return ok;
 }
 
 // ---- map stage kernels (see kernels.cuh "map stage")
@@ -407,6 +486,7 @@ struct bsb_engine {
   struct KStat { const char *name; double ms; long long launches, units; };
   std::vector<KStat> kstat;
   bool profiling = false;
+  bool fastFft = true;             // specialised STFT kernels where the geometry has them (bsb_set_fast_fft; off = the run-time-geometry path)
   bool overlap = true;             // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1 (two CUDA
                                    // streams).  Gains nothing while every stream is live (each kernel fills the GPU alone), but
                                    // once the shorter streams of a batch have ended the chain runs on a fraction of the SMs and
@@ -520,7 +600,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     return k;
   };
 #ifdef BS_HOSTEMU
-  std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)fft_pitch(g.M) + g.L + preterms_smem_floats(g.C, g.longStep) + 64) / 4 + 1);
+  std::vector<f4> smv((map_smem_floats(g.B) + 4 * (size_t)fft_pitch(g.M) + g.L + preterms_smem_floats(g.C, g.longStep) + fast_smem_floats_max() + 64) / 4 + 1);
   float *sm = (float *)smv.data();
   const size_t recPerStream = (size_t)((nSlots + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C);
   auto mapE = g.C == 2 ? map_energy<2> : (g.C == 1 ? map_energy<1> : map_energy<0>);
@@ -534,9 +614,11 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
         long long m = slot0 + t;
         if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
         for (int which = 0; which < 2; ++which)
-          for (int c = 0; c < g.C; ++c)
-            analyse_window(e->dg, e->dt, sd.clip + (size_t)c * sd.clipLen, e->dWindows[2 * (sd.blockBase + m) + which],
-                           e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B, sm, 0, 1, which == 1);
+          for (int c = 0; c < g.C; ++c) {
+            cf *X = e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B;
+            const float *x = sd.clip + (size_t)c * sd.clipLen; const Window w = e->dWindows[2 * (sd.blockBase + m) + which];
+            if (!e->fastFft || !fast_analyse_any(e->dg, e->dt, x, w, X, sm, which == 1)) analyse_window(e->dg, e->dt, x, w, X, sm, 0, 1, which == 1);
+          }
       }
     }
     account("map_energy_kernel", nBlk * g.C);
@@ -614,7 +696,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
         for (int t = 0; t < nSlots && slot0 + t < e->hs[s].nBlocks; ++t)
           for (int c = 0; c < g.C; ++c) {
             const size_t blk = (size_t)s * nSlots + t;
-            synth_frame(e->dg, e->dt, e->specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, sm, 0, 1);
+            if (!e->fastFft || !fast_synth_any(e->dg, e->dt, e->specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, sm))
+              synth_frame(e->dg, e->dt, e->specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, sm, 0, 1);
           }
     }
     if (!(synthMode & kSynthFrames)) account("ola_kernel", nBlk * g.C);
@@ -654,7 +737,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     const unsigned nCta = (unsigned)((size_t)S * nSlots);
     if (twoStreams && e->backUsed[buf]) cudaStreamWaitEvent(qF, e->evBack[buf], 0);   // the chain that read this record buffer is done
     span("analysis_kernel", nNew * 2 * g.C, [&] {
-      analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
+      if (!e->fastFft || !launch_analysis_fast(e->dg, e->dt, S, nSlots, q, e->dStreams, e->dBlocks, e->dWindows, slot0, e->specIn))
+        analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
     span("map_energy_kernel", nBlk * g.C, [&] {
       map_energy_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     // the smoothers: one launch over the whole chunk, one lane per (stream, block) (slicing the chunk so that the arrays stay
@@ -689,7 +773,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
   if (stages & 2) {
     if (synthMode & (kSynthAdd | kSynthFrames))
       span("isynth_kernel", nBlk * g.C, [&] {
-        isynth_kernel<<<(unsigned)((size_t)S * nSlots * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, e->specOut, st); });
+        if (!e->fastFft || !launch_isynth_fast(e->dg, e->dt, S, nSlots, q, e->dStreams, slot0, e->specOut, st))
+          isynth_kernel<<<(unsigned)((size_t)S * nSlots * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, e->specOut, st); });
     const long long span_n = (long long)std::min<long long>(nSlots, e->maxBlocksOr1(slot0)) * g.H + g.L;
     if (!(synthMode & kSynthFrames)) {
       span("ola_kernel", nBlk * g.C, [&] {
@@ -717,7 +802,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   if (e->g.longStep < 1 || e->g.longStep > 32) { delete e; return nullptr; }
   make_tables(e->g, e->T);
   const Geometry &g = e->g;
-  e->dg = DevGeom{g.C, g.L, g.H, g.N, g.B, g.M, g.inner, g.outer, g.split, g.longStep, g.L >> 1, (int)e->T.wpStart.size(), 0, 1u, 0};
+  e->dg = DevGeom{g.C, g.L, g.H, g.N, g.B, g.M, g.inner, g.outer, g.split, g.longStep, g.L >> 1, (int)e->T.wpStart.size(), 0, 1u, 0, 0};
   {   // multiply-shift division by `outer`, verified for every index it will see
     bool ok = false;
     for (int sh = 0; sh <= 20 && !ok; ++sh) {
@@ -734,6 +819,9 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   e->dt.untangle = upload(e, e->T.untangle, e->owned); e->dt.rot = upload(e, e->T.rot, e->owned);
   e->dt.specRot = upload(e, e->T.specRot, e->owned);
   e->dt.wpStart = upload(e, e->T.wpStart, e->owned); e->dt.wpSteady = upload(e, e->T.wpSteady, e->owned);
+  e->dt.otw = upload(e, e->T.otw, e->owned);
+  e->dg.packTabOk = e->T.packTab.empty() ? 0 : 1;
+  e->dt.packTab = e->dg.packTabOk ? upload(e, e->T.packTab, e->owned) : nullptr;
 #ifndef BS_HOSTEMU
   cudaStreamSynchronize(0);   // table uploads done before any run can be queued on another stream
   cudaStreamCreateWithFlags(&e->sFront, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&e->sBack, cudaStreamNonBlocking);
@@ -746,7 +834,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   if (cudaHostAlloc((void **)&e->hChainErr, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *e->hChainErr = 0; else e->hChainErr = nullptr;
   const size_t smA = 4 * (size_t)fft_pitch(g.M) * sizeof(float);
   if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
-      cudaFuncSetAttribute(isynth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
+      cudaFuncSetAttribute(isynth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess || !fast_set_smem() ||
       cudaFuncSetAttribute(preterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
       chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep, chain_warps(g.C, g.longStep, 1 << 20))) != cudaSuccess ||
       cudaFuncSetAttribute(map_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
@@ -1201,6 +1289,8 @@ int bsb_run_host(bsb_engine *e, const float *const *hClips, float *const *hOuts,
 }
 
 void bsb_set_overlap(bsb_engine *e, int on) { e->overlap = on != 0; }
+void bsb_set_fast_fft(bsb_engine *e, int on) { e->fastFft = on != 0; }
+int bsb_fast_fft_active(const bsb_engine *e) { return (e->fastFft && fast_ok(e->dg) && e->streams.size() <= 65535) ? 1 : 0; }
 
 int bsb_synchronize(bsb_engine *e) {
 #ifndef BS_HOSTEMU

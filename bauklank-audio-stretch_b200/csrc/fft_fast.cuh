@@ -1,0 +1,370 @@
+// Specialised STFT kernels for the preset geometries: the same arithmetic as analyse_window / synth_frame (kernels.cuh)
+// -- the reference's radix-4 decimation-in-time butterflies on the same values in the same order (W#21/W#34 forward,
+// W#20/W#33 inverse, outer DFT-3/5 of W#35 4404-4625 and W#48 10408-10628, untangle, window) -- with the data movement
+// rebuilt around it.  The run-time-geometry path spends more instructions on indices, predicates and shared-memory
+// traffic than on the butterflies (ncu: 19 400 warp instructions per 3072-point analysis, 7 500 of them FADD/FMUL); here
+// every stride is a compile-time constant and a transform is a fixed sequence of stages:
+//
+//   forward   pack (window, zero-phase rotate, half-bin rotation; a leading radix-2 pass if log2(inner) is odd)
+//             -> [radix-16 = two fused radix-4 passes in registers] x n -> [radix-4] -> radix-4 + outer twiddles + DFT-3/5
+//             in registers -> untangle (pairs k, M-1-k) -> spectrum in HBM
+//   inverse   untangle^-1 from HBM (+ radix-2) -> the same passes, inverse butterflies -> last radix-4 + outer DFT
+//             + half-bin rotation + synthesis window in registers -> frame in HBM
+//
+// Complex values travel between stages as interleaved {re, im} pairs (one 64-bit shared-memory access per value), two
+// buffers used alternately; every buffer carries the padding that makes its reader conflict-free (its writer always
+// stores consecutive elements from consecutive lanes).  Stage bodies are (tid) work loops over NT logical threads so
+// that the serial test emulation (BS_HOSTEMU) can run the identical code.
+#pragma once
+#include "kernels.cuh"
+
+namespace bs {
+
+constexpr int kFastNT = 256;
+
+// geometry of a specialised transform
+template <int LG, int OUTER>
+struct FastGeom {
+  static constexpr int inner = 1 << LG, M = inner * OUTER, NT = kFastNT;
+  static constexpr int lg0 = LG & 1;                       // lgSize after the radix-2 pass that the pack stage absorbs
+  static constexpr int rem = LG - lg0 - 2;                 // bits left for the stages before the final radix-4 (+ outer DFT)
+  static constexpr int nR16 = rem / 4;
+  static constexpr bool hasR4 = (rem % 4) == 2;
+  static constexpr int nStages = nR16 + (hasR4 ? 1 : 0) + 1;   // shared-memory stages after the pack
+  static_assert(rem >= 0 && (rem % 2) == 0, "unsupported inner size");
+};
+
+// buffer layout: element e of sub-transform `sub` lives at sub * PITCH + e + (e >> SHIFT) * ADD   (ADD == 0: no padding)
+template <int SHIFT, int ADD, int PITCH>
+struct Lay {
+  static constexpr int pitch = PITCH;
+  BS_HHD static int at(int sub, int e) { return sub * PITCH + e + (ADD ? ((e >> SHIFT) * ADD) : 0); }
+};
+constexpr int lay_padded(int n, int shift, int add) { return n + (add ? ((n >> shift) * add) : 0); }
+constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
+// A stage reads runs of G consecutive elements per lane group, the groups P elements apart; with G < 16 the groups of
+// a half warp would share banks unless every P elements are followed by G elements of padding.
+//   radix-16 at lgSize: G = strideB = inner >> (lgSize + 4), P = 16 G;   radix-4 at lgSize: G = inner >> (lgSize + 2), P = 4 G
+//   the final radix-4 (stride 1) reads its four inputs as two 128-bit words: 2 elements of padding per 16
+template <int LG, int OUTER, int K> struct StageOf {   // stage K (0-based) after the pack
+  using F = FastGeom<LG, OUTER>;
+  static constexpr bool isR16 = K < F::nR16;
+  static constexpr bool isLast = K == F::nStages - 1;
+  static constexpr int lgSize = isR16 ? F::lg0 + 4 * K : (isLast ? LG - 2 : F::lg0 + 4 * F::nR16);
+  static constexpr int G = isR16 ? (F::inner >> (lgSize + 4)) : (F::inner >> (lgSize + 2));
+  static constexpr int P = isR16 ? 16 * G : 4 * G;
+  static constexpr int shift = isLast ? 4 : ilog2c(P);
+  static constexpr int add = isLast ? 2 : (G >= 16 ? 0 : G);
+  static constexpr int pitch = (lay_padded(F::inner, shift, add) + 1) & ~1;
+  using In = Lay<shift, add, pitch>;
+};
+template <int LG, int OUTER> struct NaturalLay { using L = Lay<0, 0, (1 << LG)>; };   // spectrum order k = i + s * inner
+// shared-memory floats of one CTA: two buffers, each large enough for any stage's input
+template <int LG, int OUTER, int K = 0> struct FastSmem {
+  using F = FastGeom<LG, OUTER>;
+  static constexpr int here = K < F::nStages ? StageOf<LG, OUTER, K>::pitch * OUTER : 0;
+  static constexpr int rest = FastSmem<LG, OUTER, K + 1>::value;
+  static constexpr int value = here > rest ? here : rest;
+};
+template <int LG, int OUTER> struct FastSmem<LG, OUTER, 8> { static constexpr int value = (1 << LG) * OUTER; };
+template <int LG, int OUTER> struct FastBuf { static constexpr int elems = (FastSmem<LG, OUTER>::value + 1) & ~1; };
+template <int LG, int OUTER> constexpr size_t fast_smem_bytes() { return 2 * (size_t)FastBuf<LG, OUTER>::elems * sizeof(cf); }
+
+// ---- the outer stage of one bin: twiddles on sub-transforms 1.., then the DFT across them (outer_stage_t, kernels.cuh)
+template <bool INV, int OUTER>
+BS_HD void outer_point(float *xr, float *xi, const cf *w /* [OUTER-1] */) {
+  if (OUTER < 2) return;
+#pragma unroll
+  for (int s = 1; s < OUTER; ++s) {
+    const float vr = xr[s], vi = xi[s], wr = w[s - 1].re, wi = w[s - 1].im;
+    if (!INV) { xr[s] = (wr * vr) - (wi * vi); xi[s] = (wi * vr) + (vi * wr); }
+    else { xr[s] = (vi * wi) + (vr * wr); xi[s] = (vi * wr) - (wi * vr); }
+  }
+  if (OUTER == 3) {
+    const float h = INV ? 0x1.bb67aep-1f : -0x1.bb67aep-1f;
+    const float ar = xr[0], br = xr[1], cr = xr[2], ai = xi[0], bi = xi[1], ci = xi[2];
+    xr[0] = (br + ar) + cr; xi[0] = ci + (bi + ai);
+    const float p = ar + (br * -0.5f), q = bi * h, r = cr * -0.5f, t = ci * h;
+    const float u = ai + (bi * -0.5f), v = br * h, x = cr * h, y = ci * -0.5f;
+    xr[1] = ((p - q) + r) + t; xi[1] = ((u + v) - x) + y;
+    xr[2] = ((p + q) + r) - t; xi[2] = ((u - v) + x) + y;
+  } else if (OUTER == 5) {
+    const float c1 = 0x1.3c6ef4p-2f, c2 = 0x1.9e377ap-1f, s1 = 0x1.e6f0e2p-1f, s2 = 0x1.2cf23p-1f;
+    const float ar = xr[0], br = xr[1], cr = xr[2], d_r = xr[3], er = xr[4];
+    const float ai = xi[0], bi = xi[1], ci = xi[2], d_i = xi[3], ei = xi[4];
+    const float dcR = d_r + cr, ebR = er + br, dcI = d_i + ci, ebI = ei + bi;
+    xr[0] = (dcR + ar) + ebR; xi[0] = (ai + dcI) + ebI;
+    const float p1r = ar + ((ebR * c1) - (dcR * c2)), p1i = ai + ((ebI * c1) - (dcI * c2));
+    const float p2r = ar + ((dcR * c1) - (ebR * c2)), p2i = ai + ((dcI * c1) - (ebI * c2));
+    float q1r, q1i, q2r, q2i;
+    if (!INV) {
+      const float a = d_i - ci, b = ei - bi, c = cr - d_r, d = br - er;
+      q1r = (a * -s2) - (b * s1); q1i = (c * -s2) - (d * s1);
+      q2r = (b * -s2) + (a * s1); q2i = (d * -s2) + (c * s1);
+    } else {
+      const float a = ei - bi, b = d_i - ci, c = br - er, d = cr - d_r;
+      q1r = (a * s1) + (b * s2); q1i = (c * s1) + (d * s2);
+      q2r = (a * s2) - (b * s1); q2i = (c * s2) - (d * s1);
+    }
+    xr[1] = p1r + q1r; xi[1] = p1i + q1i;
+    xr[2] = p2r + q2r; xi[2] = p2i + q2i;
+    xr[3] = p2r - q2r; xi[3] = p2i - q2i;
+    xr[4] = p1r - q1r; xi[4] = p1i - q1i;
+  }
+}
+
+// ---- radix-16 stage: radix-4 passes at sub-transform sizes 2^LGS and 2^(LGS+2), fused in registers (pow2_ffts_t)
+template <int LG, int OUTER, bool INV, int LGS, class LIn, class LOut>
+BS_HD void fast_r16(const cf *tw, const cf *src, cf *dst, int tid) {
+  constexpr int lgStrideA = LG - LGS - 2, lgStrideB = lgStrideA - 2, lgPer = LG - 4, nItems = OUTER << lgPer, strideB = 1 << lgStrideB;
+  static_assert(lgStrideB >= 0, "radix-16 stage does not fit");
+  for (int idx = tid; idx < nItems; idx += kFastNT) {
+    const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), iA = r >> lgStrideB, sB = r & (strideB - 1);
+    const int base = (iA << (lgStrideA + 2)) + sB;
+    float vr[4][4], vi[4][4];   // [a][j]
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const cf v = src[LIn::at(sub, base + (j << lgStrideA) + (a << lgStrideB))]; vr[a][j] = v.re; vi[a][j] = v.im; }
+    {
+      const cf tB = tw[iA << lgStrideA], tC = tw[(2 * iA) << lgStrideA], tD = tw[(3 * iA) << lgStrideA];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) bfly4<INV>(vr[a][0], vi[a][0], vr[a][1], vi[a][1], vr[a][2], vi[a][2], vr[a][3], vi[a][3], tB, tC, tD);
+    }
+    const int obase = (iA << lgStrideB) + sB;
+#pragma unroll
+    for (int jA = 0; jA < 4; ++jA) {
+      const int iB = iA + (jA << LGS);
+      const cf tB = tw[iB << lgStrideB], tC = tw[(2 * iB) << lgStrideB], tD = tw[(3 * iB) << lgStrideB];
+      bfly4<INV>(vr[0][jA], vi[0][jA], vr[1][jA], vi[1][jA], vr[2][jA], vi[2][jA], vr[3][jA], vi[3][jA], tB, tC, tD);
+#pragma unroll
+      for (int jB = 0; jB < 4; ++jB) {
+        cf o; o.re = vr[jB][jA]; o.im = vi[jB][jA];
+        dst[LOut::at(sub, obase + (jA << (LGS + lgStrideB)) + (jB << (LGS + 2 + lgStrideB)))] = o;
+      }
+    }
+  }
+}
+
+// ---- a single radix-4 pass at sub-transform size 2^LGS (not the last one)
+template <int LG, int OUTER, bool INV, int LGS, class LIn, class LOut>
+BS_HD void fast_r4(const cf *tw, const cf *src, cf *dst, int tid) {
+  constexpr int lgStride = LG - LGS - 2, stride = 1 << lgStride, lgPer = LG - 2, nItems = OUTER << lgPer;
+  for (int idx = tid; idx < nItems; idx += kFastNT) {
+    const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), i = r >> lgStride, s = r & (stride - 1);
+    const cf tB = tw[i << lgStride], tC = tw[(2 * i) << lgStride], tD = tw[(3 * i) << lgStride];
+    const int pa = ((4 * i) << lgStride) + s;
+    cf a = src[LIn::at(sub, pa)], b = src[LIn::at(sub, pa + stride)], c = src[LIn::at(sub, pa + 2 * stride)], d = src[LIn::at(sub, pa + 3 * stride)];
+    bfly4<INV>(a.re, a.im, b.re, b.im, c.re, c.im, d.re, d.im, tB, tC, tD);
+    const int po = (i << lgStride) + s, qs = 1 << (LGS + lgStride);
+    dst[LOut::at(sub, po)] = a; dst[LOut::at(sub, po + qs)] = b; dst[LOut::at(sub, po + 2 * qs)] = c; dst[LOut::at(sub, po + 3 * qs)] = d;
+  }
+}
+
+// ---- the last radix-4 pass (stride 1) of every sub-transform of one bin quadruple, then the outer stage of the four bins
+// it produces, all in registers.  emit(k, re, im) receives bin k = i + m * inner/4 + s * inner of the finished transform.
+template <int LG, int OUTER, bool INV, class LIn, class Emit>
+BS_HD void fast_last(const cf *tw, const cf *otw, const cf *src, int tid, Emit &&emit) {
+  constexpr int inner = 1 << LG, quarter = inner >> 2;
+  for (int i = tid; i < quarter; i += kFastNT) {
+    float vr[OUTER][4], vi[OUTER][4];
+    const cf tB = tw[i], tC = tw[2 * i], tD = tw[3 * i];
+#pragma unroll
+    for (int s = 0; s < OUTER; ++s) {
+      const f4 *p = (const f4 *)(src + LIn::at(s, 4 * i));   // four consecutive elements, 16-byte aligned (padding is 2 per 16)
+      const f4 lo = p[0], hi = p[1];
+      vr[s][0] = lo.x; vi[s][0] = lo.y; vr[s][1] = lo.z; vi[s][1] = lo.w; vr[s][2] = hi.x; vi[s][2] = hi.y; vr[s][3] = hi.z; vi[s][3] = hi.w;
+      bfly4<INV>(vr[s][0], vi[s][0], vr[s][1], vi[s][1], vr[s][2], vi[s][2], vr[s][3], vi[s][3], tB, tC, tD);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = i + m * quarter;
+      float xr[OUTER], xi[OUTER];
+      cf w[OUTER > 1 ? OUTER - 1 : 1];
+#pragma unroll
+      for (int s = 1; s < OUTER; ++s) w[s - 1] = otw[(size_t)k * (OUTER - 1) + (s - 1)];
+#pragma unroll
+      for (int s = 0; s < OUTER; ++s) { xr[s] = vr[s][m]; xi[s] = vi[s][m]; }
+      outer_point<INV, OUTER>(xr, xi, w);
+#pragma unroll
+      for (int s = 0; s < OUTER; ++s) emit(k + s * inner, xr[s], xi[s]);
+    }
+  }
+}
+
+// one packed, windowed, rotated input point of the forward transform (analyse_window's pack loop): j = packed pair index
+struct PackCtx { const float *xs; const f4 *tab; int lo, span, jA, jCA /* jC - jA */, off, cStart; };
+BS_HD cf fast_pack_point(const PackCtx &c, int j) {
+  const bool inA = j < c.jA, live = (unsigned)(j - c.jA) >= (unsigned)c.jCA;
+  const int i = 2 * j + (inA ? c.off : -c.cStart);
+  const f4 t = c.tab[j];
+  float x0 = 0.f, x1 = 0.f;
+  if (live && (unsigned)(i - c.lo) < (unsigned)c.span) x0 = c.xs[i];
+  if (live && (unsigned)(i + 1 - c.lo) < (unsigned)c.span) x1 = c.xs[i + 1];
+  const float t0 = live ? x0 * t.x : 0.f, t1 = live ? x1 * t.y : 0.f;
+  cf z; z.re = (t.z * t0) - (t.w * t1); z.im = (t.w * t0) + (t.z * t1);
+  return z;
+}
+
+template <int LG, int OUTER, class LOut>
+BS_HD void fast_fwd_pack(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *dst, int tid) {
+  using F = FastGeom<LG, OUTER>;
+  constexpr int M = F::M, inner = F::inner;
+  PackCtx c;
+  c.xs = x + w.start; c.tab = (const f4 *)T.packTab; c.lo = w.lo; c.span = w.hi - w.lo;
+  c.off = g.off; c.cStart = g.N - g.off; c.jA = (g.L - g.off) >> 1; c.jCA = (c.cStart >> 1) - c.jA;
+  if (!F::lg0) {
+#pragma unroll 4
+    for (int j = tid; j < M; j += kFastNT) {
+      const int q = j / OUTER, sub = j - q * OUTER;
+      dst[LOut::at(sub, q)] = fast_pack_point(c, j);
+    }
+  } else {   // the radix-2 pass on elements q and q + inner/2 of a sub-transform = packed pairs j and j + M/2
+#pragma unroll 2
+    for (int j = tid; j < M / 2; j += kFastNT) {
+      const int q = j / OUTER, sub = j - q * OUTER;
+      const cf a = fast_pack_point(c, j), b = fast_pack_point(c, j + M / 2);
+      cf lo, hi; lo.re = b.re + a.re; lo.im = b.im + a.im; hi.re = a.re - b.re; hi.im = a.im - b.im;
+      dst[LOut::at(sub, q)] = lo; dst[LOut::at(sub, q + inner / 2)] = hi;
+    }
+  }
+}
+
+// untangle of the forward transform: bins i and M-1-i from the complex transform's outputs (analyse_window's last loop)
+template <int LG, int OUTER>
+BS_HD void fast_fwd_untangle(const DevTables &T, const cf *Y /* natural order */, cf *X, bool rotate, int tid) {
+  constexpr int M = FastGeom<LG, OUTER>::M, half = M >> 1;
+#pragma unroll 2
+  for (int p = tid; p < half; p += kFastNT) {
+    const int i = (p < half - 1) ? p : half;   // the reference's loop leaves pair (half, half-1) as written by its last iteration
+    const int j = M - 1 - i;
+    const cf u = T.untangle[i], a = Y[i], b = Y[j];
+    const float sI = (b.im + a.im) * 0.5f, dR = (a.re - b.re) * 0.5f;
+    const float pp = (sI * u.re) + (dR * u.im), dI = (a.im - b.im) * 0.5f;
+    const float qq = (dR * u.re) - (sI * u.im), sR = (b.re + a.re) * 0.5f;
+    cf xi_, xj_;
+    xi_.im = pp + dI; xi_.re = qq + sR; xj_.im = pp - dI; xj_.re = sR - qq;
+    if (rotate) { xi_ = rot_prev(xi_, T.specRot[i]); xj_ = rot_prev(xj_, T.specRot[j]); }
+    X[i] = xi_; X[j] = xj_;
+  }
+}
+
+// untangle^-1 of the inverse transform (synth_frame's first loop): spectrum pairs -> the complex transform's inputs
+BS_HD void fast_inv_pair(const cf un, const cf xi_, const cf xj_, cf &oi, cf &oj) {
+  const float sI = xj_.im + xi_.im, dR = xi_.re - xj_.re;
+  const float p = (sI * un.im) + (dR * un.re), sR = xj_.re + xi_.re;
+  const float q = (sI * un.re) - (dR * un.im), dI = xi_.im - xj_.im;
+  oi.re = p + sR; oi.im = q + dI; oj.re = sR - p; oj.im = q - dI;
+}
+template <int LG, int OUTER, class LOut>
+BS_HD void fast_inv_untangle(const DevTables &T, const cf *X, cf *dst, int tid) {
+  using F = FastGeom<LG, OUTER>;
+  constexpr int M = F::M, half = M >> 1, inner = F::inner;
+  auto put = [&](int k, cf v) { const int q = k / OUTER, sub = k - q * OUTER; dst[LOut::at(sub, q)] = v; };
+  if (!F::lg0) {
+#pragma unroll 2
+    for (int p = tid; p < half; p += kFastNT) {
+      const int i = (p < half - 1) ? p : half, j = M - 1 - i;
+      cf oi, oj;
+      fast_inv_pair(T.untangle[i], X[i], X[j], oi, oj);
+      put(i, oi); put(j, oj);
+    }
+  } else {
+    // with the radix-2 pass: elements k and k + M/2 meet, so a work item takes the pairs (i, M-1-i) and (M/2-1-i, M/2+i)
+    constexpr int quarter = M >> 2;
+    for (int i = tid; i < quarter; i += kFastNT) {
+      cf a0, a1, b0, b1;   // a0 = element i, a1 = element M-1-i, b0 = element M/2+i, b1 = element M/2-1-i
+      fast_inv_pair(T.untangle[i], X[i], X[M - 1 - i], a0, a1);
+      if (i == 0) fast_inv_pair(T.untangle[half], X[half], X[half - 1], b0, b1);          // the pair the reference's loop writes last
+      else fast_inv_pair(T.untangle[half - 1 - i], X[half - 1 - i], X[half + i], b1, b0);
+      auto r2 = [&](int k, cf a, cf b) {   // a at k, b at k + M/2
+        const int q = k / OUTER, sub = k - q * OUTER;
+        cf lo, hi; lo.re = b.re + a.re; lo.im = b.im + a.im; hi.re = a.re - b.re; hi.im = a.im - b.im;
+        dst[LOut::at(sub, q)] = lo; dst[LOut::at(sub, q + inner / 2)] = hi;
+      };
+      r2(i, a0, b0);
+      r2(half - 1 - i, b1, a1);
+    }
+  }
+  (void)put;
+}
+
+// ---- stage sequencing: stage K reads buffer (K & 1), writes the other one
+template <int LG, int OUTER, bool INV, int K>
+BS_HD void fast_mid_stage(const cf *tw, cf *buf0, cf *buf1, int tid) {
+  using S = StageOf<LG, OUTER, K>;
+  using Nx = StageOf<LG, OUTER, K + 1>;
+  const cf *src = (K & 1) ? buf1 : buf0; cf *dst = (K & 1) ? buf0 : buf1;
+  if constexpr (S::isR16) fast_r16<LG, OUTER, INV, S::lgSize, typename S::In, typename Nx::In>(tw, src, dst, tid);
+  else fast_r4<LG, OUTER, INV, S::lgSize, typename S::In, typename Nx::In>(tw, src, dst, tid);
+}
+
+// Runs the stages between the pack and the last one; SYNC() between them.  Returns nothing: after it the input of the last
+// stage is in buffer ((nStages - 1) & 1).
+#ifdef BS_HOSTEMU
+#define BS_FAST_FORALL(stmt) for (int tid = 0; tid < kFastNT; ++tid) { stmt; }
+#else
+#define BS_FAST_FORALL(stmt) { const int tid = threadIdx.x; stmt; } __syncthreads();
+#endif
+template <int LG, int OUTER, bool INV>
+BS_HD void fast_mid_stages(const cf *tw, cf *buf0, cf *buf1) {
+  using F = FastGeom<LG, OUTER>;
+  if constexpr (F::nStages > 1) { BS_FAST_FORALL((fast_mid_stage<LG, OUTER, INV, 0>(tw, buf0, buf1, tid))) }
+  if constexpr (F::nStages > 2) { BS_FAST_FORALL((fast_mid_stage<LG, OUTER, INV, 1>(tw, buf0, buf1, tid))) }
+  if constexpr (F::nStages > 3) { BS_FAST_FORALL((fast_mid_stage<LG, OUTER, INV, 2>(tw, buf0, buf1, tid))) }
+  static_assert(F::nStages <= 4, "add a stage");
+}
+
+// whole forward transform of one window of one channel; sm = 2 * fast_buf_elems cf (16-byte aligned)
+template <int LG, int OUTER>
+BS_HD void fast_analyse(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, cf *sm, bool rotate) {
+  using F = FastGeom<LG, OUTER>;
+  constexpr int NB = FastBuf<LG, OUTER>::elems;
+  cf *buf0 = sm, *buf1 = sm + NB;
+  using L0 = typename StageOf<LG, OUTER, 0>::In;
+  BS_FAST_FORALL((fast_fwd_pack<LG, OUTER, L0>(g, T, x, w, buf0, tid)))
+  fast_mid_stages<LG, OUTER, false>(T.tw, buf0, buf1);
+  constexpr int KL = F::nStages - 1;
+  using LL = typename StageOf<LG, OUTER, KL>::In;
+  cf *src = (KL & 1) ? buf1 : buf0, *Y = (KL & 1) ? buf0 : buf1;
+  BS_FAST_FORALL((fast_last<LG, OUTER, false, LL>(T.tw, T.otw, src, tid, [&](int k, float re, float im) { cf v; v.re = re; v.im = im; Y[k] = v; })))
+  BS_FAST_FORALL((fast_fwd_untangle<LG, OUTER>(T, Y, X, rotate, tid)))
+}
+
+// whole inverse transform of one channel's output spectrum, synthesis window applied (synth_frame)
+template <int LG, int OUTER>
+BS_HD void fast_synth(const DevGeom &g, const DevTables &T, const cf *X, float *frame, cf *sm) {
+  using F = FastGeom<LG, OUTER>;
+  constexpr int NB = FastBuf<LG, OUTER>::elems;
+  cf *buf0 = sm, *buf1 = sm + NB;
+  using L0 = typename StageOf<LG, OUTER, 0>::In;
+  BS_FAST_FORALL((fast_inv_untangle<LG, OUTER, L0>(T, X, buf0, tid)))
+  fast_mid_stages<LG, OUTER, true>(T.tw, buf0, buf1);
+  constexpr int KL = F::nStages - 1;
+  using LL = typename StageOf<LG, OUTER, KL>::In;
+  const cf *src = (KL & 1) ? buf1 : buf0;
+  const f4 *tab = (const f4 *)T.packTab;
+  const int jA = (g.L - g.off) >> 1, jC = (g.N - g.off) >> 1, off = g.off, cStart = g.N - g.off;
+  // the last pass hands every finished time-domain pair straight to the half-bin rotation and the synthesis window; the
+  // table's window coefficients carry the sign of the first half (ring -= t*w there = adding -(t*w) = t*(-w))
+  BS_FAST_FORALL((fast_last<LG, OUTER, true, LL>(T.tw, T.otw, src, tid, [&](int j, float re, float im) {
+    const bool inA = j < jA;
+    if (!inA && j < jC) return;
+    const f4 t = tab[j];
+    const float t1 = (t.z * im) - (t.w * re), t0 = (t.w * im) + (t.z * re);
+    f2 o; o.x = t0 * t.x; o.y = t1 * t.y;
+    *(f2 *)(frame + (inA ? 2 * j + off : 2 * j - cStart)) = o;
+  })))
+}
+
+// geometries with a specialised path (every other one takes analyse_window / synth_frame)
+BS_HHD bool fast_geometry(int inner, int outer) {
+  return (inner == 1024 && outer == 3) || (inner == 512 && outer == 5) || (inner == 1024 && outer == 5) || (inner == 2048 && outer == 3) ||
+         (inner == 512 && outer == 1);
+}
+// ... provided the window halves fall on pair boundaries (they do for every even block size)
+BS_HHD bool fast_ok(const DevGeom &g) {
+  return g.packTabOk && fast_geometry(g.inner, g.outer) && (((g.L - g.off) | (g.N - g.off) | g.off) & 1) == 0;
+}
+
+}  // namespace bs

@@ -42,11 +42,13 @@ struct DevGeom {
   int wpStartLen;
   int incremental;  // blocks arrive one at a time (compat shim): always carry the input spectrum forward
   unsigned divMagic; int divShift;   // j / outer == (j * divMagic) >> divShift for every j < M (checked at create time)
+  int packTabOk;                     // DevTables::packTab exists (window halves on pair boundaries)
 };
 enum : int { kSynthEmit = 1, kSynthAdd = 2, kSynthFrames = 4 };   // kSynthFrames: windowed frames only, no overlap-add (the compat shim keeps the reference's own output ring)
 struct DevTables {
   const float *win; const cf *tw; const float *otr, *oti; const cf *untangle, *rot, *specRot;
   const float *wpStart, *wpSteady;
+  const float *packTab; const cf *otw;   // fft_fast.cuh
 };
 // per-stream device record
 struct StreamDev {

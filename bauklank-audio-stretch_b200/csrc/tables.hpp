@@ -93,6 +93,9 @@ struct Tables {
   std::vector<cf> untangle;      // [N/4+1]
   std::vector<cf> rot;           // [M] half-bin rotations
   std::vector<cf> specRot;       // [B] running rotation applied to output/prevInput on a new spectrum (S1)
+  std::vector<float> packTab;    // [M][4] per packed sample pair: signed window coefficients of its two samples, half-bin rotation
+                                 //        (empty unless the window halves fall on pair boundaries) -- fft_fast.cuh
+  std::vector<cf> otw;           // [inner][outer-1] the outer twiddles again, the ones of a bin side by side
   std::vector<float> wpStart;    // window-product denominators for the first wpStart.size() output samples
   std::vector<float> wpSteady;   // [H] periodic part after that
   std::vector<float> winProd;    // [L] (w*N)*w
@@ -147,6 +150,26 @@ inline void make_fft_tables(const Geometry &g, Tables &T) {
   T.rot.resize(M);
   for (int i = 0; i < M; ++i)
     T.rot[i] = polar1(((N & 2) && i == M - 1) ? (float)(((double)i * -kPi2) / (double)N) : (float)(((double)i * -kPi2) * rN));
+  T.otw.assign(no > 0 ? no : 1, cf{0.f, 0.f});
+  for (int i = 0; i < inner && outer >= 2; ++i)
+    for (int s = 1; s < outer; ++s) T.otw[(size_t)i * (outer - 1) + (s - 1)] = cf{T.otr[i + inner * (s - 1)], T.oti[i + inner * (s - 1)]};
+}
+// The window and the half-bin rotation as the specialised kernels consume them: packed pair j holds window samples i, i+1
+// with i = 2j + off (second half of the window, j < jA) or 2j - cStart (first half, sign flipped: the half-bin shift), and
+// is multiplied by rot[j].  x * (-w) == -(x * w) exactly, so the sign lives in the table.  (W#35 / W#48 9986-10932)
+inline void make_pack_table(const Geometry &g, Tables &T) {
+  const int L = g.L, N = g.N, M = g.M, off = L >> 1, nA = L - off, cStart = N - off;
+  T.packTab.clear();
+  if (((nA | cStart | off) & 1) != 0) return;
+  T.packTab.assign((size_t)4 * M, 0.f);
+  for (int j = 0; j < M; ++j) {
+    const int n = 2 * j;
+    const bool inA = n < nA, inC = n >= cStart;
+    float w0 = 0.f, w1 = 0.f;
+    if (inA) { w0 = T.win[n + off]; w1 = T.win[n + off + 1]; }
+    else if (inC) { w0 = -T.win[n - cStart]; w1 = -T.win[n - cStart + 1]; }
+    T.packTab[4 * j] = w0; T.packTab[4 * j + 1] = w1; T.packTab[4 * j + 2] = T.rot[j].re; T.packTab[4 * j + 3] = T.rot[j].im;
+  }
 }
 
 // S1: rot = polar(2pi*H*0.5/N), rotStep = polar(2pi*H*(1.5/N - 0.5/N)); running f32 product over bins (W#48 8193-8229)
@@ -200,6 +223,7 @@ inline void make_window_products(const Geometry &g, Tables &T) {
 inline void make_tables(const Geometry &g, Tables &T) {
   make_window(g, T.win);
   make_fft_tables(g, T);
+  make_pack_table(g, T);
   make_spec_rot(g, T.specRot);
   make_window_products(g, T);
 }

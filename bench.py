@@ -244,6 +244,8 @@ def main_gpu(args):
         outs.append(outs_all[off:off + 2 * n].view(2, n)); off += 2 * n
     drives = [bs.KioskDrive(n_out[i], [bs.segment(rate=float(rates[i]), semitones=float(sts[i]), tonality_hz=8000.0)]) for i in range(S)]
     eng = bs.BatchStretch(2, SR, preset=args.preset)
+    if args.no_fast_fft:
+        eng.set_fast_fft(False)
     t0 = time.perf_counter()
     eng.plan(clips, drives, outputs=outs)
     plan_s = time.perf_counter() - t0
@@ -382,6 +384,7 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=32)
     ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast-fft", action="store_true", help="A/B: the run-time-geometry STFT kernels instead of the specialised ones")
     ap.add_argument("--preset", default="default", choices=["default", "cheaper"], help="engine preset (the headline number uses default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -135,6 +135,11 @@ void bsb_set_profiling(bsb_engine *e, int on);
  * beside the analysis / map / term kernels of chunk i+1; off = every kernel in order on the caller's stream (used to
  * time kernels in isolation).  Results are identical either way. */
 void bsb_set_overlap(bsb_engine *e, int on);
+/* STFT kernels specialised for the preset geometries (default on where one exists: 48 kHz presetDefault / presetCheaper,
+ * the kiosk's blockMs 200, 96 kHz presetDefault, block 960); off = the run-time-geometry kernels every other
+ * configuration uses.  Results are identical either way (same butterflies, same order). */
+void bsb_set_fast_fft(bsb_engine *e, int on);
+int bsb_fast_fft_active(const bsb_engine *e);   /* 1 = this engine's runs use the specialised STFT kernels */
 int bsb_kernel_count(const bsb_engine *e);
 int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units);
 

@@ -316,3 +316,26 @@ def test_other_channel_counts_and_geometries_against_live_oracle(channels, block
     same, err, snr = cases.compare(outs[0].cpu().numpy(), ref)
     assert err <= MAX_ABS_ERR and snr >= MIN_SNR_DB and same, (same, err, snr)
     eng.close()
+
+
+@pytest.mark.parametrize("channels,block,interval,split,sr", [
+    (2, 5760, 1440, 0, 48000), (2, 4800, 1920, 1, 48000), (2, 9600, 2400, 1, 48000), (1, 11520, 2880, 0, 96000), (3, 960, 240, 1, 96000)])
+def test_specialised_stft_kernels_on_gpu(channels, block, interval, split, sr, bs):
+    """fft_fast.cuh on the device against the run-time-geometry kernels and the CPU oracle (see the CPU twin of this test)."""
+    import torch
+    rng = np.random.default_rng(block)
+    n_in = int(0.5 * sr)
+    clip = (0.2 * rng.standard_normal((channels, n_in))).astype(np.float32)
+    case = dict(drive="kiosk", sr=sr, n_out=int(0.35 * sr), block=(block, interval, split), seed=3,
+                segments=[cases.seg(rate=0.83, input=0.0131, semitones=3.0, formant_semitones=-2.0, formant_compensation=True)])
+    e = refdrive.PortEngine(seed=3)
+    ref = cases.run_case(e, case, clip=clip); e.close()
+    outs = []
+    for fast in (True, False):
+        eng = bs.BatchStretch(channels, sr, block_samples=block, interval_samples=interval, split_computation=bool(split))
+        eng.set_fast_fft(fast)
+        assert eng.fast_fft_active() == fast
+        o = eng.plan([torch.from_numpy(clip).cuda()], [cases.batch_drive(bs, case, n_in)], chunk_blocks=9)
+        eng.run(); torch.cuda.synchronize()
+        outs.append(o[0].cpu().numpy()); eng.close()
+    assert cases.compare(outs[0], outs[1])[0] and cases.compare(outs[0], ref)[0]

@@ -196,3 +196,27 @@ def test_shim_flush_at_many_positions_of_the_block_cycle(emu):
             if not cases.compare(ya, yb)[0]:
                 bad.append((n_in, n_out, calls))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("channels,block,interval,split,sr", [
+    (2, 5760, 1440, 0, 48000), (2, 4800, 1920, 1, 48000), (2, 9600, 2400, 1, 48000), (1, 11520, 2880, 0, 96000), (3, 960, 240, 1, 96000)])
+def test_specialised_stft_kernels_equal_the_generic_ones_and_the_oracle(channels, block, interval, split, sr, emu):
+    """fft_fast.cuh (the preset geometries: inner x outer = 1024x3, 512x5, 1024x5, 2048x3, 512x1) against the run-time-geometry
+    path of kernels.cuh and against the CPU oracle, through the serial emulation of the same source; a window that starts
+    before the clip, the short pre-roll of the non-split presets and an odd clip offset are all in there."""
+    rng = np.random.default_rng(block)
+    n_in = int(0.5 * sr)
+    clip = (0.2 * rng.standard_normal((channels, n_in))).astype(np.float32)
+    case = dict(drive="kiosk", sr=sr, n_out=int(0.35 * sr), block=(block, interval, split), seed=3,
+                segments=[cases.seg(rate=0.83, input=0.0131, semitones=3.0, formant_semitones=-2.0, formant_compensation=True)])
+    e = refdrive.PortEngine(seed=3)
+    ref = cases.run_case(e, case, clip=clip); e.close()
+    outs = []
+    for fast in (True, False):
+        eng = bs.BatchStretch(channels, sr, block_samples=block, interval_samples=interval, split_computation=bool(split), lib=emu)
+        eng.set_fast_fft(fast)
+        assert eng.fast_fft_active() == fast
+        o = eng.plan([np.ascontiguousarray(clip)], [cases.batch_drive(bs, case, n_in)], chunk_blocks=9)
+        eng.run()
+        outs.append(np.array(o[0])); eng.close()
+    assert cases.compare(outs[0], outs[1])[0] and cases.compare(outs[0], ref)[0]
