@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T
 
 // the same two kernels for the preset geometries (fft_fast.cuh): grid (slot, stream, {cur,prev} x channel) -- no index division
 template <int LG, int OUTER>
-__global__ void __launch_bounds__(kFastNT, 3) analysis_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+__global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) analysis_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
                                                                   const Window *windows, long long slot0, int nSlots, cf *specIn) {
   extern __shared__ __align__(16) float sm[];
   const int slot = blockIdx.x, s = blockIdx.y, which = blockIdx.z & 1, c = blockIdx.z >> 1;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kFastNT, 3) analysis_fast_kernel(DevGeom g, De
   fast_analyse<LG, OUTER>(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, (cf *)sm, which == 1);
 }
 template <int LG, int OUTER>
-__global__ void __launch_bounds__(kFastNT, 3) isynth_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
+__global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) isynth_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
                                                                 const cf *specOut, StateDev st) {
   extern __shared__ __align__(16) float sm[];
   const int slot = blockIdx.x, s = blockIdx.y, c = blockIdx.z;

@@ -35,10 +35,13 @@ struct FastGeom {
 };
 
 // buffer layout: element e of sub-transform `sub` lives at sub * PITCH + e + (e >> SHIFT) * ADD   (ADD == 0: no padding)
+// A stage addresses e = e0 + d with a thread-dependent e0 and compile-time offsets d that never carry into each other
+// below bit SHIFT (see the stages), so the padding separates: at(sub, e0) once per work item, plus the constant pad(d).
 template <int SHIFT, int ADD, int PITCH>
 struct Lay {
   static constexpr int pitch = PITCH;
   BS_HHD static int at(int sub, int e) { return sub * PITCH + e + (ADD ? ((e >> SHIFT) * ADD) : 0); }
+  BS_HHD static constexpr int pad(int d) { return d + (ADD ? ((d >> SHIFT) * ADD) : 0); }
 };
 constexpr int lay_padded(int n, int shift, int add) { return n + (add ? ((n >> shift) * add) : 0); }
 constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
@@ -55,7 +58,12 @@ template <int LG, int OUTER, int K> struct StageOf {   // stage K (0-based) afte
   static constexpr int P = isR16 ? 16 * G : 4 * G;
   static constexpr int shift = isLast ? 4 : ilog2c(P);
   static constexpr int add = isLast ? 2 : (G >= 16 ? 0 : G);
-  static constexpr int pitch = (lay_padded(F::inner, shift, add) + 1) & ~1;
+  // The pack stage (and untangle^-1) stores element (j % OUTER, j / OUTER) from lane j: 16 consecutive j are conflict-free
+  // exactly when the sub-transform pitch is 11 (OUTER 3) or 13 (OUTER 5) modulo 16 elements -- found by enumeration.
+  static constexpr int packMod = OUTER == 3 ? 11 : (OUTER == 5 ? 13 : 0);
+  static constexpr int need = lay_padded(F::inner, shift, add);
+  static constexpr int pitch = (K == 0 && packMod) ? need + ((packMod - need % 16 + 16) % 16) : ((need + 1) & ~1);
+  static_assert(!(K == 0 && isLast), "a single-stage transform would need an even pitch here");
   using In = Lay<shift, add, pitch>;
 };
 template <int LG, int OUTER> struct NaturalLay { using L = Lay<0, 0, (1 << LG)>; };   // spectrum order k = i + s * inner
@@ -69,6 +77,11 @@ template <int LG, int OUTER, int K = 0> struct FastSmem {
 template <int LG, int OUTER> struct FastSmem<LG, OUTER, 8> { static constexpr int value = (1 << LG) * OUTER; };
 template <int LG, int OUTER> struct FastBuf { static constexpr int elems = (FastSmem<LG, OUTER>::value + 1) & ~1; };
 template <int LG, int OUTER> constexpr size_t fast_smem_bytes() { return 2 * (size_t)FastBuf<LG, OUTER>::elems * sizeof(cf); }
+// CTAs per SM the kernels are compiled for: three where shared memory allows (80 registers), else what fits of 227 KB
+template <int LG, int OUTER> struct FastOcc {
+  static constexpr int bySmem = (int)(232448 / (2 * (size_t)FastBuf<LG, OUTER>::elems * sizeof(cf) + 1024));
+  static constexpr int ctas = bySmem >= 3 ? 3 : (bySmem < 1 ? 1 : bySmem);
+};
 
 // ---- the outer stage of one bin: twiddles on sub-transforms 1.., then the DFT across them (outer_stage_t, kernels.cuh)
 template <bool INV, int OUTER>
@@ -122,25 +135,29 @@ BS_HD void fast_r16(const cf *tw, const cf *src, cf *dst, int tid) {
     const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), iA = r >> lgStrideB, sB = r & (strideB - 1);
     const int base = (iA << (lgStrideA + 2)) + sB;
     float vr[4][4], vi[4][4];   // [a][j]
+    const cf *ps = src + LIn::at(sub, base);
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { const cf v = src[LIn::at(sub, base + (j << lgStrideA) + (a << lgStrideB))]; vr[a][j] = v.re; vi[a][j] = v.im; }
+      for (int j = 0; j < 4; ++j) { const cf v = ps[LIn::pad((j << lgStrideA) + (a << lgStrideB))]; vr[a][j] = v.re; vi[a][j] = v.im; }
     {
-      const cf tB = tw[iA << lgStrideA], tC = tw[(2 * iA) << lgStrideA], tD = tw[(3 * iA) << lgStrideA];
+      const cf *pt = tw + (iA << lgStrideA);
+      const cf tB = pt[0], tC = pt[iA << lgStrideA], tD = pt[(2 * iA) << lgStrideA];
 #pragma unroll
       for (int a = 0; a < 4; ++a) bfly4<INV>(vr[a][0], vi[a][0], vr[a][1], vi[a][1], vr[a][2], vi[a][2], vr[a][3], vi[a][3], tB, tC, tD);
     }
-    const int obase = (iA << lgStrideB) + sB;
+    cf *pd = dst + LOut::at(sub, (iA << lgStrideB) + sB);   // = element r of the sub-transform: consecutive lanes, consecutive elements
+    const cf *pt = tw + (iA << lgStrideB);
 #pragma unroll
     for (int jA = 0; jA < 4; ++jA) {
-      const int iB = iA + (jA << LGS);
-      const cf tB = tw[iB << lgStrideB], tC = tw[(2 * iB) << lgStrideB], tD = tw[(3 * iB) << lgStrideB];
+      // iB = iA + (jA << LGS): tw[iB << lgStrideB], tw[2 iB << lgStrideB], tw[3 iB << lgStrideB] = constant offsets from tw[k iA << lgStrideB]
+      constexpr int one = 1 << (LGS + lgStrideB);
+      const cf tB = pt[jA * one], tC = pt[(iA << lgStrideB) + 2 * jA * one], tD = pt[((2 * iA) << lgStrideB) + 3 * jA * one];
       bfly4<INV>(vr[0][jA], vi[0][jA], vr[1][jA], vi[1][jA], vr[2][jA], vi[2][jA], vr[3][jA], vi[3][jA], tB, tC, tD);
 #pragma unroll
       for (int jB = 0; jB < 4; ++jB) {
         cf o; o.re = vr[jB][jA]; o.im = vi[jB][jA];
-        dst[LOut::at(sub, obase + (jA << (LGS + lgStrideB)) + (jB << (LGS + 2 + lgStrideB)))] = o;
+        pd[LOut::pad((jA << (LGS + lgStrideB)) + (jB << (LGS + 2 + lgStrideB)))] = o;
       }
     }
   }
@@ -153,11 +170,12 @@ BS_HD void fast_r4(const cf *tw, const cf *src, cf *dst, int tid) {
   for (int idx = tid; idx < nItems; idx += kFastNT) {
     const int sub = idx >> lgPer, r = idx & ((1 << lgPer) - 1), i = r >> lgStride, s = r & (stride - 1);
     const cf tB = tw[i << lgStride], tC = tw[(2 * i) << lgStride], tD = tw[(3 * i) << lgStride];
-    const int pa = ((4 * i) << lgStride) + s;
-    cf a = src[LIn::at(sub, pa)], b = src[LIn::at(sub, pa + stride)], c = src[LIn::at(sub, pa + 2 * stride)], d = src[LIn::at(sub, pa + 3 * stride)];
+    const cf *ps = src + LIn::at(sub, ((4 * i) << lgStride) + s);
+    cf a = ps[0], b = ps[LIn::pad(stride)], c = ps[LIn::pad(2 * stride)], d = ps[LIn::pad(3 * stride)];
     bfly4<INV>(a.re, a.im, b.re, b.im, c.re, c.im, d.re, d.im, tB, tC, tD);
-    const int po = (i << lgStride) + s, qs = 1 << (LGS + lgStride);
-    dst[LOut::at(sub, po)] = a; dst[LOut::at(sub, po + qs)] = b; dst[LOut::at(sub, po + 2 * qs)] = c; dst[LOut::at(sub, po + 3 * qs)] = d;
+    constexpr int qs = 1 << (LGS + lgStride);
+    cf *pd = dst + LOut::at(sub, (i << lgStride) + s);
+    pd[0] = a; pd[LOut::pad(qs)] = b; pd[LOut::pad(2 * qs)] = c; pd[LOut::pad(3 * qs)] = d;
   }
 }
 
@@ -193,15 +211,32 @@ BS_HD void fast_last(const cf *tw, const cf *otw, const cf *src, int tid, Emit &
 }
 
 // one packed, windowed, rotated input point of the forward transform (analyse_window's pack loop): j = packed pair index
-struct PackCtx { const float *xs; const f4 *tab; int lo, span, jA, jCA /* jC - jA */, off, cStart; };
+struct PackCtx { const float *xs; const f4 *tab; int lo, hi, span, jA, jC, off, cStart; bool aligned; };
 BS_HD cf fast_pack_point(const PackCtx &c, int j) {
-  const bool inA = j < c.jA, live = (unsigned)(j - c.jA) >= (unsigned)c.jCA;
-  const int i = 2 * j + (inA ? c.off : -c.cStart);
   const f4 t = c.tab[j];
-  float x0 = 0.f, x1 = 0.f;
-  if (live && (unsigned)(i - c.lo) < (unsigned)c.span) x0 = c.xs[i];
-  if (live && (unsigned)(i + 1 - c.lo) < (unsigned)c.span) x1 = c.xs[i + 1];
-  const float t0 = live ? x0 * t.x : 0.f, t1 = live ? x1 * t.y : 0.f;
+  float t0, t1;
+  // Warp-uniform shortcut: the 32 pairs this warp packs in one trip (j is consecutive over its lanes) lie in one half of the
+  // window and inside the part of it the clip covers -- no per-sample predicates.  (The serial emulation runs the general
+  // path only; it computes the same values.)
+#ifndef BS_HOSTEMU
+  const int jw = j & ~31;
+  const bool allA = jw + 31 < c.jA, allC = jw >= c.jC;
+  const int ib = allA ? c.off : -c.cStart, iw = 2 * jw + ib;
+  if ((allA || allC) && iw >= c.lo && iw + 64 <= c.hi) {
+    const float *px = c.xs + (2 * j + ib);
+    float x0, x1;
+    if (c.aligned) { const f2 v = *(const f2 *)px; x0 = v.x; x1 = v.y; } else { x0 = px[0]; x1 = px[1]; }
+    t0 = x0 * t.x; t1 = x1 * t.y;
+  } else
+#endif
+  {
+    const bool inA = j < c.jA, live = inA || j >= c.jC;
+    const int i = 2 * j + (inA ? c.off : -c.cStart);
+    float x0 = 0.f, x1 = 0.f;
+    if (live && (unsigned)(i - c.lo) < (unsigned)c.span) x0 = c.xs[i];
+    if (live && (unsigned)(i + 1 - c.lo) < (unsigned)c.span) x1 = c.xs[i + 1];
+    t0 = live ? x0 * t.x : 0.f; t1 = live ? x1 * t.y : 0.f;
+  }
   cf z; z.re = (t.z * t0) - (t.w * t1); z.im = (t.w * t0) + (t.z * t1);
   return z;
 }
@@ -211,8 +246,9 @@ BS_HD void fast_fwd_pack(const DevGeom &g, const DevTables &T, const float *x, W
   using F = FastGeom<LG, OUTER>;
   constexpr int M = F::M, inner = F::inner;
   PackCtx c;
-  c.xs = x + w.start; c.tab = (const f4 *)T.packTab; c.lo = w.lo; c.span = w.hi - w.lo;
-  c.off = g.off; c.cStart = g.N - g.off; c.jA = (g.L - g.off) >> 1; c.jCA = (c.cStart >> 1) - c.jA;
+  c.xs = x + w.start; c.tab = (const f4 *)T.packTab; c.lo = w.lo; c.hi = w.hi; c.span = w.hi - w.lo;
+  c.off = g.off; c.cStart = g.N - g.off; c.jA = (g.L - g.off) >> 1; c.jC = c.cStart >> 1;
+  c.aligned = (((size_t)c.xs) & 7) == 0;   // sample pairs start at even window positions: 8-byte loads if the window start allows
   if (!F::lg0) {
 #pragma unroll 4
     for (int j = tid; j < M; j += kFastNT) {
