@@ -5,9 +5,9 @@ Import name: ``bauklank_audio_stretch_b200`` (the repo-root shim maps it onto th
 hyphen as the project layout asks).
 """
 from ._capi import load_library, Segment, EXPORTS  # noqa: F401
-from .batch import BatchStretch, KioskDrive, StreamingDrive, TableDrive, segment  # noqa: F401
+from .batch import BatchStretch, KioskDrive, StreamingDrive, TableDrive, TraceDrive, segment, trace_events  # noqa: F401
 from .worklet import WorkletTimeline, ControllerMapper  # noqa: F401
 from .engine import StretchEngine  # noqa: F401
 from . import shard  # noqa: F401
 
-__all__ = ["StretchEngine", "BatchStretch", "KioskDrive", "StreamingDrive", "TableDrive", "WorkletTimeline", "ControllerMapper", "segment", "load_library", "Segment", "EXPORTS", "shard"]
+__all__ = ["StretchEngine", "BatchStretch", "KioskDrive", "StreamingDrive", "TableDrive", "TraceDrive", "trace_events", "WorkletTimeline", "ControllerMapper", "segment", "load_library", "Segment", "EXPORTS", "shard"]

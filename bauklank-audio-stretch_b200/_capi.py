@@ -28,6 +28,14 @@ class Quantum(C.Structure):
                 ("active", C.c_int32), ("transpose_factor", C.c_float), ("formant_factor", C.c_float)]
 
 
+class TraceEvent(C.Structure):
+    """``bsb_trace_event``: one ``schedule()`` call of a control trace, applied before render quantum ``quantum``."""
+    _fields_ = [("quantum", C.c_longlong), ("output_time", C.c_double), ("input", C.c_double), ("rate", C.c_double),
+                ("semitones", C.c_double), ("loop_start", C.c_double), ("loop_end", C.c_double), ("tonality_hz", C.c_double),
+                ("formant_semitones", C.c_double), ("formant_base_hz", C.c_double), ("active", C.c_int32),
+                ("formant_compensation", C.c_int32), ("transpose_factor", C.c_double), ("formant_factor", C.c_double)]
+
+
 _BATCH_SIG = {
     "bsb_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "bsb_create_preset": (C.c_void_p, [C.c_int, C.c_double, C.c_int]),
@@ -44,6 +52,8 @@ _BATCH_SIG = {
                                 C.POINTER(Segment), C.c_int, C.c_uint32]),
     "bsb_add_kiosk_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
                                       C.POINTER(Quantum), C.c_longlong, C.c_uint32]),
+    "bsb_add_kiosk_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
+                                      C.POINTER(TraceEvent), C.c_longlong, C.c_uint32]),
     "bsb_query_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "bsb_add_streaming": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int,
                                     C.c_longlong, C.POINTER(Segment), C.c_int, C.c_uint32]),
@@ -64,6 +74,7 @@ _BATCH_SIG = {
     "bsb_set_fast_fft": (None, [C.c_void_p, C.c_int]),
     "bsb_fast_fft_active": (C.c_int, [C.c_void_p]),
     "bsb_kernel_count": (C.c_int, [C.c_void_p]),
+    "bsb_kernel_launches": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "bsb_kernel_stat": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                   C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
 }

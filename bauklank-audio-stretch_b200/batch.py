@@ -60,6 +60,41 @@ class TableDrive:
     seed: int = 1
 
 
+@dataclass
+class TraceDrive:
+    """Buffer playback under a control trace: ``events`` = ctypes array of ``bsb_trace_event`` (``trace_events``), each a
+    ``schedule()`` call made before a render quantum; the time map is kept inside the library exactly like the worklet keeps
+    it (``bsb_add_kiosk_trace``)."""
+    n_out: int
+    events: object
+    quantum: int = 128
+    seed: int = 1
+
+
+def trace_events(events):
+    """[(quantum_index, "schedule", (args_dict,))] -- what ``ControllerMapper.trace_to_events`` produces and
+    ``WorkletTimeline.resolve`` consumes -- as a ctypes array of ``bsb_trace_event``.  Keys of args_dict are the worklet's
+    (active input rate semitones tonalityHz formantSemitones formantCompensation formantBaseHz loopStart loopEnd outputTime);
+    a missing key is "not in the call's object" (inherited or derived, see ``bsb_trace_event``)."""
+    nan = float("nan")
+    events = sorted(events, key=lambda e: e[0])
+    arr = (_capi.TraceEvent * len(events))()
+    for t, (k, method, args) in zip(arr, events):
+        if method != "schedule" or len(args) != 1:
+            raise ValueError("only schedule(obj) calls can be compiled into a trace (use TableDrive for the rest)")
+        o = args[0]
+        t.quantum = int(k)
+        t.output_time = float(o.get("outputTime", nan)); t.input = float(o["input"]) if o.get("input") is not None else nan
+        t.rate = float(o.get("rate", nan)); t.semitones = float(o.get("semitones", nan))
+        t.loop_start = float(o.get("loopStart", nan)); t.loop_end = float(o.get("loopEnd", nan))
+        t.tonality_hz = float(o.get("tonalityHz", nan)); t.formant_semitones = float(o.get("formantSemitones", nan))
+        t.formant_base_hz = float(o.get("formantBaseHz", nan))
+        t.active = -1 if "active" not in o else int(bool(o["active"]))
+        t.formant_compensation = -1 if "formantCompensation" not in o else int(bool(o["formantCompensation"]))
+        t.transpose_factor = float(o.get("transposeFactor", nan)); t.formant_factor = float(o.get("formantFactor", nan))
+    return arr
+
+
 def _ptr(a):
     if hasattr(a, "data_ptr"):
         return a.data_ptr()
@@ -126,6 +161,14 @@ class BatchStretch:
             else:
                 assert clip.flags["C_CONTIGUOUS"] and clip.dtype == np.float32
             clip_len = int(clip.shape[1])
+            if isinstance(d, TraceDrive):
+                n_out = int(d.n_out)
+                out = outputs[i] if outputs is not None else _alloc_like(clip, self.channels, n_out)
+                self._check(self.lib.bsb_add_kiosk_trace(self.h, i, _ptr(clip), clip_len, _ptr(out), n_out, int(d.quantum),
+                                                         d.events, len(d.events), int(d.seed) & 0xFFFFFFFF))
+                self._keep.append((clip, out, d.events))
+                outs.append(out)
+                continue
             if isinstance(d, TableDrive):
                 n_out = int(d.n_out)
                 segs = d.table
@@ -176,16 +219,16 @@ class BatchStretch:
         are complete; with ``sync=False`` the copies may still be in flight -- call ``synchronize()`` (or synchronise
         the stream) before reading ``host_outs``."""
         n = len(self._keep)
-        assert len(host_clips) == n and len(host_outs) == n
+        assert len(host_clips) == n and (host_outs is None or len(host_outs) == n)
         if cuda_stream is None:
             cuda_stream = 0
             if self._keep and hasattr(self._keep[0][0], "data_ptr"):
                 import torch
                 cuda_stream = torch.cuda.current_stream().cuda_stream
-        for (clip, out, _), hc, ho in zip(self._keep, host_clips, host_outs):
-            assert tuple(hc.shape) == tuple(clip.shape) and tuple(ho.shape) == tuple(out.shape)
+        for i, ((clip, out, _), hc) in enumerate(zip(self._keep, host_clips)):
+            assert tuple(hc.shape) == tuple(clip.shape) and (host_outs is None or tuple(host_outs[i].shape) == tuple(out.shape))
         ins = (C.c_void_p * n)(*[_ptr(x) for x in host_clips])
-        outs = (C.c_void_p * n)(*[_ptr(x) for x in host_outs])
+        outs = (C.c_void_p * n)(*[_ptr(x) for x in host_outs]) if host_outs is not None else None   # None: outputs stay on the device
         self._check(self.lib.bsb_run_host(self.h, ins, outs, C.c_void_p(cuda_stream)))
         if sync:
             self.synchronize()
@@ -230,6 +273,18 @@ class BatchStretch:
             self.lib.bsb_kernel_stat(self.h, i, C.byref(name), C.byref(ms), C.byref(n), C.byref(u))
             out[name.value.decode()] = dict(ms=ms.value, launches=n.value, units=u.value)
         return out
+
+    def kernel_launches(self, name):
+        """[(ms, units)] of every launch of kernel ``name`` in the last run, in launch order (ms needs profiling on)."""
+        for i in range(self.lib.bsb_kernel_count(self.h)):
+            nm, ms, n, u = C.c_char_p(), C.c_double(), C.c_longlong(), C.c_longlong()
+            self.lib.bsb_kernel_stat(self.h, i, C.byref(nm), C.byref(ms), C.byref(n), C.byref(u))
+            if nm.value.decode() == name:
+                cnt = int(n.value)
+                a, b = (C.c_double * max(cnt, 1))(), (C.c_longlong * max(cnt, 1))()
+                got = self.lib.bsb_kernel_launches(self.h, i, a, b, cnt)
+                return [(a[j], b[j]) for j in range(min(got, cnt))]
+        return []
 
     def block_info(self, stream, block):
         a = (C.c_longlong * 8)()

@@ -344,6 +344,84 @@ inline void plan_kiosk_table(const Geometry &g, int quantum, long long nOut, con
   }
 }
 
+// The worklet's control plane in front of the same drive: a trace of schedule() calls, each made
+// between two render quanta, edits the time map exactly like remoteMethods.schedule (app/SignalsmithStretch.mjs:656-701:
+// later segments popped, active / rate / semitones / loop bounds inherited from the latest one, input extrapolated at its
+// rate -- 0 if it was inactive --, then every segment whose successor starts by the NEW segment's output time shifted out,
+// so a segment scheduled ahead is current at once); every quantum then looks its segment up like process() does (:840-844).
+// All JS numbers are doubles.  One stored audio buffer covering the whole clip, as the kiosk app adds it (app/multi/app.mjs:369-376).
+struct TraceEvent {
+  long long quantum;      // applied before this render quantum (currentTime = quantum * q / sampleRate)
+  double outputTime;      // NaN: currentTime
+  double input;           // NaN: extrapolated
+  double rate, semitones, loopStart, loopEnd;   // NaN: inherited
+  double tonalityHz, formantSemitones, formantBaseHz;   // not inherited by the reference: must be given
+  int active;             // < 0: inherited
+  int formantCompensation;
+  double transposeFactor = NAN, formantFactor = NAN;
+};
+inline void plan_kiosk_trace(const Geometry &g, double sampleRate, int quantum, long long nOut, long long clipLen,
+                             const TraceEvent *ev, long long nEv, StreamPlan &plan) {
+  KioskPlanner kp(g, plan);
+  const double inLatS = (double)g.inLat / sampleRate, outLatS = (double)g.outLat / sampleRate;
+  std::vector<Segment> tm;
+  {   // the worklet's initial segment (:587-600)
+    Segment s0{}; s0.output = 0; s0.input = 0; s0.rate = 1; s0.semitones = 0; s0.tonalityHz = 8000; s0.formantSemitones = 0; s0.formantBaseHz = 0;
+    s0.loopStart = 0; s0.loopEnd = 0; s0.active = 0; s0.formantCompensation = 0;
+    tm.push_back(s0);
+  }
+  plan.nOut = nOut;
+  long long pos = 0, ei = 0;
+  for (long long k = 0; pos < nOut; ++k) {
+    const double currentTime = (double)(k * quantum) / sampleRate;
+    for (; ei < nEv && ev[ei].quantum <= k; ++ei) {
+      const TraceEvent &e = ev[ei];
+      if (std::isnan(e.tonalityHz) || std::isnan(e.formantSemitones) || std::isnan(e.formantBaseHz) || e.formantCompensation < 0) {
+        plan.error = "schedule() without tonalityHz / formantSemitones / formantCompensation / formantBaseHz: the reference does not inherit them and would hand NaN to the engine";
+        return;
+      }
+      const double outputTime = std::isnan(e.outputTime) ? currentTime : e.outputTime;
+      Segment latest = tm.back();
+      while (!tm.empty() && tm.back().output >= outputTime) { latest = tm.back(); tm.pop_back(); }
+      Segment s{};
+      s.active = e.active < 0 ? latest.active : (e.active ? 1 : 0);
+      s.output = outputTime;
+      s.rate = std::isnan(e.rate) ? latest.rate : e.rate;
+      s.semitones = std::isnan(e.semitones) ? latest.semitones : e.semitones;
+      s.loopStart = std::isnan(e.loopStart) ? latest.loopStart : e.loopStart;
+      s.loopEnd = std::isnan(e.loopEnd) ? latest.loopEnd : e.loopEnd;
+      s.tonalityHz = e.tonalityHz; s.formantSemitones = e.formantSemitones; s.formantBaseHz = e.formantBaseHz;
+      s.formantCompensation = e.formantCompensation ? 1 : 0;
+      s.transposeFactor = e.transposeFactor; s.formantFactor = e.formantFactor;
+      s.input = std::isnan(e.input) ? latest.input + (s.output - latest.output) * (latest.active ? latest.rate : 0.0) : e.input;
+      tm.push_back(s);
+      size_t drop = 0;
+      while (tm.size() - drop > 1 && tm[drop + 1].output <= outputTime) ++drop;
+      if (drop) tm.erase(tm.begin(), tm.begin() + drop);
+    }
+    const int q = (int)std::min<long long>(quantum, nOut - pos);
+    const double outputTime = currentTime + outLatS;
+    {
+      size_t drop = 0;
+      while (tm.size() - drop > 1 && tm[drop + 1].output <= outputTime) ++drop;
+      if (drop) tm.erase(tm.begin(), tm.begin() + drop);
+    }
+    Segment &seg = tm[0];
+    apply_segment_params(kp.ctl.p, seg, sampleRate);
+    long long end = 0;
+    if (seg.active) {
+      double inputTime = seg.input + (outputTime - seg.output) * seg.rate;
+      const double loopLength = seg.loopEnd - seg.loopStart;
+      if (loopLength > 0 && inputTime >= seg.loopEnd) { seg.input -= loopLength; inputTime -= loopLength; }
+      inputTime += inLatS;
+      end = (long long)std::floor(inputTime * sampleRate + 0.5);
+    }
+    kp.quantum(q, seg.active != 0, seg.rate, end, 0, clipLen);
+    if (plan.error) return;
+    pos += q;
+  }
+}
+
 // Streaming drive (live-input branch generalised): process(nIn, nOut) over a contiguous input, no seek.
 // Parameter segments are keyed by the output time of the first sample of a call.
 inline void plan_stream(const Geometry &g, double sampleRate, int nIn, int nOut, long long nCalls, long long clipLen,

@@ -485,6 +485,8 @@ struct bsb_engine {
   // (one CUDA event pair per launch, read back lazily so the run itself is never serialised)
   struct KStat { const char *name; double ms; long long launches, units; };
   std::vector<KStat> kstat;
+  struct LaunchRec { int k; double ms; long long units; };
+  std::vector<LaunchRec> launchRecs;   // of the last run, in launch order (ms only while profiling)
   bool profiling = false;
   bool fastFft = true;             // specialised STFT kernels where the geometry has them (bsb_set_fast_fft; off = the run-time-geometry path)
   bool overlap = true;             // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1 (two CUDA
@@ -500,7 +502,7 @@ struct bsb_engine {
   cudaStream_t sFront = nullptr, sBack = nullptr, sIn = nullptr, sOut = nullptr;
   cudaEvent_t evFront[2] = {nullptr, nullptr}, evBack[2] = {nullptr, nullptr}, evFork = nullptr, evJoin[2] = {nullptr, nullptr};
   bool backUsed[2] = {false, false};
-  struct Span { int k; cudaEvent_t a, b; };
+  struct Span { int k; cudaEvent_t a, b; size_t rec; };
   std::vector<Span> spans; std::vector<cudaEvent_t> evPool; size_t evUsed = 0;
   cudaEvent_t get_event() {
     if (evUsed == evPool.size()) { cudaEvent_t ev; cudaEventCreate(&ev); evPool.push_back(ev); }
@@ -597,6 +599,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
   auto account = [&](const char *name, long long units) {
     const int k = e->kidx(name);
     e->kstat[k].launches += 1; e->kstat[k].units += units; e->launches += 1;
+    e->launchRecs.push_back({k, 0.0, units});
     return k;
   };
 #ifdef BS_HOSTEMU
@@ -730,7 +733,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     if (e->profiling) {
       cudaEvent_t a = e->get_event(), b = e->get_event();
       cudaEventRecord(a, q); launch(); cudaEventRecord(b, q);
-      e->spans.push_back({k, a, b});
+      e->spans.push_back({k, a, b, e->launchRecs.size() - 1});
     } else launch();
   };
   if (stages & 1) {
@@ -906,6 +909,7 @@ int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long lo
     for (auto &sp : e->spans) {
       cudaEventSynchronize(sp.b);
       float ms1 = 0.f; cudaEventElapsedTime(&ms1, sp.a, sp.b); e->kstat[sp.k].ms += ms1;
+      if (sp.rec < e->launchRecs.size()) e->launchRecs[sp.rec].ms = ms1;
     }
     e->spans.clear(); e->evUsed = 0;
   }
@@ -913,6 +917,15 @@ int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long lo
   const bsb_engine::KStat &k = e->kstat[i];
   *name = k.name; *ms = k.ms; *launches = k.launches; *units = k.units;
   return 0;
+}
+
+int bsb_kernel_launches(bsb_engine *e, int i, double *ms, long long *units, int max) {
+  const char *name; double t; long long a, b;
+  if (bsb_kernel_stat(e, i, &name, &t, &a, &b) != 0) return -1;   // (folds the pending event pairs)
+  int n = 0;
+  for (const auto &r : e->launchRecs)
+    if (r.k == i) { if (n < max) { if (ms) ms[n] = r.ms; if (units) units[n] = r.units; } ++n; }
+  return n;
 }
 
 int bsb_begin(bsb_engine *e, int n) {
@@ -968,6 +981,25 @@ int bsb_add_kiosk_table(bsb_engine *e, int si, const float *dClip, long long cli
   Stream &s = e->streams[si];
   s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
   plan_kiosk_table(e->g, quantum, nOut, qs.data(), nQuanta, s.plan);
+  if (s.plan.error) return e->fail("stream %d: %s", si, s.plan.error);
+  s.planned = true; e->committed = false;
+  return 0;
+}
+
+int bsb_add_kiosk_trace(bsb_engine *e, int si, const float *dClip, long long clipLen, float *dOut, long long nOut, int quantum,
+                        const bsb_trace_event *events, long long nEvents, uint32_t seed) {
+  if (si < 0 || si >= (int)e->streams.size()) return e->fail("stream index out of range");
+  if (quantum < 1 || nOut < 0 || clipLen < 0 || nEvents < 0 || (nEvents > 0 && !events)) return e->fail("bad sizes");
+  std::vector<TraceEvent> ev((size_t)nEvents);
+  for (long long i = 0; i < nEvents; ++i) {
+    const bsb_trace_event &t = events[i];
+    if (i && t.quantum < events[i - 1].quantum) return e->fail("trace events must be ordered by quantum");
+    ev[i] = TraceEvent{t.quantum, t.output_time, t.input, t.rate, t.semitones, t.loop_start, t.loop_end, t.tonality_hz, t.formant_semitones,
+                       t.formant_base_hz, t.active, t.formant_compensation, t.transpose_factor, t.formant_factor};
+  }
+  Stream &s = e->streams[si];
+  s = Stream(); s.clip = dClip; s.out = dOut; s.clipLen = clipLen; s.seed = seed;
+  plan_kiosk_trace(e->g, e->sampleRate, quantum, nOut, clipLen, ev.data(), nEvents, s.plan);
   if (s.plan.error) return e->fail("stream %d: %s", si, s.plan.error);
   s.planned = true; e->committed = false;
   return 0;
@@ -1186,6 +1218,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
   e->launches = 0;
   e->lastRunStream = q;
   for (auto &k : e->kstat) { k.ms = 0.0; k.launches = 0; k.units = 0; }
+  e->launchRecs.clear();
   // streams whose silence gate closed for good (inactive time-map segments): the output from there on is zeros
   for (int s = 0; s < S; ++s) {
     const StreamDev &d = e->hs[s];
@@ -1201,7 +1234,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     std::memcpy((void *)e->streams[s].clip, hClips[s], (size_t)g.C * e->streams[s].clipLen * sizeof(float));
   for (const bsb_engine::Chunk &c : e->chunks)
     if (e->maxBlocks > 0 && launch_chunk(e, c.slot0, c.nSlots, c.nLive, c.ctas, q, q, 0, 3, kSynthEmit | kSynthAdd)) return -1;
-  for (int s = 0; s < S && hOuts; ++s)
+  for (int s = 0; s < S && hClips && hOuts; ++s)
     std::memcpy(hOuts[s], e->streams[s].out, (size_t)g.C * e->streams[s].plan.nOut * sizeof(float));
   for (size_t i = 0; i < e->gate.size(); ++i) {
     for (long long k = 0; k < e->gate[i].nCalls; ++k) e->dLoud[e->gate[i].callBase + k] = gate_call_loud(e->gate[i], g.C, k);
@@ -1210,7 +1243,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
   for (size_t i = 0; i < e->seekWatch.size(); ++i) e->dSeekFailed[i] = seek_watch_failed(e->seekWatch[i], g.C);
 #else
   e->spans.clear(); e->evUsed = 0;
-  const bool host = hClips != nullptr && hOuts != nullptr;
+  const bool host = hClips != nullptr;
   const std::vector<bsb_engine::Chunk> &chunks = host ? e->chunksHost : e->chunks;
   const std::vector<long long> &needEnd = host ? e->needEndHost : e->needEnd;
   const bool two = e->overlap && e->recBuf[1] != nullptr && chunks.size() > 1;
@@ -1239,7 +1272,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
       cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, e->sIn); cudaStreamWaitEvent(qF, ev, 0);
     }
     if (launch_chunk(e, slot0, ck.nSlots, ck.nLive, ck.ctas, qF, qB, two ? (int)(i & 1) : 0, 3, kSynthEmit | kSynthAdd)) return -1;
-    if (host) {   // the output samples this chunk emitted
+    if (host && hOuts) {   // the output samples this chunk emitted
       cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, qB); cudaStreamWaitEvent(e->sOut, ev, 0);
       for (int s = 0; s < S; ++s) {
         const StreamDev &d = e->hs[s];
@@ -1253,7 +1286,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     }
     ++i;
   }
-  if (host)   // what no block covers: the zeros behind a closed silence gate (written on `cudaStream` before the fork)
+  if (host && hOuts)   // what no block covers: the zeros behind a closed silence gate (written on `cudaStream` before the fork)
     for (int s = 0; s < S; ++s) {
       const StreamDev &d = e->hs[s];
       if (d.nOut > fetched[s])
@@ -1284,7 +1317,7 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
 int bsb_run(bsb_engine *e, void *cudaStream) { return run_impl(e, (stream_t)cudaStream, nullptr, nullptr); }
 
 int bsb_run_host(bsb_engine *e, const float *const *hClips, float *const *hOuts, void *cudaStream) {
-  if (!hClips || !hOuts) return e->fail("bsb_run_host needs host clip and output pointers");
+  if (!hClips) return e->fail("bsb_run_host needs host clip pointers");
   return run_impl(e, (stream_t)cudaStream, hClips, hOuts);
 }
 

@@ -17,6 +17,11 @@
 // that the serial test emulation (BS_HOSTEMU) can run the identical code.
 #pragma once
 #include "kernels.cuh"
+#ifdef BS_HOSTEMU
+#include <algorithm>
+using std::max;
+using std::min;
+#endif
 
 namespace bs {
 
@@ -210,78 +215,118 @@ BS_HD void fast_last(const cf *tw, const cf *otw, const cf *src, int tid, Emit &
   }
 }
 
-// one packed, windowed, rotated input point of the forward transform (analyse_window's pack loop): j = packed pair index
-struct PackCtx { const float *xs; const f4 *tab; int lo, hi, span, jA, jC, off, cStart; bool aligned; };
-BS_HD cf fast_pack_point(const PackCtx &c, int j) {
-  const f4 t = c.tab[j];
-  float t0, t1;
-  // Warp-uniform shortcut: the 32 pairs this warp packs in one trip (j is consecutive over its lanes) lie in one half of the
-  // window and inside the part of it the clip covers -- no per-sample predicates.  (The serial emulation runs the general
-  // path only; it computes the same values.)
-#ifndef BS_HOSTEMU
-  const int jw = j & ~31;
-  const bool allA = jw + 31 < c.jA, allC = jw >= c.jC;
-  const int ib = allA ? c.off : -c.cStart, iw = 2 * jw + ib;
-  if ((allA || allC) && iw >= c.lo && iw + 64 <= c.hi) {
-    const float *px = c.xs + (2 * j + ib);
-    float x0, x1;
-    if (c.aligned) { const f2 v = *(const f2 *)px; x0 = v.x; x1 = v.y; } else { x0 = px[0]; x1 = px[1]; }
-    t0 = x0 * t.x; t1 = x1 * t.y;
-  } else
-#endif
-  {
-    const bool inA = j < c.jA, live = inA || j >= c.jC;
-    const int i = 2 * j + (inA ? c.off : -c.cStart);
-    float x0 = 0.f, x1 = 0.f;
-    if (live && (unsigned)(i - c.lo) < (unsigned)c.span) x0 = c.xs[i];
-    if (live && (unsigned)(i + 1 - c.lo) < (unsigned)c.span) x1 = c.xs[i + 1];
-    t0 = live ? x0 * t.x : 0.f; t1 = live ? x1 * t.y : 0.f;
+// The pack stage of the forward transform (analyse_window's pack loop): packed pair j = window samples i, i+1 with
+// i = 2j + off (second half of the window, j < jA) or 2j - cStart (first half, j >= jC; the sign of the half-bin shift is
+// in the table), zeros between; samples outside [lo, hi) -- beyond the clip, or the short pre-roll of a "previous"
+// window -- read as zero.  PAIR: both samples of a pair are valid together and 8-byte aligned (one 64-bit load).
+// Loads of U pairs are issued before the first one is used.
+struct PackCtx { const float *xs; const f4 *tab; int lo, span, jA, jC, off, cStart; bool none; };
+template <bool PAIR>
+BS_HD void fast_pack_load(const PackCtx &c, int j, float &x0, float &x1, f4 &t, bool &live) {
+  const bool inA = j < c.jA;
+  live = inA || j >= c.jC;
+  const int i = 2 * j + (inA ? c.off : -c.cStart);
+  const bool v0 = live && !c.none && (unsigned)(i - c.lo) < (unsigned)c.span;
+  t = c.tab[j];
+  // no branch around the loads (the U pairs of a trip must be in flight together): a sample that is not there is read from
+  // the nearest position that is (the caller has made sure there is one: span > 0) and replaced by zero
+  const int hiM = c.lo + c.span - (PAIR ? 2 : 1);
+  if (PAIR) { const int ic = min(max(i, c.lo), hiM); const f2 v = *(const f2 *)(c.xs + ic); x0 = v0 ? v.x : 0.f; x1 = v0 ? v.y : 0.f; }
+  else {
+    const bool v1 = live && !c.none && (unsigned)(i + 1 - c.lo) < (unsigned)c.span;
+    const float a = c.xs[min(max(i, c.lo), hiM)], b = c.xs[min(max(i + 1, c.lo), hiM)];
+    x0 = v0 ? a : 0.f; x1 = v1 ? b : 0.f;
   }
+}
+BS_HD cf fast_pack_finish(float x0, float x1, const f4 t, bool live) {
+  const float t0 = live ? x0 * t.x : 0.f, t1 = live ? x1 * t.y : 0.f;
   cf z; z.re = (t.z * t0) - (t.w * t1); z.im = (t.w * t0) + (t.z * t1);
   return z;
 }
-
-template <int LG, int OUTER, class LOut>
-BS_HD void fast_fwd_pack(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *dst, int tid) {
+template <int LG, int OUTER, class LOut, bool PAIR>
+BS_HD void fast_fwd_pack_t(const PackCtx &c, cf *dst, int tid) {
   using F = FastGeom<LG, OUTER>;
   constexpr int M = F::M, inner = F::inner;
-  PackCtx c;
-  c.xs = x + w.start; c.tab = (const f4 *)T.packTab; c.lo = w.lo; c.hi = w.hi; c.span = w.hi - w.lo;
-  c.off = g.off; c.cStart = g.N - g.off; c.jA = (g.L - g.off) >> 1; c.jC = c.cStart >> 1;
-  c.aligned = (((size_t)c.xs) & 7) == 0;   // sample pairs start at even window positions: 8-byte loads if the window start allows
   if (!F::lg0) {
-#pragma unroll 4
-    for (int j = tid; j < M; j += kFastNT) {
-      const int q = j / OUTER, sub = j - q * OUTER;
-      dst[LOut::at(sub, q)] = fast_pack_point(c, j);
+    constexpr int U = 4;
+    constexpr bool whole = (M % (kFastNT * U)) == 0;   // every trip is full: no bounds checks between the loads
+    for (int j0 = tid; j0 < M; j0 += kFastNT * U) {
+      float x0[U], x1[U]; f4 t[U]; bool live[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int j = j0 + u * kFastNT; if (whole || j < M) fast_pack_load<PAIR>(c, j, x0[u], x1[u], t[u], live[u]); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * kFastNT;
+        if (whole || j < M) { const int q = j / OUTER, sub = j - q * OUTER; dst[LOut::at(sub, q)] = fast_pack_finish(x0[u], x1[u], t[u], live[u]); }
+      }
     }
   } else {   // the radix-2 pass on elements q and q + inner/2 of a sub-transform = packed pairs j and j + M/2
-#pragma unroll 2
-    for (int j = tid; j < M / 2; j += kFastNT) {
-      const int q = j / OUTER, sub = j - q * OUTER;
-      const cf a = fast_pack_point(c, j), b = fast_pack_point(c, j + M / 2);
-      cf lo, hi; lo.re = b.re + a.re; lo.im = b.im + a.im; hi.re = a.re - b.re; hi.im = a.im - b.im;
-      dst[LOut::at(sub, q)] = lo; dst[LOut::at(sub, q + inner / 2)] = hi;
+    constexpr int U = (M / 2) % (2 * kFastNT) == 0 ? 2 : 1;   // full trips only
+    static_assert((M / 2) % (kFastNT * U) == 0 || M / 2 < kFastNT, "pack trips");
+    for (int j0 = tid; j0 < M / 2; j0 += kFastNT * U) {
+      float x0[2 * U], x1[2 * U]; f4 t[2 * U]; bool live[2 * U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * kFastNT;
+        if (j < M / 2) { fast_pack_load<PAIR>(c, j, x0[2 * u], x1[2 * u], t[2 * u], live[2 * u]); fast_pack_load<PAIR>(c, j + M / 2, x0[2 * u + 1], x1[2 * u + 1], t[2 * u + 1], live[2 * u + 1]); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * kFastNT;
+        if (j < M / 2) {
+          const int q = j / OUTER, sub = j - q * OUTER;
+          const cf a = fast_pack_finish(x0[2 * u], x1[2 * u], t[2 * u], live[2 * u]), b = fast_pack_finish(x0[2 * u + 1], x1[2 * u + 1], t[2 * u + 1], live[2 * u + 1]);
+          cf lo, hi; lo.re = b.re + a.re; lo.im = b.im + a.im; hi.re = a.re - b.re; hi.im = a.im - b.im;
+          cf *pd = dst + LOut::at(sub, q);
+          pd[0] = lo; pd[LOut::pad(inner / 2)] = hi;
+        }
+      }
     }
   }
+}
+template <int LG, int OUTER, class LOut>
+BS_HD void fast_fwd_pack(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *dst, int tid) {
+  PackCtx c;
+  c.xs = x + w.start; c.tab = (const f4 *)T.packTab; c.lo = w.lo; c.span = w.hi - w.lo; c.none = false;
+  c.off = g.off; c.cStart = g.N - g.off; c.jA = (g.L - g.off) >> 1; c.jC = c.cStart >> 1;
+  // pairs start at even window positions: whole pairs are valid or not, and 8-byte aligned, if lo, hi and the start allow
+  const bool pair = ((((size_t)c.xs) & 7) == 0) && ((w.lo | w.hi) & 1) == 0;
+  if (c.span <= 0) {   // nothing of the clip in this window: every sample reads as zero (loads go to the table, results are dropped)
+    c.xs = (const float *)T.packTab; c.lo = 0; c.span = 1; c.none = true;
+    fast_fwd_pack_t<LG, OUTER, LOut, false>(c, dst, tid);
+  } else if (pair) fast_fwd_pack_t<LG, OUTER, LOut, true>(c, dst, tid);
+  else fast_fwd_pack_t<LG, OUTER, LOut, false>(c, dst, tid);
 }
 
 // untangle of the forward transform: bins i and M-1-i from the complex transform's outputs (analyse_window's last loop)
 template <int LG, int OUTER>
 BS_HD void fast_fwd_untangle(const DevTables &T, const cf *Y /* natural order */, cf *X, bool rotate, int tid) {
-  constexpr int M = FastGeom<LG, OUTER>::M, half = M >> 1;
-#pragma unroll 2
-  for (int p = tid; p < half; p += kFastNT) {
-    const int i = (p < half - 1) ? p : half;   // the reference's loop leaves pair (half, half-1) as written by its last iteration
-    const int j = M - 1 - i;
-    const cf u = T.untangle[i], a = Y[i], b = Y[j];
-    const float sI = (b.im + a.im) * 0.5f, dR = (a.re - b.re) * 0.5f;
-    const float pp = (sI * u.re) + (dR * u.im), dI = (a.im - b.im) * 0.5f;
-    const float qq = (dR * u.re) - (sI * u.im), sR = (b.re + a.re) * 0.5f;
-    cf xi_, xj_;
-    xi_.im = pp + dI; xi_.re = qq + sR; xj_.im = pp - dI; xj_.re = sR - qq;
-    if (rotate) { xi_ = rot_prev(xi_, T.specRot[i]); xj_ = rot_prev(xj_, T.specRot[j]); }
-    X[i] = xi_; X[j] = xj_;
+  constexpr int M = FastGeom<LG, OUTER>::M, half = M >> 1, U = 3;
+  for (int p0 = tid; p0 < half; p0 += kFastNT * U) {
+    cf u[U], a[U], b[U], ri[U], rj[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int p = p0 + k * kFastNT;
+      if (p < half) {
+        const int i = (p < half - 1) ? p : half, j = M - 1 - i;   // the reference's loop leaves pair (half, half-1) as written by its last iteration
+        u[k] = T.untangle[i]; a[k] = Y[i]; b[k] = Y[j];
+        if (rotate) { ri[k] = T.specRot[i]; rj[k] = T.specRot[j]; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int p = p0 + k * kFastNT;
+      if (p < half) {
+        const int i = (p < half - 1) ? p : half, j = M - 1 - i;
+        const float sI = (b[k].im + a[k].im) * 0.5f, dR = (a[k].re - b[k].re) * 0.5f;
+        const float pp = (sI * u[k].re) + (dR * u[k].im), dI = (a[k].im - b[k].im) * 0.5f;
+        const float qq = (dR * u[k].re) - (sI * u[k].im), sR = (b[k].re + a[k].re) * 0.5f;
+        cf xi_, xj_;
+        xi_.im = pp + dI; xi_.re = qq + sR; xj_.im = pp - dI; xj_.re = sR - qq;
+        if (rotate) { xi_ = rot_prev(xi_, ri[k]); xj_ = rot_prev(xj_, rj[k]); }
+        X[i] = xi_; X[j] = xj_;
+      }
+    }
   }
 }
 
@@ -298,12 +343,24 @@ BS_HD void fast_inv_untangle(const DevTables &T, const cf *X, cf *dst, int tid) 
   constexpr int M = F::M, half = M >> 1, inner = F::inner;
   auto put = [&](int k, cf v) { const int q = k / OUTER, sub = k - q * OUTER; dst[LOut::at(sub, q)] = v; };
   if (!F::lg0) {
-#pragma unroll 2
-    for (int p = tid; p < half; p += kFastNT) {
-      const int i = (p < half - 1) ? p : half, j = M - 1 - i;
-      cf oi, oj;
-      fast_inv_pair(T.untangle[i], X[i], X[j], oi, oj);
-      put(i, oi); put(j, oj);
+    constexpr int U = 3;   // loads of U pairs in flight before the first is used
+    for (int p0 = tid; p0 < half; p0 += kFastNT * U) {
+      cf un[U], xi_[U], xj_[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int p = p0 + k * kFastNT;
+        if (p < half) { const int i = (p < half - 1) ? p : half; un[k] = T.untangle[i]; xi_[k] = X[i]; xj_[k] = X[M - 1 - i]; }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int p = p0 + k * kFastNT;
+        if (p < half) {
+          const int i = (p < half - 1) ? p : half, j = M - 1 - i;
+          cf oi, oj;
+          fast_inv_pair(un[k], xi_[k], xj_[k], oi, oj);
+          put(i, oi); put(j, oj);
+        }
+      }
     }
   } else {
     // with the radix-2 pass: elements k and k + M/2 meet, so a work item takes the pairs (i, M-1-i) and (M/2-1-i, M/2+i)
@@ -385,11 +442,10 @@ BS_HD void fast_synth(const DevGeom &g, const DevTables &T, const cf *X, float *
   // table's window coefficients carry the sign of the first half (ring -= t*w there = adding -(t*w) = t*(-w))
   BS_FAST_FORALL((fast_last<LG, OUTER, true, LL>(T.tw, T.otw, src, tid, [&](int j, float re, float im) {
     const bool inA = j < jA;
-    if (!inA && j < jC) return;
     const f4 t = tab[j];
     const float t1 = (t.z * im) - (t.w * re), t0 = (t.w * im) + (t.z * re);
     f2 o; o.x = t0 * t.x; o.y = t1 * t.y;
-    *(f2 *)(frame + (inA ? 2 * j + off : 2 * j - cStart)) = o;
+    if (inA || j >= jC) *(f2 *)(frame + (inA ? 2 * j + off : 2 * j - cStart)) = o;
   })))
 }
 

@@ -94,6 +94,22 @@ typedef struct bsb_quantum {
 } bsb_quantum;
 int bsb_add_kiosk_table(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, long long n_out,
                         int quantum, const bsb_quantum *table, long long n_quanta, uint32_t seed);
+/* The same drive from a control trace: schedule() calls (remoteMethods.schedule, app/SignalsmithStretch.mjs:656-701), each
+ * applied before render quantum `quantum`, edit the worklet's time map; every render quantum then looks its segment up like
+ * process() does (:840-844).  This is what a controller's `set` messages become after the kiosk app's mapping
+ * (app/multi/app.mjs:478-616, mirrored by the Python ControllerMapper).  NaN / negative = "not in the call's object":
+ * output_time defaults to currentTime, input is extrapolated, rate / semitones / loop bounds / active are inherited from
+ * the latest segment; tonality_hz, formant_semitones, formant_base_hz and formant_compensation are NOT inherited by the
+ * reference (it would hand NaN to the engine) and must be given.  One stored audio buffer = the whole clip. */
+typedef struct bsb_trace_event {
+  long long quantum;
+  double output_time, input, rate, semitones, loop_start, loop_end;
+  double tonality_hz, formant_semitones, formant_base_hz;
+  int32_t active, formant_compensation;
+  double transpose_factor, formant_factor;   /* NaN = unset, see bsb_segment */
+} bsb_trace_event;
+int bsb_add_kiosk_trace(bsb_engine *e, int stream, const float *d_clip, long long clip_len, float *d_out, long long n_out,
+                        int quantum, const bsb_trace_event *events, long long n_events, uint32_t seed);
 /* configure() arithmetic without a device (W#25): out = {fftSamples, bands, inputLatency, outputLatency, longStep, inner*16+outer} */
 int bsb_query_geometry(int block_samples, int interval_samples, int split_computation, int out[6]);
 /* streaming drive: `process(n_in, n_out)` n_calls times over a contiguous input (:870-882 generalised) */
@@ -108,6 +124,7 @@ int bsb_run(bsb_engine *e, void *cuda_stream);
  * copies are pipelined with the kernels time chunk by time chunk (input of chunk i+1 and output of chunk i-1 move
  * while chunk i computes).  Everything is ordered after, and joined back into, `cuda_stream`. */
 int bsb_run_host(bsb_engine *e, const float *const *h_clips, float *const *h_outs, void *cuda_stream);
+/* (h_outs may be NULL: the inputs come from the host, the outputs stay in the device buffers given to bsb_add_*) */
 /* block until everything the last bsb_run / bsb_run_host queued has finished (the host outputs of bsb_run_host are only
  * complete after this, or after the caller's own synchronisation of `cuda_stream`) */
 int bsb_synchronize(bsb_engine *e);
@@ -142,6 +159,9 @@ void bsb_set_fast_fft(bsb_engine *e, int on);
 int bsb_fast_fft_active(const bsb_engine *e);   /* 1 = this engine's runs use the specialised STFT kernels */
 int bsb_kernel_count(const bsb_engine *e);
 int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units);
+/* the launches of kernel i one by one (profiling on): device ms and units of up to `max` launches in launch order; returns
+ * how many the last run made */
+int bsb_kernel_launches(bsb_engine *e, int i, double *ms, long long *units, int max);
 
 /* Self-test of the branch-free divide / square-root helpers of the chain kernel (device pointers, n elements):
  * q = x / d, r = sqrt(x) for positive d; flags bit0/bit1 = the operand pair was outside the helpers' safe range (the

@@ -190,3 +190,34 @@ def test_restart_after_the_gate_closed_is_refused_and_a_silent_seek_is_reported(
     eng.run()
     assert eng.gate_events() == 1
     eng.close()
+
+
+@pytest.mark.parametrize("preset", ["default", "cheaper"])
+def test_native_trace_drive_equals_the_python_mirror(preset, emu):
+    """bsb_add_kiosk_trace keeps the worklet's time map inside the library (schedule() semantics in C++): same bits as the
+    Python mirror's per-quantum table, for the full-feature trace, a controller trace, and a pause."""
+    clip = refdrive.survey_clip(30000)
+    n_out = 40000
+    m = bs.ControllerMapper(audio_duration=30000 / 48000.0, channel="B")
+    rng = np.random.default_rng(4)
+    lines, t = [], 0.0
+    while t < 0.8:
+        key = "rate" if rng.random() < 0.5 else "tone"
+        val = float(np.exp(rng.uniform(np.log(0.5), np.log(2.0)))) if key == "rate" else int(rng.integers(-12, 13))
+        lines.append((t, json.dumps(dict(type="set", channel="B", key=key, value=val))))
+        t += float(rng.uniform(0.02, 0.1))
+    traces = [_trace(), m.trace_to_events(lines), _stop_start_trace("pause")]
+    for ev in traces:
+        tl = bs.WorkletTimeline(48000.0, config=dict(preset=preset), lib=emu); tl.addBuffers(clip)
+        recs = tl.resolve(n_out, events=ev)
+        eng = bs.BatchStretch(2, 48000.0, preset=preset, lib=emu)
+        c = np.ascontiguousarray(clip)
+        outs = eng.plan([c, c], [bs.TableDrive(n_out, bs.WorkletTimeline.table(recs)), bs.TraceDrive(n_out, bs.trace_events(ev))])
+        eng.run()
+        assert cases.compare(np.array(outs[0]), np.array(outs[1]))[0] and np.abs(np.array(outs[1])).max() > 1e-2
+        for b in range(eng.stream_blocks(0)):
+            assert eng.block_info(0, b) == eng.block_info(1, b)
+        eng.close()
+    with pytest.raises(RuntimeError, match="NaN"):        # the quirk the mirror refuses is refused here too
+        eng = bs.BatchStretch(2, 48000.0, lib=emu)
+        eng.plan([np.ascontiguousarray(clip)], [bs.TraceDrive(1000, bs.trace_events([(0, "schedule", (dict(active=True),))]))])
