@@ -78,21 +78,27 @@ def trace_events(events):
     a missing key is "not in the call's object" (inherited or derived, see ``bsb_trace_event``)."""
     nan = float("nan")
     events = sorted(events, key=lambda e: e[0])
-    arr = (_capi.TraceEvent * len(events))()
-    for t, (k, method, args) in zip(arr, events):
+    for _, method, args in events:
         if method != "schedule" or len(args) != 1:
             raise ValueError("only schedule(obj) calls can be compiled into a trace (use TableDrive for the rest)")
-        o = args[0]
-        t.quantum = int(k)
-        t.output_time = float(o.get("outputTime", nan)); t.input = float(o["input"]) if o.get("input") is not None else nan
-        t.rate = float(o.get("rate", nan)); t.semitones = float(o.get("semitones", nan))
-        t.loop_start = float(o.get("loopStart", nan)); t.loop_end = float(o.get("loopEnd", nan))
-        t.tonality_hz = float(o.get("tonalityHz", nan)); t.formant_semitones = float(o.get("formantSemitones", nan))
-        t.formant_base_hz = float(o.get("formantBaseHz", nan))
-        t.active = -1 if "active" not in o else int(bool(o["active"]))
-        t.formant_compensation = -1 if "formantCompensation" not in o else int(bool(o["formantCompensation"]))
-        t.transpose_factor = float(o.get("transposeFactor", nan)); t.formant_factor = float(o.get("formantFactor", nan))
+    objs = [e[2][0] for e in events]
+    a = np.zeros(len(events), dtype=_TRACE_DTYPE)       # same layout as bsb_trace_event (checked at import)
+    a["quantum"] = [int(e[0]) for e in events]
+    for field, key in _TRACE_KEYS:
+        a[field] = [nan if o.get(key) is None else float(o[key]) for o in objs]
+    a["active"] = [-1 if "active" not in o else int(bool(o["active"])) for o in objs]
+    a["formant_compensation"] = [-1 if "formantCompensation" not in o else int(bool(o["formantCompensation"])) for o in objs]
+    arr = (_capi.TraceEvent * len(events))()
+    if len(events):
+        C.memmove(arr, a.ctypes.data, a.nbytes)
     return arr
+
+
+_TRACE_KEYS = (("output_time", "outputTime"), ("input", "input"), ("rate", "rate"), ("semitones", "semitones"), ("loop_start", "loopStart"),
+               ("loop_end", "loopEnd"), ("tonality_hz", "tonalityHz"), ("formant_semitones", "formantSemitones"),
+               ("formant_base_hz", "formantBaseHz"), ("transpose_factor", "transposeFactor"), ("formant_factor", "formantFactor"))
+_TRACE_DTYPE = np.dtype([(n, {C.c_longlong: "<i8", C.c_double: "<f8", C.c_int32: "<i4"}[t]) for n, t in _capi.TraceEvent._fields_], align=True)
+assert _TRACE_DTYPE.itemsize == C.sizeof(_capi.TraceEvent) and all(_TRACE_DTYPE.fields[n][1] == getattr(_capi.TraceEvent, n).offset for n, _ in _capi.TraceEvent._fields_)
 
 
 def _ptr(a):

@@ -364,12 +364,21 @@ class ControllerMapper:
         """Serial lines ``(t_seconds, json_text)`` -> sorted events for ``WorkletTimeline.resolve`` / ``render``: each
         accepted ``set`` for this channel becomes one ``schedule`` call made at the first render quantum whose
         currentTime is >= t (the message is handled between render calls)."""
-        events = []
+        msgs = []
         for t, text in lines:
             try:
-                msg = self.normalize(json.loads(text))
+                msgs.append((t, json.loads(text)))
             except (ValueError, TypeError):
                 continue
+        return self.messages_to_events(msgs, sample_rate)
+
+    def messages_to_events(self, msgs, sample_rate=48000.0):
+        """The same for already parsed messages ``(t_seconds, dict)`` (what the bridge hands on after json.loads)."""
+        events = []
+        for t, msg in msgs:
+            if not isinstance(msg, dict):
+                continue
+            msg = self.normalize(msg)
             if msg.get("type") != "set" or msg.get("channel", self.channel) != self.channel:
                 continue
             if not self.apply_set(str(msg.get("key", "")), msg.get("value")):
