@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T
   if (m >= sd.nBlocks) return;
   if (!(blocks[sd.blockBase + m].flags & kNew)) return;
   const Window w = windows[2 * (sd.blockBase + m) + which];
-  cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * g.B;
+  cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * guard_pitch(g.B) + kGuard;
   analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x, which == 1);
 }
 
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) analysis_
   if (m >= sd.nBlocks) return;
   if (!(blocks[sd.blockBase + m].flags & kNew)) return;
   const Window w = windows[2 * (sd.blockBase + m) + which];
-  cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * g.B;
+  cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * guard_pitch(g.B) + kGuard;
   fast_analyse<LG, OUTER>(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, (cf *)sm, which == 1);
 }
 template <int LG, int OUTER>
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256) map_energy_kernel(DevGeom g, const Stream
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
   const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
   if (!c.valid) return;
-  const size_t CB = (size_t)g.C * g.B;
+  const size_t CBg = (size_t)g.C * guard_pitch(g.B);
   const cf *inp = block_input(g, c.rec2, s, slot0, nSlots, specIn, st.lastInput);
-  float *inE = st.inEnergy + c.slot * CB, *en = st.energy + c.slot * g.B, *sm = st.smoothed + c.slot * g.B;
+  float *inE = st.inEnergy + c.slot * CBg + kGuard, *en = st.energy + c.slot * g.B, *sm = st.smoothed + c.slot * g.B;
   float *fm = st.fm + c.slot * fm_pitch(g.B), *mp = st.map + c.slot * g.B * 2;
   if (g.C == 2) map_energy<2>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
   else if (g.C == 1) map_energy<1>(g, c.rec, inp, inE, en, sm, fm, mp, threadIdx.x, blockDim.x);
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) map_fmapply_kernel(DevGeom g, const Strea
   const int t = blockIdx.x % nSlots, s = blockIdx.x / nSlots;
   const SlotCtx c = slot_ctx(streams, blocks, blocks2, slot0, nSlots, s, t);
   if (!c.valid || !(c.rec.flags & kFormants)) return;
-  float *inE = st.inEnergy + c.slot * (size_t)g.C * g.B; const float *fm = st.fm + c.slot * fm_pitch(g.B);
+  float *inE = st.inEnergy + c.slot * (size_t)g.C * guard_pitch(g.B) + kGuard; const float *fm = st.fm + c.slot * fm_pitch(g.B);
   if (g.C == 2) fm_apply<2>(g, c.rec, c.rec2, fm, inE, threadIdx.x, blockDim.x);
   else if (g.C == 1) fm_apply<1>(g, c.rec, c.rec2, fm, inE, threadIdx.x, blockDim.x);
   else fm_apply<0>(g, c.rec, c.rec2, fm, inE, threadIdx.x, blockDim.x);
@@ -291,16 +291,16 @@ __global__ void __launch_bounds__(kTermTile, BS_TERM_CTAS) preterms_kernel(DevGe
   if (m >= sd.nBlocks) return;
   const BlockRec rec = blocks[sd.blockBase + m];
   const BlockRec2 rec2 = blocks2[sd.blockBase + m];
-  const size_t CB = (size_t)g.C * g.B, slot = (size_t)s * nSlots + t;
+  const size_t CB = (size_t)g.C * g.B, CBg = (size_t)g.C * guard_pitch(g.B), slot = (size_t)s * nSlots + t;
   const cf *inp = block_input(g, rec2, s, slot0, nSlots, specIn, st.lastInput);
-  const cf *prev = (rec.flags & kNew) ? specIn + (slot * 2 + 1) * CB : nullptr;
-  const float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
+  const cf *prev = (rec.flags & kNew) ? specIn + (slot * 2 + 1) * CBg + kGuard : nullptr;
+  const float *inE = st.inEnergy + slot * CBg + kGuard, *mp = st.map + slot * g.B * 2;
   const bool last = (m + 1 == sd.nBlocks) || (t + 1 == nSlots);
   const uint32_t rng0 = minstd_jump(st.seeds[s], (uint32_t)(((unsigned long long)rec2.rngSkip * (unsigned long long)(2 * g.B - 2)) % 2147483646ull));
   float *rr = st.rec + (size_t)s * ((nSlots + 31) / 32) * rec_group_floats(g.B, g.longStep, g.C) + rec_slot_offset(t, g.B, g.longStep, g.C);
   const float *pE = st.predE[st.parity] + (size_t)s * CB;
   float *pEo = last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr;
-  const float *pInE = t > 0 ? inE - CB : nullptr, *pMap = t > 0 ? mp - (size_t)g.B * 2 : nullptr;
+  const float *pInE = t > 0 ? inE - CBg : nullptr, *pMap = t > 0 ? mp - (size_t)g.B * 2 : nullptr;
   const int tid = threadIdx.x, nt = blockDim.x;
   extern __shared__ float4 sm4[];
   float *sm = (float *)sm4;
@@ -321,10 +321,10 @@ __global__ void __launch_bounds__(256) carry_kernel(DevGeom g, const StreamDev *
   if (!(g.incremental || (mLast + 1 < sd.nBlocks && !(blocks[sd.blockBase + mLast + 1].flags & kNew)))) return;
   const BlockRec2 r2 = blocks2[sd.blockBase + mLast];
   if (r2.lastNew < slot0) return;
-  const size_t CB = (size_t)g.C * g.B;
-  const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput);
-  cf *dst = st.lastInput + (size_t)s * CB;
-  for (int i = threadIdx.x; i < (int)CB; i += blockDim.x) dst[i] = src[i];
+  const size_t CBg = (size_t)g.C * guard_pitch(g.B);   // (guards and all: they are zero on both sides)
+  const cf *src = block_input(g, r2, s, slot0, nSlots, specIn, st.lastInput) - kGuard;
+  cf *dst = st.lastInput + (size_t)s * CBg;
+  for (int i = threadIdx.x; i < (int)CBg; i += blockDim.x) dst[i] = src[i];
 }
 
 // warps per chain CTA: as many as the chunk can use, the kernel was compiled for, and shared memory holds
@@ -552,7 +552,7 @@ static void reset_state(bsb_engine *e, stream_t q) {
   StateDev &st = e->st;
   // reset(): zero phase state, rings, maps (the RNG is re-derived from the per-stream seed and the block table)
   dzero(st.outSpec, S * CB * sizeof(cf), q); dzero(st.predE[0], S * CB * sizeof(float), q); dzero(st.predE[1], S * CB * sizeof(float), q);
-  dzero(st.lastInput, S * CB * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
+  dzero(st.lastInput, S * (size_t)g.C * guard_pitch(g.B) * sizeof(cf), q); dzero(st.freqEst, 2 * (size_t)S * sizeof(float), q);
   dzero(st.ring[0], (size_t)S * g.C * g.L * sizeof(float), q); dzero(st.ring[1], (size_t)S * g.C * g.L * sizeof(float), q);
   st.ringPar = 0;
   st.parity = 0;
@@ -565,7 +565,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
   const Geometry &g = e->g;
   const int S = nLive;   // streams are kept longest first: the ones with blocks left at slot0 are the first nLive
 #ifdef BS_HOSTEMU
-  const size_t CB = (size_t)g.C * g.B;
+  const size_t CB = (size_t)g.C * g.B, CBg = (size_t)g.C * guard_pitch(g.B);
 #endif
   e->st.rec = e->recBuf[buf];
   StateDev &st = e->st;
@@ -618,7 +618,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
         if (!(e->dBlocks[sd.blockBase + m].flags & kNew)) continue;
         for (int which = 0; which < 2; ++which)
           for (int c = 0; c < g.C; ++c) {
-            cf *X = e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * g.B;
+            cf *X = e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * guard_pitch(g.B) + kGuard;
             const float *x = sd.clip + (size_t)c * sd.clipLen; const Window w = e->dWindows[2 * (sd.blockBase + m) + which];
             if (!e->fastFft || !fast_analyse_any(e->dg, e->dt, x, w, X, sm, which == 1)) analyse_window(e->dg, e->dt, x, w, X, sm, 0, 1, which == 1);
           }
@@ -635,7 +635,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
         long long m = slot0 + t; const size_t slot = (size_t)s * nSlots + t;
         const BlockRec rec = e->dBlocks[sd.blockBase + m];
         const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
-        float *inE = st.inEnergy + slot * CB, *en = st.energy + slot * g.B, *smo = st.smoothed + slot * g.B, *fm = st.fm + slot * fm_pitch(g.B);
+        float *inE = st.inEnergy + slot * CBg + kGuard, *en = st.energy + slot * g.B, *smo = st.smoothed + slot * g.B, *fm = st.fm + slot * fm_pitch(g.B);
         float *mp = st.map + slot * g.B * 2;
         mapE(e->dg, rec, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput), inE, en, smo, fm, mp, 0, 1);
         if (rec.flags & kMapped) {
@@ -657,11 +657,11 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
         long long m = slot0 + t; const size_t slot = (size_t)s * nSlots + t;
         const BlockRec rec = e->dBlocks[sd.blockBase + m];
         const BlockRec2 rec2 = e->dBlocks2[sd.blockBase + m];
-        const float *inE = st.inEnergy + slot * CB, *mp = st.map + slot * g.B * 2;
+        const float *inE = st.inEnergy + slot * CBg + kGuard, *mp = st.map + slot * g.B * 2;
         const bool last = (m + 1 == sd.nBlocks) || (t + 1 == nSlots);
         const uint32_t rng0 = minstd_jump(st.seeds[s], (uint32_t)(((unsigned long long)rec2.rngSkip * (unsigned long long)(2 * g.B - 2)) % 2147483646ull));
         termFn(e->dg, e->dt, rec, rng0, block_input(e->dg, rec2, s, slot0, nSlots, e->specIn, st.lastInput),
-               (rec.flags & kNew) ? e->specIn + (slot * 2 + 1) * CB : nullptr, inE, mp, t > 0 ? inE - CB : nullptr,
+               (rec.flags & kNew) ? e->specIn + (slot * 2 + 1) * CBg + kGuard : nullptr, inE, mp, t > 0 ? inE - CBg : nullptr,
                t > 0 ? mp - (size_t)g.B * 2 : nullptr, st.predE[st.parity] + (size_t)s * CB,
                last ? st.predE[st.parity ^ 1] + (size_t)s * CB : nullptr,
                st.rec + (size_t)s * recPerStream + rec_slot_offset(t, g.B, g.longStep, g.C), sm, 0, 1);
@@ -687,7 +687,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
       if (e->dg.incremental || (mLast + 1 < sd.nBlocks && !(e->dBlocks[sd.blockBase + mLast + 1].flags & kNew))) {
         const BlockRec2 r2 = e->dBlocks2[sd.blockBase + mLast];
         if (r2.lastNew >= slot0)
-          std::memcpy(st.lastInput + (size_t)s * CB, block_input(e->dg, r2, s, slot0, nSlots, e->specIn, st.lastInput), CB * sizeof(cf));
+          std::memcpy(st.lastInput + (size_t)s * CBg, block_input(e->dg, r2, s, slot0, nSlots, e->specIn, st.lastInput) - kGuard, CBg * sizeof(cf));
       }
     }
     st.parity ^= 1;
@@ -1082,7 +1082,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->totalBlocks = (long long)blocks.size();
   e->hostBlocks = blocks;
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
-  const size_t CB = (size_t)g.C * g.B;
+  const size_t CB = (size_t)g.C * g.B, CBg = (size_t)g.C * guard_pitch(g.B);
   // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
   const size_t perSlot = (size_t)S * ((size_t)g.C * g.L * 4 + (size_t)g.B * 12 + CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (e->overlap ? 2 : 1) * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
   const bool autoChunk = chunkBlocks <= 0;
@@ -1146,7 +1146,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   auto &own = e->batchOwned;
   e->dStreams = upload(e, e->hs, own); e->dBlocks = upload(e, blocks, own); e->dBlocks2 = upload(e, blocks2, own);
   e->dWindows = upload(e, windows, own); e->dSeeds = upload(e, seeds, own);
-  e->specIn = dalloc<cf>(allocSlots * 2 * CB, own);
+  e->specIn = dalloc<cf>(allocSlots * 2 * CBg, own);
   e->specOut = dalloc<cf>(allocSlots * CB, own);
   e->dChainProg = dalloc<int>((size_t)std::max(cap, S) + 64, own);
   e->dChainErr = dalloc<int>(1, own);
@@ -1154,10 +1154,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   StateDev &st = e->st;
   const size_t nSlotTot = allocSlots;
   st.outSpec = dalloc<cf>(S * CB, own); st.predE[0] = dalloc<float>(S * CB, own); st.predE[1] = dalloc<float>(S * CB, own);
-  st.lastInput = dalloc<cf>(S * CB, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
+  st.lastInput = dalloc<cf>(S * CBg, own); st.freqEst = dalloc<float>(2 * (size_t)S, own);
   st.ring[0] = dalloc<float>((size_t)S * g.C * g.L, own); st.ring[1] = dalloc<float>((size_t)S * g.C * g.L, own);
   st.frames = dalloc<float>(nSlotTot * g.C * g.L, own); st.ringPar = 0;
-  st.inEnergy = dalloc<float>(nSlotTot * CB, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
+  st.inEnergy = dalloc<float>(nSlotTot * CBg, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
   st.energy = dalloc<float>(nSlotTot * g.B, own); st.smoothed = dalloc<float>(nSlotTot * g.B, own); st.fm = dalloc<float>(nSlotTot * fm_pitch(g.B), own);
   const size_t recFloats = ((allocSlots + 31) / 32 + S) * rec_group_floats(g.B, g.longStep, g.C);
@@ -1171,6 +1171,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
     free_batch(e);
     return e->fail("device allocation failed (streams=%d, chunk=%d)", S, chunkBlocks);
   }
+  dzero(e->specIn, allocSlots * 2 * CBg * sizeof(cf), 0); dzero(st.inEnergy, nSlotTot * CBg * sizeof(float), 0);   // the guard zeros (kGuard)
   e->gate.clear(); e->gateStream.clear(); e->gateCallsTotal = 0; e->gateMaxCalls = 0;
   for (int s = 0; s < S; ++s) {
     const Stream &x = e->streams[s];
@@ -1602,7 +1603,7 @@ void compat_process(int nIn, int nOut) {
         c->ctl->resetBlockProcess();
         const size_t CB = (size_t)C * g.B;
         // every Band cleared: input, prevInput, output (inputEnergy is rewritten by each block)
-        dzero(c->e->st.outSpec, CB * sizeof(cf), 0); dzero(c->e->st.lastInput, CB * sizeof(cf), 0);
+        dzero(c->e->st.outSpec, CB * sizeof(cf), 0); dzero(c->e->st.lastInput, (size_t)C * guard_pitch(g.B) * sizeof(cf), 0);
         std::fill(c->lastCur.begin(), c->lastCur.end(), 0.f);
       }
       if (nIn > 0) {

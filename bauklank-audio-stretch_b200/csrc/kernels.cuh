@@ -83,6 +83,12 @@ struct StateDev {
 };
 
 BS_HD int trunc_i32(float x) { return fabsf(x) < 2147483648.0f ? (int)x : INT32_MIN; }
+// Arrays the term stage interpolates in at data-dependent positions (analysis spectra, the carried input spectrum, input
+// energies) carry two zero elements on either side of every channel: a position outside [0, B) reads as 0 (W#48 9314-9455)
+// without a bounds check -- the index is clamped to [-2, B] and both neighbours then fall on guard zeros.  Channel pitch
+// B + 4; pointers to such arrays point at element 0.  The guards are zeroed once when the arrays are allocated and never written.
+constexpr int kGuard = 2;
+BS_HHD int guard_pitch(int B) { return B + 2 * kGuard; }
 struct alignas(16) f4 { float x, y, z, w; };
 struct alignas(8) f2 { float x, y; };
 
@@ -597,22 +603,18 @@ BS_HD float smooth_pass(float *v, int n, float slew, float s) {
   for (; i < n; ++i) { s = ((v[i] - s) * slew) + s; v[i] = s; }
   return s;
 }
+// interpolation in a guarded array (see kGuard): elements outside [0, B) read as zero
+BS_HD int guard_index(int low, int B) { low = low < -kGuard ? -kGuard : low; return low > B ? B : low; }
 BS_HD cf lerp_c(const cf *a, int B, int low, float fr) {
-  cf lo = {0.f, 0.f}, hi = {0.f, 0.f}, r;
-  if (low >= 0 && low < B) lo = a[low];
-  if (low + 1 >= 0 && low + 1 < B) hi = a[low + 1];
-  r.re = ((hi.re - lo.re) * fr) + lo.re; r.im = ((hi.im - lo.im) * fr) + lo.im;
-  return r;
-}
-BS_HD cf lerp_prev(const cf *a, const cf *rot, int B, int low, float fr) {  // rot == nullptr: no rotation
-  cf lo = {0.f, 0.f}, hi = {0.f, 0.f}, r;
-  if (low >= 0 && low < B) lo = rot ? rot_prev(a[low], rot[low]) : a[low];
-  if (low + 1 >= 0 && low + 1 < B) hi = rot ? rot_prev(a[low + 1], rot[low + 1]) : a[low + 1];
+  const int l = guard_index(low, B);
+  const cf lo = a[l], hi = a[l + 1];
+  cf r;
   r.re = ((hi.re - lo.re) * fr) + lo.re; r.im = ((hi.im - lo.im) * fr) + lo.im;
   return r;
 }
 BS_HD float lerp_f(const float *a, int B, int low, float fr) {
-  float lo = (low >= 0 && low < B) ? a[low] : 0.f, hi = (low + 1 >= 0 && low + 1 < B) ? a[low + 1] : 0.f;
+  const int l = guard_index(low, B);
+  const float lo = a[l], hi = a[l + 1];
   return ((hi - lo) * fr) + lo;
 }
 // minstd_rand: state after n steps from x (x_{k+1} = 48271 x_k mod 2^31-1), by square-and-multiply
@@ -672,9 +674,9 @@ BS_HD void map_energy(const DevGeom &g, const BlockRec rec, const cf *inp, float
   for (int k = tid; k < B; k += nt) {
     float e = 0.f;
     for (int c = 0; c < C; ++c) {
-      const cf v = inp[(size_t)c * B + k];
+      const cf v = inp[(size_t)c * guard_pitch(B) + k];
       const float en = (v.im * v.im) + (v.re * v.re);
-      inEnergy[(size_t)c * B + k] = en;
+      inEnergy[(size_t)c * guard_pitch(B) + k] = en;
       e = e + en;
     }
     if (mapped || formants) energy[k] = e;
@@ -922,7 +924,7 @@ BS_HD void fm_apply(const DevGeom &g, const BlockRec rec, const BlockRec2 rec2, 
       env = (fr * (fm[idx + 1] - lo)) + lo;
     }
     float g2 = env / (metric + 1e-30f); g2 = g2 * g2;
-    for (int c = 0; c < C; ++c) { size_t o = (size_t)c * B + k; inEnergy[o] = g2 * inEnergy[o]; }
+    for (int c = 0; c < C; ++c) { size_t o = (size_t)c * guard_pitch(B) + k; inEnergy[o] = g2 * inEnergy[o]; }
   }
 }
 
@@ -990,9 +992,8 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
   const int NRP = nr_pitch(C), NR = nr_stage(C);   // NR: row stride of the staging rows (padded against bank conflicts)
   const size_t rowStride = rec_row_stride(C);
   const bool isNew = rec.flags & kNew;
-  const cf *prv = isNew ? inPrev : inp;
-  const cf *prvRot = nullptr;   // a new block's previous spectrum was rotated (S1) by the analysis kernel when it was stored
-  const int longStep = g.longStep;
+  const cf *prv = isNew ? inPrev : inp;   // (a new block's previous spectrum was rotated (S1) by the analysis kernel when it was stored)
+  const int longStep = g.longStep, BP = guard_pitch(B);
   const float tf = rec.timeFactor < 0.5f ? 0.5f : rec.timeFactor;
   const float rlo = ((tf > 2.0f) ? 4.0f : 0.0f) - tf, rscale = (tf - rlo) * 0x1p-31f, fLong = (float)longStep;
   const bool randomTF = !(tf <= 2.0f);
@@ -1017,10 +1018,10 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
       int mc = 0; float me = 0.f, pRe = 0.f, pIm = 0.f;
       float enC[2], inRe[2], inIm[2], s5[2][3];   // stereo: the row stays in registers
       for (int c = 0; c < C; ++c) {
-        const float en = lerp_f(inEnergy + (size_t)c * B, B, low, fr) * gpos;
-        const cf in = lerp_c(inp + (size_t)c * B, B, low, fr);
-        const cf pv = lerp_prev(prv + (size_t)c * B, prvRot, B, low, fr);
-        const float prevE = prevMap ? (lerp_f(prevInE + (size_t)c * B, B, lowP, frP) * gP) : prevEState[(size_t)c * B + k];
+        const float en = lerp_f(inEnergy + (size_t)c * BP, B, low, fr) * gpos;
+        const cf in = lerp_c(inp + (size_t)c * BP, B, low, fr);
+        const cf pv = lerp_c(prv + (size_t)c * BP, B, low, fr);
+        const float prevE = prevMap ? (lerp_f(prevInE + (size_t)c * BP, B, lowP, frP) * gP) : prevEState[(size_t)c * B + k];
         if (predEOut) predEOut[(size_t)c * B + k] = en;
         const float tIm = (pv.re * in.im) - (pv.im * in.re), tRe = (pv.im * in.im) + (pv.re * in.re);
         const float dv = ((en > prevE) ? en : prevE) + 1e-15f;
@@ -1039,7 +1040,7 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
         else { ra[9 + 5 * c + 3] = wRe; ra[9 + 5 * c + 4] = wIm; }
       }
       if (CT != 2) ra[8] = __int_as_float_hd(mc);
-      const cf *ic = inp + (size_t)mc * B;
+      const cf *ic = inp + (size_t)mc * BP;
       // S6 terms of the maximum channel (W#48 9458-9873): upward neighbours k-1, k-longStep and downward neighbours k+1,
       // k+longStep (whose predIn is re-interpolated here for channel mc).  With random time factors (timeFactor > 2)
       // the "up" pair and the "down" pair each draw one value, in bin order.
@@ -1144,9 +1145,9 @@ BS_HD void chain_bin(const float *ra, int mc, int k, int B, int ls, cf oPrev, cf
 // input spectrum of block m: the "current" analysis of the most recent block that had a new spectrum
 BS_HD const cf *block_input(const DevGeom &g, const BlockRec2 &r2, int s, long long slot0, int nSlots, const cf *specIn,
                                                  const cf *lastInput) {
-  const size_t CB = (size_t)g.C * g.B;
-  if (r2.lastNew >= slot0) return specIn + (((size_t)s * nSlots + (r2.lastNew - slot0)) * 2 + 0) * CB;
-  return lastInput + (size_t)s * CB;
+  const size_t CB = (size_t)g.C * guard_pitch(g.B);   // guarded arrays: the pointer returned is channel 0's element 0
+  if (r2.lastNew >= slot0) return specIn + (((size_t)s * nSlots + (r2.lastNew - slot0)) * 2 + 0) * CB + kGuard;
+  return lastInput + (size_t)s * CB + kGuard;
 }
 
 #ifdef BS_HOSTEMU

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 for c in $cfgs; do
   extra=""
   [ "$c" = "4" ] && extra="--seconds ${CFG4_SECONDS:-600}"
-  /usr/bin/time -f "cfg$c wall %e s" timeout 900 python bench.py --config $c $extra > gpurun_out/${tag}_cfg$c.json 2> gpurun_out/${tag}_cfg$c.err; echo "cfg$c rc=$?"
+  SECONDS=0; timeout 900 python bench.py --config $c $extra > gpurun_out/${tag}_cfg$c.json 2> gpurun_out/${tag}_cfg$c.err; echo "cfg$c rc=$? wall ${SECONDS}s"
   tail -2 gpurun_out/${tag}_cfg$c.err
   python - <<PY
 import json

@@ -61,7 +61,7 @@ def test_config0_30s_clip_both_drives(env):
     _check(o[0].cpu().numpy(), ref2, "config 0 streaming")
     assert eng.gate_events() == 0
     lat = eng.inputLatency() + eng.outputLatency()
-    assert np.abs(ref2[:, lat:] - clip[:, :ref2.shape[1] - lat]).max() <= 5e-7      # streaming at rate 1 = the input, delayed
+    assert np.abs(ref2[:, lat:] - clip[:, :ref2.shape[1] - lat]).max() <= 2e-6      # streaming at rate 1 = the input, delayed (f32 rounding of a 0.7-amplitude signal)
     eng.close()
 
 
