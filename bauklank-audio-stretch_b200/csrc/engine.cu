@@ -1083,17 +1083,25 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->hostBlocks = blocks;
   if (blocks.empty()) { blocks.push_back(BlockRec{}); blocks2.push_back(BlockRec2{}); windows.resize(2); }
   const size_t CB = (size_t)g.C * g.B, CBg = (size_t)g.C * guard_pitch(g.B);
-  // per slot: specIn (cur+prev) + specOut + inEnergy + map + term records
-  const size_t perSlot = (size_t)S * ((size_t)g.C * g.L * 4 + (size_t)g.B * 12 + CB * sizeof(cf) * 3 + CB * 4 + (size_t)g.B * 8 + (e->overlap ? 2 : 1) * rec_group_floats(g.B, g.longStep, g.C) * 4 / 32);
+  // scratch per chunk slot of one stream: specIn (cur+prev, guarded) + specOut + frames + inEnergy (guarded) + map/energy/smoothed/fm;
+  // the term records come in groups of 32 slots per stream (one chain warp), two buffers with the chunk pipelining
+  const size_t slotBytes = 2 * CBg * sizeof(cf) + CB * sizeof(cf) + (size_t)g.C * g.L * 4 + CBg * 4 + (size_t)g.B * 16 + (size_t)fm_pitch(g.B) * 4 + 16;
+  const size_t groupBytes = (e->overlap ? 2 : 1) * rec_group_floats(g.B, g.longStep, g.C) * 4;
+  auto scratch_for = [&](size_t chunk) { return (size_t)S * (chunk * slotBytes + ((chunk + 31) / 32) * groupBytes); };
+  const size_t perSlot = (size_t)S * (slotBytes + groupBytes / 32);
   const bool autoChunk = chunkBlocks <= 0;
   // scratch budget: 56 GB of the 180, less on a device that has less to give (other engines of the process, other tenants)
   size_t budget = (size_t)56 << 30;
 #ifndef BS_HOSTEMU
-  { size_t freeB = 0, totalB = 0; if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) budget = std::min(budget, freeB / 10 * 7); }
+  { size_t freeB = 0, totalB = 0; if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) budget = std::min(budget, freeB > ((size_t)6 << 30) ? freeB - ((size_t)6 << 30) : freeB / 2); }
 #endif
-  if (autoChunk) {
-    chunkBlocks = (int)std::min<size_t>(256, std::max<size_t>(1, budget / perSlot));
-    if (chunkBlocks > 32) chunkBlocks &= ~31;   // whole warps of the chain wavefront
+  if (autoChunk) {   // whole warps of the chain wavefront (32 blocks per stream) while they fit, down to one block per stream
+    chunkBlocks = 256;
+    while (chunkBlocks > 32 && scratch_for(chunkBlocks) > budget) chunkBlocks -= 32;
+    while (chunkBlocks > 1 && scratch_for(chunkBlocks) > budget) chunkBlocks /= 2;
+    if (scratch_for(chunkBlocks) > budget)
+      return e->fail("not enough device memory for %d streams: %.1f GB of scratch needed for one block per stream, %.1f GB free", S,
+                     scratch_for(chunkBlocks) / 1073741824.0, budget / 1073741824.0);
   }
   if (e->maxBlocks > 0 && chunkBlocks > e->maxBlocks) chunkBlocks = (int)e->maxBlocks;
   e->chunk = chunkBlocks;
@@ -1160,7 +1168,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   st.inEnergy = dalloc<float>(nSlotTot * CBg, own); st.map = dalloc<float>(nSlotTot * g.B * 2, own);
   st.fmAuto = dalloc<float>(nSlotTot * 2, own); st.fmBase = dalloc<float>(nSlotTot, own);
   st.energy = dalloc<float>(nSlotTot * g.B, own); st.smoothed = dalloc<float>(nSlotTot * g.B, own); st.fm = dalloc<float>(nSlotTot * fm_pitch(g.B), own);
-  const size_t recFloats = ((allocSlots + 31) / 32 + S) * rec_group_floats(g.B, g.longStep, g.C);
+  size_t recGroups = 1;   // record groups (32 slots of one stream) the fullest chunk of either list uses
+  for (const auto *list : {&e->chunks, &e->chunksHost})
+    for (const bsb_engine::Chunk &c : *list) recGroups = std::max(recGroups, (size_t)c.nLive * (size_t)((c.nSlots + 31) / 32));
+  const size_t recFloats = recGroups * rec_group_floats(g.B, g.longStep, g.C);
   e->recBuf[0] = dalloc<float>(recFloats, own);
   e->recBuf[1] = (e->overlap && e->chunksHost.size() > 1) ? dalloc<float>(recFloats, own) : nullptr;   // only for chunk pipelining
   st.rec = e->recBuf[0];
