@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,6 +57,19 @@ static void dzero(void *p, size_t n, stream_t) { std::memset(p, 0, n); }
 static void h2d(void *d, const void *h, size_t n, stream_t) { std::memcpy(d, h, n); }
 #else
 typedef cudaStream_t stream_t;
+// A kernel's dynamic shared-memory limit is process-wide state: engines of different geometries live side by side (a batch of
+// mixed presets = two engines), so the limit is only ever raised, never set to what the newest engine happens to need.
+template <class K>
+static cudaError_t raise_smem_limit(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<const void *, size_t> limit;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &cur = limit[(const void *)kernel];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (ce == cudaSuccess) cur = bytes;
+  return ce;
+}
 static bool dev_ok(std::string &err) {
   int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) { err = std::string("no CUDA device: ") + cudaGetErrorString(e); return false; }
@@ -130,8 +145,8 @@ static bool launch_isynth_fast(const DevGeom &g, const DevTables &T, int S, int 
 }
 static bool fast_set_smem() {
   bool ok = true;
-#define X_(LG, OUTER) ok = ok && cudaFuncSetAttribute(analysis_fast_kernel<LG, OUTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<LG, OUTER>()) == cudaSuccess && \
-                       cudaFuncSetAttribute(isynth_fast_kernel<LG, OUTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem_bytes<LG, OUTER>()) == cudaSuccess;
+#define X_(LG, OUTER) ok = ok && raise_smem_limit(analysis_fast_kernel<LG, OUTER>, (size_t)fast_smem_bytes<LG, OUTER>()) == cudaSuccess && \
+                       raise_smem_limit(isynth_fast_kernel<LG, OUTER>, (size_t)fast_smem_bytes<LG, OUTER>()) == cudaSuccess;
   BS_FAST_GEOMS(X_)
 #undef X_
   return ok;
@@ -344,7 +359,7 @@ typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &,
 static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>, launch_chain<3>, launch_chain<4>,
                                                 launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
 template <int C> static cudaError_t chain_attr(size_t smem) {
-  return cudaFuncSetAttribute(chain_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return raise_smem_limit(chain_kernel<C>, (size_t)smem);
 }
 template <int C> static int chain_occ(int threads, size_t smem) {
   int n = 0;
@@ -728,6 +743,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
   const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
   const bool twoStreams = (qF != qB);
   stream_t q = qF;
+  bool launchFailed = false;
   auto span = [&](const char *name, long long units, auto &&launch) {
     const int k = account(name, units);
     if (e->profiling) {
@@ -735,6 +751,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
       cudaEventRecord(a, q); launch(); cudaEventRecord(b, q);
       e->spans.push_back({k, a, b, e->launchRecs.size() - 1});
     } else launch();
+    const cudaError_t ce = cudaGetLastError();   // (a host-side query: says which launch was refused, and why)
+    if (ce != cudaSuccess && !launchFailed) { launchFailed = true; e->fail("launch of %s failed (%d streams x %d slots): %s", name, S, nSlots, cudaGetErrorString(ce)); }
   };
   if (stages & 1) {
     const unsigned nCta = (unsigned)((size_t)S * nSlots);
@@ -787,6 +805,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
       st.ringPar ^= 1;
     }
   }
+  if (launchFailed) return -1;
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return e->fail("kernel launch failed: %s", cudaGetErrorString(ce));
 #endif
@@ -836,11 +855,11 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   cudaEventCreateWithFlags(&e->evFork, cudaEventDisableTiming);
   if (cudaHostAlloc((void **)&e->hChainErr, sizeof(int), cudaHostAllocDefault) == cudaSuccess) *e->hChainErr = 0; else e->hChainErr = nullptr;
   const size_t smA = 4 * (size_t)fft_pitch(g.M) * sizeof(float);
-  if (cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess ||
-      cudaFuncSetAttribute(isynth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA) != cudaSuccess || !fast_set_smem() ||
-      cudaFuncSetAttribute(preterms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
+  if (raise_smem_limit(analysis_kernel, (size_t)smA) != cudaSuccess ||
+      raise_smem_limit(isynth_kernel, (size_t)smA) != cudaSuccess || !fast_set_smem() ||
+      raise_smem_limit(preterms_kernel, (size_t)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
       chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep, chain_warps(g.C, g.longStep, 1 << 20))) != cudaSuccess ||
-      cudaFuncSetAttribute(map_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
+      raise_smem_limit(map_peaks_kernel, (size_t)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
     std::fprintf(stderr, "bauklank_stretch: block %d / interval %d needs more shared memory than one SM has\n", block, interval);
     bsb_destroy(e); return nullptr;
   }

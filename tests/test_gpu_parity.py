@@ -339,3 +339,19 @@ def test_specialised_stft_kernels_on_gpu(channels, block, interval, split, sr, b
         eng.run(); torch.cuda.synchronize()
         outs.append(o[0].cpu().numpy()); eng.close()
     assert cases.compare(outs[0], outs[1])[0] and cases.compare(outs[0], ref)[0]
+
+
+def test_engines_of_different_geometries_side_by_side(bs, golden):
+    """Two engines in one process (a batch of mixed presets = one engine per preset): a later engine with smaller shared-memory
+    needs must not lower the limits the earlier one launches with."""
+    import torch
+    a_case, b_case = cases.CASES["KA5"], cases.CASES["lowlat_8ch_formant_auto"]
+    ca, cb = cases.make_clip(a_case["clip"]), cases.make_clip(b_case["clip"])
+    ea = cases.make_batch(bs, a_case, 2)
+    oa = ea.plan([torch.from_numpy(ca).cuda()], [cases.batch_drive(bs, a_case, ca.shape[1])])
+    eb = cases.make_batch(bs, b_case, 8)            # created after ea: block 960, much smaller kernels' shared memory
+    ob = eb.plan([torch.from_numpy(cb).cuda()], [cases.batch_drive(bs, b_case, cb.shape[1])])
+    ea.run(); eb.run(); ea.run(); torch.cuda.synchronize()
+    assert_matches_golden("KA5", oa[0].cpu().numpy(), golden)
+    assert_matches_golden("lowlat_8ch_formant_auto", ob[0].cpu().numpy(), golden)
+    ea.close(); eb.close()
