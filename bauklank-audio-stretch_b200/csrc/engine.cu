@@ -17,6 +17,7 @@
 #ifndef BS_HOSTEMU
 #include <cuda_runtime.h>
 #include "chain.cuh"
+#include "chain_wide.cuh"
 #endif
 
 namespace bs {
@@ -349,22 +350,33 @@ static int chain_warps(int C, int longStep, int nSlots) {
   return w;
 }
 
+// one or two channels: a lane per block (chain.cuh); three and more: the channels of a block over lanes (chain_wide.cuh)
 template <int C>
 static void launch_chain(int S, int warps, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
                          const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st, int ctas, int *prog, int *err) {
-  chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+  if constexpr (C <= 2) chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+  else chain_wide_kernel<C><<<S * ctas, 32 * kChainWarps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
 }
 typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
                                 long long, int, const cf *, cf *, const StateDev &, int, int *, int *);
 static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>, launch_chain<3>, launch_chain<4>,
                                                 launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
 template <int C> static cudaError_t chain_attr(size_t smem) {
-  return raise_smem_limit(chain_kernel<C>, (size_t)smem);
+  if constexpr (C <= 2) return raise_smem_limit(chain_kernel<C>, (size_t)smem);
+  else return raise_smem_limit(chain_wide_kernel<C>, (size_t)smem);
 }
 template <int C> static int chain_occ(int threads, size_t smem) {
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_kernel<C>, threads, smem) != cudaSuccess) n = 1;
+  cudaError_t ce;
+  if constexpr (C <= 2) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_kernel<C>, threads, smem);
+  else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C>, 32 * kChainWarps, smem);
+  if (ce != cudaSuccess) n = 1;
   return n < 1 ? 1 : n;
+}
+// blocks of a stream one chain CTA walks in a pass, and the shared memory it needs
+static int chain_pass_blocks(int C, int longStep, int nSlots) { return C <= 2 ? 32 * chain_warps(C, longStep, nSlots) : wide_pass_blocks(C); }
+static size_t chain_cta_smem(int C, int longStep, int nSlots) {
+  return C <= 2 ? chain_smem_bytes(C, longStep, chain_warps(C, longStep, nSlots)) : wide_smem_bytes(C, longStep);
 }
 static int chain_resident_ctas(int C, int threads, size_t smem) {   // chain CTAs the whole GPU holds at once
   int dev = 0, sms = 1; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -740,7 +752,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
   const size_t smA = 4 * (size_t)fft_pitch(g.M) * sizeof(float);
   const int chainWarps = chain_warps(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots);
   const size_t smT = preterms_smem_floats(g.C, g.longStep) * sizeof(float);
-  const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_smem_bytes(g.C, g.longStep, chainWarps);
+  const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_cta_smem(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots);
   const bool twoStreams = (qF != qB);
   stream_t q = qF;
   bool launchFailed = false;
@@ -858,7 +870,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   if (raise_smem_limit(analysis_kernel, (size_t)smA) != cudaSuccess ||
       raise_smem_limit(isynth_kernel, (size_t)smA) != cudaSuccess || !fast_set_smem() ||
       raise_smem_limit(preterms_kernel, (size_t)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
-      chain_set_smem(g.C, chain_smem_bytes(g.C, g.longStep, chain_warps(g.C, g.longStep, 1 << 20))) != cudaSuccess ||
+      chain_set_smem(g.C, chain_cta_smem(g.C, g.longStep, 1 << 20)) != cudaSuccess ||
       raise_smem_limit(map_peaks_kernel, (size_t)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
     std::fprintf(stderr, "bauklank_stretch: block %d / interval %d needs more shared memory than one SM has\n", block, interval);
     bsb_destroy(e); return nullptr;
@@ -1062,13 +1074,14 @@ int bsb_rebind(bsb_engine *e, int si, const float *dClip, float *dOut) {
 }
 
 #ifdef BS_HOSTEMU
-static int chain_warps(int, int, int nSlots) { return std::max(1, std::min(8, (nSlots + 31) / 32)); }   // (planning only)
+static int chain_pass_blocks(int C, int, int nSlots) { return C <= 2 ? 32 * std::max(1, std::min(8, (nSlots + 31) / 32)) : (C <= 4 ? 64 : 32); }   // (planning only)
 #endif
-static int chain_capacity(bsb_engine *e, int threads) {   // chain CTAs resident at once on this GPU
+static int chain_capacity(bsb_engine *e) {   // chain CTAs resident at once on this GPU
 #ifdef BS_HOSTEMU
-  (void)e; (void)threads; return 296;
+  (void)e; return 296;
 #else
-  return std::max(1, chain_resident_ctas(e->g.C, threads, chain_smem_bytes(e->g.C, e->g.longStep, threads / 32)));
+  const int threads = e->g.C <= 2 ? chain_pass_blocks(e->g.C, e->g.longStep, 1 << 20) : 32 * kChainWarps;   // (a lane per block / a lane per channel)
+  return std::max(1, chain_resident_ctas(e->g.C, threads, chain_cta_smem(e->g.C, e->g.longStep, 1 << 20)));
 #endif
 }
 
@@ -1126,8 +1139,8 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->chunk = chunkBlocks;
   // slots allocated in all: S x chunk, or -- a small batch of long streams -- as many as the chain kernel can work on at
   // once when every stream's wavefront is relayed across several CTAs
-  const int perPass = 32 * chain_warps(g.C, g.longStep, 1 << 20);
-  const int cap = chain_capacity(e, perPass);
+  const int perPass = chain_pass_blocks(g.C, g.longStep, 1 << 20);
+  const int cap = chain_capacity(e);
   size_t allocSlots = (size_t)S * chunkBlocks;
   const bool relayOk = autoChunk && chunkBlocks >= perPass && !e->dg.incremental;
   if (relayOk) {

@@ -934,7 +934,7 @@ BS_HD void fm_apply(const DevGeom &g, const BlockRec rec, const BlockRec2 rec2, 
 //   0..3 up1.re up1.im upLong.re upLong.im | 4..7 down1.re down1.im downLong.re downLong.im | 8 maxChannel (int bits)
 //   9+5c: energy, predIn.re, predIn.im, chanTwist.re, chanTwist.im            (bin k)
 //   9+5C+3c: S5 twist.re, twist.im, divisor                                   (bin q)
-BS_HHD int nr_floats(int C) { return (9 + 8 * C + 3) & ~3; }
+BS_HHD constexpr int nr_floats(int C) { return (9 + 8 * C + 3) & ~3; }
 BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
 // Storage is "wavefront-major": the slots of a chunk are grouped by 32 (one warp of the chain kernel), and inside a
 // group the rows of the 32 blocks are interleaved along diagonals u = row + lane*lag, so that the 32 rows a warp
@@ -943,7 +943,9 @@ BS_HHD int rec_rows(int B, int longStep) { return B + longStep + 1; }
 // Stereo rows are stored compactly in 24 floats = 96 bytes (three whole 32-byte sectors): the logical row has 25 fields;
 // the max-channel index travels in the sign bit of channel 1's energy (energies are never negative) and the fields
 // behind it move up by one.  Other channel counts keep the logical row, padded to whole 128-byte lines.
-BS_HHD int nr_pitch(int C) { return C == 2 ? 24 : (nr_floats(C) + 31) & ~31; }
+// Three and more channels (chain_wide.cuh reads single fields of the rows of several blocks at once): the smallest pitch that
+// is 8 modulo 32 floats, so that the same field of different blocks' rows falls into different shared-memory banks.
+BS_HHD constexpr int nr_pitch(int C) { return C == 2 ? 24 : (C == 1 ? 32 : ((nr_floats(C) - 8 + 31) & ~31) + 8); }
 // row stride of preterms' staging rows.  Stereo rows are staged in their stored (packed) form, 24 floats in a 28-float
 // pitch: 16-byte stores by consecutive threads then fall into eight different bank groups.
 BS_HHD int nr_stage(int C) { return C == 2 ? 28 : nr_pitch(C) + 4; }
