@@ -17,14 +17,18 @@
 namespace bs {
 
 constexpr int kWideStages = 4;
+constexpr int kWideTile = 16;     // bins per relay tile: a CTA follows its predecessor two tiles behind, and a long single stream is
+                                  // a chain of hundreds of such hand-overs (chain_kernel's 64 would cost 130 steps each)
 BS_HHD constexpr int wide_cpl(int C) { return C <= 4 ? 4 : 8; }                  // lanes per block
 BS_HHD constexpr int wide_bpw(int C) { return 32 / wide_cpl(C); }                // blocks per warp
-BS_HHD constexpr int wide_pass_blocks(int C) { return kChainWarps * wide_bpw(C); }   // blocks per CTA
-BS_HHD size_t wide_smem_bytes(int C, int longStep) {
+BS_HHD constexpr int wide_pass_blocks(int C, int warps) { return warps * wide_bpw(C); }   // blocks per CTA
+BS_HHD size_t wide_smem_bytes(int C, int longStep, int warps) {
   const size_t perWarp = (size_t)kWideStages * wide_bpw(C) * nr_pitch(C) * sizeof(float) + (size_t)(chain_ring_n(longStep) + chain_ring_o(longStep)) * 32 * sizeof(cf);
-  return kChainWarps * perWarp + 2 * (size_t)kChainTile * C * sizeof(cf) + 2 * (size_t)kChainWarps * C * sizeof(cf) +
-         (size_t)kChainWarps * kWideStages * sizeof(unsigned long long) + 16;
+  return warps * perWarp + 2 * (size_t)kWideTile * C * sizeof(cf) + 2 * (size_t)warps * C * sizeof(cf) + (size_t)warps * kWideStages * sizeof(unsigned long long) + 16;
 }
+// Warps per CTA by how many streams there are to fill the GPU with: every warp of a CTA executes every step, so a step of a
+// full CTA costs 8 warps' instructions on one SM, and a lone stream's wavefront is the faster the fewer blocks share an SM.
+BS_HHD int wide_warps_for(int streams) { return streams >= 64 ? 8 : (streams >= 16 ? 4 : 2); }
 
 // the phase sum of S6 at bin k (chain_bin / chain_fast, kernels.cuh / chain.cuh): no division in here, one form for both
 __device__ __forceinline__ void chain_phase(const float *ra, int k, int B, int ls, cf oPrev, cf oLong, cf n1, cf nL, float &phRe, float &phIm) {
@@ -51,9 +55,9 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
                                                                      const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
                                                                      cf *specOut, StateDev st, int ctas, int *prog, int *err) {
   extern __shared__ float4 sm4[];
-  constexpr int CPL = wide_cpl(C), BPW = wide_bpw(C), NRP = nr_pitch(C), SO = 9 + 5 * C, TL = kChainTile, NSTG = kWideStages, nW = kChainWarps;
-  constexpr int perPass = nW * BPW, nThreads = 32 * nW;
+  constexpr int CPL = wide_cpl(C), BPW = wide_bpw(C), NRP = nr_pitch(C), SO = 9 + 5 * C, TL = kWideTile, NSTG = kWideStages;
   constexpr unsigned full = 0xffffffffu;
+  const int nW = blockDim.x >> 5, perPass = nW * BPW, nThreads = blockDim.x;
   __shared__ int ticket;
   if (ctas > 1) {   // relayed launch: logical CTA index = order of arrival (chain.cuh)
     if (threadIdx.x == 0) ticket = atomicAdd(prog, 1);
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
       const cf *src = stOut;
       if (relay) {
         src = specOut + ((size_t)s * nSlots + p0 - 1) * CB;
-        const bool ok = relay_wait(progPrev, min(B, b0 + TL));
+        const bool ok = tid != 0 || relay_wait(progPrev, min(B, b0 + TL));
         if (__syncthreads_or(!ok)) {
           if (tid == 0) { atomicExch(err, 1); __threadfence(); st_release_gpu(progMine, kRelayPoison); }
           return false;
@@ -224,9 +228,8 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
           last = out;
         }
         const bool pub = publishes && validK && ((k & (TL - 1)) == TL - 1 || k == B - 1);
-        if (__any_sync(full, pub)) {    // relay: the last block's output up to bin k is in specOut, every channel of it
-          if (pub) __threadfence();
-          __syncwarp();
+        if (__any_sync(full, pub)) {    // relay: the last block's output up to bin k is in specOut, every channel of it: the warp barrier
+          __syncwarp();                 // orders the channel lanes' stores before lane 0's release (which is cumulative)
           if (pub && cRaw == 0) st_release_gpu(progMine, k + 1);
         }
       }

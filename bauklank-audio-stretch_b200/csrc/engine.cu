@@ -355,7 +355,7 @@ template <int C>
 static void launch_chain(int S, int warps, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
                          const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st, int ctas, int *prog, int *err) {
   if constexpr (C <= 2) chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
-  else chain_wide_kernel<C><<<S * ctas, 32 * kChainWarps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+  else chain_wide_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
 }
 typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
                                 long long, int, const cf *, cf *, const StateDev &, int, int *, int *);
@@ -369,14 +369,15 @@ template <int C> static int chain_occ(int threads, size_t smem) {
   int n = 0;
   cudaError_t ce;
   if constexpr (C <= 2) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_kernel<C>, threads, smem);
-  else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C>, 32 * kChainWarps, smem);
+  else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C>, threads, smem);
   if (ce != cudaSuccess) n = 1;
   return n < 1 ? 1 : n;
 }
 // blocks of a stream one chain CTA walks in a pass, and the shared memory it needs
-static int chain_pass_blocks(int C, int longStep, int nSlots) { return C <= 2 ? 32 * chain_warps(C, longStep, nSlots) : wide_pass_blocks(C); }
-static size_t chain_cta_smem(int C, int longStep, int nSlots) {
-  return C <= 2 ? chain_smem_bytes(C, longStep, chain_warps(C, longStep, nSlots)) : wide_smem_bytes(C, longStep);
+// (wideWarps: warps per CTA of the wide kernel, chosen per batch -- wide_warps_for)
+static int chain_pass_blocks(int C, int longStep, int nSlots, int wideWarps) { return C <= 2 ? 32 * chain_warps(C, longStep, nSlots) : wide_pass_blocks(C, wideWarps); }
+static size_t chain_cta_smem(int C, int longStep, int nSlots, int wideWarps) {
+  return C <= 2 ? chain_smem_bytes(C, longStep, chain_warps(C, longStep, nSlots)) : wide_smem_bytes(C, longStep, wideWarps);
 }
 static int chain_resident_ctas(int C, int threads, size_t smem) {   // chain CTAs the whole GPU holds at once
   int dev = 0, sms = 1; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -501,6 +502,7 @@ struct bsb_engine {
   std::vector<Chunk> chunks, chunksHost;     // device-resident audio / host audio (short first chunk)
   std::vector<long long> needEndHost;
   std::vector<int> order, posOf;   // hs[pos] describes streams[order[pos]]
+  int wideWarps = 8;                                   // warps per CTA of chain_wide_kernel for this batch
   int *dChainProg = nullptr, *dChainErr = nullptr;   // relay of the chain wavefront: ticket + progress words; time-out flag
   int *hChainErr = nullptr;                           // pinned copy of the flag, refreshed behind every run
   std::vector<long long> blockBase;
@@ -750,9 +752,9 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
   }
 #else
   const size_t smA = 4 * (size_t)fft_pitch(g.M) * sizeof(float);
-  const int chainWarps = chain_warps(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots);
+  const int chainWarps = g.C <= 2 ? chain_warps(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots) : e->wideWarps;
   const size_t smT = preterms_smem_floats(g.C, g.longStep) * sizeof(float);
-  const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_cta_smem(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots);
+  const size_t smM = map_smem_floats(g.B) * sizeof(float), smC = chain_cta_smem(g.C, g.longStep, ctas > 1 ? 1 << 20 : nSlots, e->wideWarps);
   const bool twoStreams = (qF != qB);
   stream_t q = qF;
   bool launchFailed = false;
@@ -870,7 +872,7 @@ bsb_engine *bsb_create(int channels, int block, int interval, int split, double 
   if (raise_smem_limit(analysis_kernel, (size_t)smA) != cudaSuccess ||
       raise_smem_limit(isynth_kernel, (size_t)smA) != cudaSuccess || !fast_set_smem() ||
       raise_smem_limit(preterms_kernel, (size_t)(preterms_smem_floats(g.C, g.longStep) * sizeof(float))) != cudaSuccess ||
-      chain_set_smem(g.C, chain_cta_smem(g.C, g.longStep, 1 << 20)) != cudaSuccess ||
+      chain_set_smem(g.C, chain_cta_smem(g.C, g.longStep, 1 << 20, kChainWarps)) != cudaSuccess ||
       raise_smem_limit(map_peaks_kernel, (size_t)(map_smem_floats(g.B) * sizeof(float))) != cudaSuccess) {
     std::fprintf(stderr, "bauklank_stretch: block %d / interval %d needs more shared memory than one SM has\n", block, interval);
     bsb_destroy(e); return nullptr;
@@ -1074,14 +1076,14 @@ int bsb_rebind(bsb_engine *e, int si, const float *dClip, float *dOut) {
 }
 
 #ifdef BS_HOSTEMU
-static int chain_pass_blocks(int C, int, int nSlots) { return C <= 2 ? 32 * std::max(1, std::min(8, (nSlots + 31) / 32)) : (C <= 4 ? 64 : 32); }   // (planning only)
+static int chain_pass_blocks(int C, int, int nSlots, int wideWarps) { return C <= 2 ? 32 * std::max(1, std::min(8, (nSlots + 31) / 32)) : wideWarps * (C <= 4 ? 8 : 4); }   // (planning only)
 #endif
 static int chain_capacity(bsb_engine *e) {   // chain CTAs resident at once on this GPU
 #ifdef BS_HOSTEMU
   (void)e; return 296;
 #else
-  const int threads = e->g.C <= 2 ? chain_pass_blocks(e->g.C, e->g.longStep, 1 << 20) : 32 * kChainWarps;   // (a lane per block / a lane per channel)
-  return std::max(1, chain_resident_ctas(e->g.C, threads, chain_cta_smem(e->g.C, e->g.longStep, 1 << 20)));
+  const int threads = e->g.C <= 2 ? chain_pass_blocks(e->g.C, e->g.longStep, 1 << 20, e->wideWarps) : 32 * e->wideWarps;   // (a lane per block / a lane per channel)
+  return std::max(1, chain_resident_ctas(e->g.C, threads, chain_cta_smem(e->g.C, e->g.longStep, 1 << 20, e->wideWarps)));
 #endif
 }
 
@@ -1139,8 +1141,9 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->chunk = chunkBlocks;
   // slots allocated in all: S x chunk, or -- a small batch of long streams -- as many as the chain kernel can work on at
   // once when every stream's wavefront is relayed across several CTAs
-  const int perPass = chain_pass_blocks(g.C, g.longStep, 1 << 20);
-  const int cap = chain_capacity(e);
+  e->wideWarps = e->dg.incremental ? 1 : (S >= 64 ? 8 : (S >= 16 ? 4 : 2));   // (wide_warps_for; the shim walks one block at a time)
+  const int perPass = chain_pass_blocks(g.C, g.longStep, 1 << 20, e->wideWarps);
+  const int cap = std::min(chain_capacity(e), 1024);   // (more CTAs in flight than that only lengthen the queue of waiting ones)
   size_t allocSlots = (size_t)S * chunkBlocks;
   const bool relayOk = autoChunk && chunkBlocks >= perPass && !e->dg.incremental;
   if (relayOk) {
