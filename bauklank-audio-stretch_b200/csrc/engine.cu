@@ -1301,19 +1301,40 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     e->backUsed[0] = e->backUsed[1] = false;
   }
   std::vector<long long> copied(host ? S : 0, 0), fetched(host ? S : 0, 0);
+  // Host audio: streams whose buffers lie back to back with one pitch, on the device and on the host alike (a batch cut out of
+  // one big allocation -- thousands of streams then move with one strided copy per time chunk instead of one per stream; the
+  // per-call cost of cudaMemcpy2DAsync, not the bus, was what a 4096-stream job waited for).  inRun[s] / outRun[s]: streams
+  // in the run that starts at position s (0: s belongs to an earlier run).
+  std::vector<int> inRun(host ? S : 0, 1), outRun(host ? S : 0, 1);
+  if (host) {
+    for (int s = S - 2; s >= 0; --s) {
+      const StreamDev &a = e->hs[s], &b = e->hs[s + 1];
+      const size_t ci = (size_t)g.C * a.clipLen;
+      if (a.clipLen == b.clipLen && a.clipLen > 0 && b.clip == a.clip + ci && hClips[e->order[s + 1]] == hClips[e->order[s]] + ci && inRun[s + 1] < 16384) {
+        inRun[s] = inRun[s + 1] + 1; inRun[s + 1] = 0;
+      }
+      const size_t co = (size_t)g.C * a.nOut;
+      if (hOuts && a.nOut == b.nOut && a.nOut > 0 && a.nBlocks == b.nBlocks && a.outStride == a.nOut && b.outStride == b.nOut && b.out == a.out + co &&
+          hOuts[e->order[s + 1]] == hOuts[e->order[s]] + co && outRun[s + 1] < 16384) {
+        outRun[s] = outRun[s + 1] + 1; outRun[s + 1] = 0;
+      }
+    }
+  }
   long long i = 0;
   for (const bsb_engine::Chunk &ck : chunks) {
     if (e->maxBlocks <= 0) break;
     const long long slot0 = ck.slot0;
     stream_t qF = two ? e->sFront : q, qB = two ? e->sBack : q;
-    if (host) {   // clip samples first needed by this chunk, all channels of a stream in one strided copy
+    if (host) {   // clip samples first needed by this chunk, all channels of a run of streams in one strided copy
       for (int s = 0; s < S; ++s) {
-        const long long need = needEnd[(size_t)i * S + s], have = copied[s];
+        if (!inRun[s]) continue;
+        long long need = 0, have = e->hs[s].clipLen;
+        for (int r = 0; r < inRun[s]; ++r) { need = std::max(need, needEnd[(size_t)i * S + s + r]); have = std::min(have, copied[s + r]); }
         if (need > have) {
           const StreamDev &d = e->hs[s];
           cudaMemcpy2DAsync((void *)(d.clip + have), (size_t)d.clipLen * sizeof(float), hClips[e->order[s]] + have, (size_t)d.clipLen * sizeof(float),
-                            (size_t)(need - have) * sizeof(float), (size_t)g.C, cudaMemcpyHostToDevice, e->sIn);
-          copied[s] = need;
+                            (size_t)(need - have) * sizeof(float), (size_t)g.C * inRun[s], cudaMemcpyHostToDevice, e->sIn);
+          for (int r = 0; r < inRun[s]; ++r) copied[s + r] = need;
         }
       }
       cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, e->sIn); cudaStreamWaitEvent(qF, ev, 0);
@@ -1321,14 +1342,15 @@ static int run_impl(bsb_engine *e, stream_t q, const float *const *hClips, float
     if (launch_chunk(e, slot0, ck.nSlots, ck.nLive, ck.ctas, qF, qB, two ? (int)(i & 1) : 0, 3, kSynthEmit | kSynthAdd)) return -1;
     if (host && hOuts) {   // the output samples this chunk emitted
       cudaEvent_t ev = e->get_event(); cudaEventRecord(ev, qB); cudaStreamWaitEvent(e->sOut, ev, 0);
-      for (int s = 0; s < S; ++s) {
+      for (int s = 0; s < S; ++s) {   // (a run: same length, same block count -- the same sample range for all of it)
+        if (!outRun[s]) continue;
         const StreamDev &d = e->hs[s];
         const long long n0 = std::min<long long>(slot0 * g.H, d.nOut);
         const long long n1 = std::min<long long>(std::min<long long>(slot0 + ck.nSlots, d.nBlocks) * (long long)g.H, d.nOut);
         if (n1 > n0)
           cudaMemcpy2DAsync(hOuts[e->order[s]] + n0, (size_t)d.nOut * sizeof(float), d.out + n0, (size_t)d.outStride * sizeof(float),
-                            (size_t)(n1 - n0) * sizeof(float), (size_t)g.C, cudaMemcpyDeviceToHost, e->sOut);
-        fetched[s] = std::max(fetched[s], n1);
+                            (size_t)(n1 - n0) * sizeof(float), (size_t)g.C * outRun[s], cudaMemcpyDeviceToHost, e->sOut);
+        for (int r = 0; r < outRun[s]; ++r) fetched[s + r] = std::max(fetched[s + r], n1);
       }
     }
     ++i;

@@ -355,3 +355,30 @@ def test_engines_of_different_geometries_side_by_side(bs, golden):
     assert_matches_golden("KA5", oa[0].cpu().numpy(), golden)
     assert_matches_golden("lowlat_8ch_formant_auto", ob[0].cpu().numpy(), golden)
     ea.close(); eb.close()
+
+
+def test_run_host_with_streams_cut_from_one_allocation(bs):
+    """Host audio for a batch whose streams lie back to back (device and host alike, equal lengths): the per-chunk copies of a
+    run of streams are merged into one strided copy.  Same bits as the device-resident run; a stream of another length in the
+    middle of the batch breaks the run and is copied on its own."""
+    import torch
+    rng = np.random.default_rng(21)
+    n_in, n_out, S = 30000, 26000, 7
+    lens = [(n_in, n_out)] * 3 + [(20000, 9000)] + [(n_in, n_out)] * 3
+    host = torch.from_numpy((0.2 * rng.standard_normal(sum(2 * a for a, _ in lens))).astype(np.float32)).pin_memory()
+    dev_in = torch.zeros_like(host, device="cuda")
+    dev_out = torch.zeros(sum(2 * b for _, b in lens), device="cuda")
+    hout = torch.zeros(dev_out.shape).pin_memory()
+    hc, dc, do, ho, oi, oo = [], [], [], [], 0, 0
+    for a, b in lens:
+        hc.append(host[oi:oi + 2 * a].view(2, a)); dc.append(dev_in[oi:oi + 2 * a].view(2, a)); oi += 2 * a
+        do.append(dev_out[oo:oo + 2 * b].view(2, b)); ho.append(hout[oo:oo + 2 * b].view(2, b)); oo += 2 * b
+    drives = [bs.KioskDrive(b, [bs.segment(rate=0.7 + 0.1 * i, semitones=float(i - 3))]) for i, (_, b) in enumerate(lens)]
+    eng = bs.BatchStretch(2, 48000.0)
+    eng.plan(dc, drives, outputs=do, chunk_blocks=5)
+    eng.run_host(hc, ho)
+    got = hout.clone()
+    dev_in.copy_(host.cuda()); dev_out.zero_()
+    eng.run(); torch.cuda.synchronize()
+    assert torch.equal(got, dev_out.cpu()) and float(got.abs().max()) > 1e-3
+    eng.close()
