@@ -284,60 +284,6 @@ BS_HD void fast_fwd_pack_t(const PackCtx &c, cf *dst, int tid) {
     }
   }
 }
-// The same stage as a walk over SEGMENTS of the packed index (no radix-2 pass): [0, jA) is the second half of the window,
-// [jC, M) the first, and within each the clip covers a contiguous run of pairs when lo and hi are even -- up to seven
-// segments with CTA-uniform bounds, each with a loop body that has nothing left to decide per pair (a pair is read, or is
-// zero, or is in the gap).  Same values as fast_pack_load / fast_pack_finish: a sample that is not there is 0.f, a pair in the
-// gap has t0 = t1 = +0.
-template <int LG, int OUTER, class LOut, bool AL>
-BS_HD void fast_fwd_pack_segments(const PackCtx &c, cf *dst, int tid) {
-  constexpr int M = FastGeom<LG, OUTER>::M, U = 3;
-  auto put = [&](int j, float t0, float t1, const f4 t) {
-    cf z; z.re = (t.z * t0) - (t.w * t1); z.im = (t.w * t0) + (t.z * t1);
-    const int q = j / OUTER, sub = j - q * OUTER;
-    dst[LOut::at(sub, q)] = z;
-  };
-  // mode 0: pairs read from the clip at xs + 2j + ib; 1: live but outside the clip (x = 0); 2: the gap.  Trips of U pairs with
-  // nothing between their loads, then single pairs to the end of the segment.
-  auto load = [&](int j, int ib, int mode, f4 &t, float &x0, float &x1) {
-    t = c.tab[j];
-    x0 = 0.f; x1 = 0.f;
-    if (mode == 0) {
-      const float *px = c.xs + (2 * j + ib);
-      if (AL) { const f2 v = *(const f2 *)px; x0 = v.x; x1 = v.y; } else { x0 = px[0]; x1 = px[1]; }
-    }
-  };
-  auto finish = [&](int j, int mode, const f4 t, float x0, float x1) {
-    if (mode == 2) put(j, 0.f, 0.f, t);
-    else put(j, x0 * t.x, x1 * t.y, t);      // (mode 1: x = 0.f, the product keeps the coefficient's sign like the reference's)
-  };
-  auto run = [&](int j0, int j1, int ib, int mode) {
-    int jb = j0 + tid;
-    for (; jb + (U - 1) * kFastNT < j1; jb += kFastNT * U) {
-      f4 t[U]; float x0[U], x1[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) load(jb + u * kFastNT, ib, mode, t[u], x0[u], x1[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u) finish(jb + u * kFastNT, mode, t[u], x0[u], x1[u]);
-    }
-    for (; jb < j1; jb += kFastNT) {
-      f4 t; float x0, x1;
-      load(jb, ib, mode, t, x0, x1);
-      finish(jb, mode, t, x0, x1);
-    }
-  };
-  const int hi = c.lo + c.span;
-  // second half of the window: pair j holds samples 2j + off, 2j + off + 1; valid iff lo <= 2j + off and 2j + off + 2 <= hi
-  {
-    const int v0 = min(max((c.lo - c.off + 1) >> 1, 0), c.jA), v1 = min(max((hi - c.off) >> 1, v0), c.jA);
-    run(0, v0, c.off, 1); run(v0, v1, c.off, 0); run(v1, c.jA, c.off, 1);
-  }
-  run(c.jA, c.jC, 0, 2);
-  {
-    const int v0 = min(max(c.jC + ((c.lo + 1) >> 1), c.jC), M), v1 = min(max(c.jC + (hi >> 1), v0), M);
-    run(c.jC, v0, -c.cStart, 1); run(v0, v1, -c.cStart, 0); run(v1, M, -c.cStart, 1);
-  }
-}
 template <int LG, int OUTER, class LOut>
 BS_HD void fast_fwd_pack(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *dst, int tid) {
   PackCtx c;
@@ -345,13 +291,6 @@ BS_HD void fast_fwd_pack(const DevGeom &g, const DevTables &T, const float *x, W
   c.off = g.off; c.cStart = g.N - g.off; c.jA = (g.L - g.off) >> 1; c.jC = c.cStart >> 1;
   // pairs start at even window positions: whole pairs are valid or not, and 8-byte aligned, if lo, hi and the start allow
   const bool pair = ((((size_t)c.xs) & 7) == 0) && ((w.lo | w.hi) & 1) == 0;
-#ifndef BS_HOSTEMU
-  if (!FastGeom<LG, OUTER>::lg0 && c.span > 0 && ((w.lo | w.hi) & 1) == 0) {   // whole pairs: the segment walk (the emulation keeps the per-pair form)
-    if ((((size_t)c.xs) & 7) == 0) fast_fwd_pack_segments<LG, OUTER, LOut, true>(c, dst, tid);
-    else fast_fwd_pack_segments<LG, OUTER, LOut, false>(c, dst, tid);
-    return;
-  }
-#endif
   if (c.span <= 0) {   // nothing of the clip in this window: every sample reads as zero (loads go to the table, results are dropped)
     c.xs = (const float *)T.packTab; c.lo = 0; c.span = 1; c.none = true;
     fast_fwd_pack_t<LG, OUTER, LOut, false>(c, dst, tid);
