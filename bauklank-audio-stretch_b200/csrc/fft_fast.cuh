@@ -85,7 +85,7 @@ template <int LG, int OUTER> constexpr size_t fast_smem_bytes() { return 2 * (si
 // CTAs per SM the kernels are compiled for: three where shared memory allows (80 registers), else what fits of 227 KB
 template <int LG, int OUTER> struct FastOcc {
   static constexpr int bySmem = (int)(232448 / (2 * (size_t)FastBuf<LG, OUTER>::elems * sizeof(cf) + 1024));
-  static constexpr int ctas = bySmem >= 3 ? 3 : (bySmem < 1 ? 1 : bySmem);
+  static constexpr int ctas = bySmem >= 4 ? 4 : (bySmem < 1 ? 1 : bySmem);
 };
 
 // ---- the outer stage of one bin: twiddles on sub-transforms 1.., then the DFT across them (outer_stage_t, kernels.cuh)
