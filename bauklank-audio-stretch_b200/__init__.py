@@ -9,5 +9,7 @@ from .batch import BatchStretch, KioskDrive, StreamingDrive, TableDrive, TraceDr
 from .worklet import WorkletTimeline, ControllerMapper  # noqa: F401
 from .engine import StretchEngine  # noqa: F401
 from . import shard  # noqa: F401
+from . import audio  # noqa: F401
+from .audio import decode_audio  # noqa: F401
 
-__all__ = ["StretchEngine", "BatchStretch", "KioskDrive", "StreamingDrive", "TableDrive", "TraceDrive", "trace_events", "WorkletTimeline", "ControllerMapper", "segment", "load_library", "Segment", "EXPORTS", "shard"]
+__all__ = ["StretchEngine", "BatchStretch", "KioskDrive", "StreamingDrive", "TableDrive", "TraceDrive", "trace_events", "WorkletTimeline", "ControllerMapper", "segment", "load_library", "Segment", "EXPORTS", "shard", "audio", "decode_audio"]
