@@ -51,7 +51,9 @@ if os.path.exists(rep):
             "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
             "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
             "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
             "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
             "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct"]
@@ -71,10 +73,11 @@ if os.path.exists(rep):
                 traffic.setdefault(name, []).append(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
             except Exception as e:      # noqa
                 pass
-    print(open(os.path.join(P, out + "_top_kernel_ncu.txt")).read()[:6000])
+    print(open(os.path.join(P, out + "_top_kernel_ncu.txt")).read()[:1500])
     tp = os.path.join(P, "traffic.json")
     cur = json.load(open(tp)) if os.path.exists(tp) else {}
     for k, v in traffic.items():
         cur[k] = max(v)          # the fullest captured launch (a whole chunk)
-    cur["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of the fullest captured launch (one whole chunk: 256 streams x 256 blocks) in the latest ncu --set full capture of each kernel, see profiles/*_top_kernel_ncu.txt"
+    cur["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum of the FIRST launch of each kernel (first time chunk of bench.py's default workload: 256 streams x 256 blocks, every slot used) from the latest ncu --set full capture, see profiles/*_top_kernel_ncu.txt; bench.py pairs it with the event-timed duration and own-model bytes of that same launch"
+    cur["_source"] = tag
     json.dump(cur, open(tp, "w"), indent=1, sort_keys=True)
