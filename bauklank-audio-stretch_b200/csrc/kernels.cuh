@@ -508,6 +508,27 @@ BS_HHD OlaGeom ola_geom(const DevGeom &g, long long slot0, int nv, int mode) {
   o.nv = nv; o.addFrames = (mode & kSynthAdd) ? 1 : 0;
   return o;
 }
+// the per-sample read of four finished samples x..x+3: divided by the window-product sum, stored while the stream is live
+BS_HD void ola_emit_quad(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, int x, const OlaGeom &o, const f4 acc) {
+  const int H = g.H;
+  const long long n = o.ringBase + x;
+  if (n < sd.nLive) {
+    f4 wp;
+    if (n + 3 < g.wpStartLen) wp = *(const f4 *)(T.wpStart + n);
+    else if (n >= g.wpStartLen) { int q = o.wpPhase + x; q -= (q / H) * H; wp = *(const f4 *)(T.wpSteady + q); }
+    else {   // the quad straddles the end of the start-up table
+      float w[4];
+      for (int i = 0; i < 4; ++i) { const long long ni = n + i; int q = o.wpPhase + x + i; q -= (q / H) * H; w[i] = ni < g.wpStartLen ? T.wpStart[ni] : T.wpSteady[q]; }
+      wp.x = w[0]; wp.y = w[1]; wp.z = w[2]; wp.w = w[3];
+    }
+    float *dst = sd.out + (size_t)c * sd.outStride + (n - sd.outBase);
+    const float r0 = acc.x / wp.x, r1 = acc.y / wp.y, r2 = acc.z / wp.z, r3 = acc.w / wp.w;
+    dst[0] = r0;   // (scalar stores: the channel stride of `out` is the stream's length, any alignment)
+    if (n + 1 < sd.nLive) dst[1] = r1;
+    if (n + 2 < sd.nLive) dst[2] = r2;
+    if (n + 3 < sd.nLive) dst[3] = r3;
+  }
+}
 // four consecutive samples at once (x, L, H, the ring base and the frame starts all multiples of 4): same additions in
 // the same order per sample, 16-byte loads, the index divisions shared by the four
 BS_HD void ola_quad(const DevGeom &g, const DevTables &T, const StreamDev &sd, int c, int x, const OlaGeom &o,
@@ -525,25 +546,8 @@ BS_HD void ola_quad(const DevGeom &g, const DevTables &T, const StreamDev &sd, i
       acc.x = acc.x + v.x; acc.y = acc.y + v.y; acc.z = acc.z + v.z; acc.w = acc.w + v.w;
     }
   }
-  if (x < o.xE1) {
-    const long long n = o.ringBase + x;
-    if (n < sd.nLive) {
-      f4 wp;
-      if (n + 3 < g.wpStartLen) wp = *(const f4 *)(T.wpStart + n);
-      else if (n >= g.wpStartLen) { int q = o.wpPhase + x; q -= (q / H) * H; wp = *(const f4 *)(T.wpSteady + q); }
-      else {   // the quad straddles the end of the start-up table
-        float w[4];
-        for (int i = 0; i < 4; ++i) { const long long ni = n + i; int q = o.wpPhase + x + i; q -= (q / H) * H; w[i] = ni < g.wpStartLen ? T.wpStart[ni] : T.wpSteady[q]; }
-        wp.x = w[0]; wp.y = w[1]; wp.z = w[2]; wp.w = w[3];
-      }
-      float *dst = sd.out + (size_t)c * sd.outStride + (n - sd.outBase);
-      const float r0 = acc.x / wp.x, r1 = acc.y / wp.y, r2 = acc.z / wp.z, r3 = acc.w / wp.w;
-      dst[0] = r0;
-      if (n + 1 < sd.nLive) dst[1] = r1;
-      if (n + 2 < sd.nLive) dst[2] = r2;
-      if (n + 3 < sd.nLive) dst[3] = r3;
-    }
-  } else *(f4 *)(ringNew + p) = acc;
+  if (x < o.xE1) ola_emit_quad(g, T, sd, c, x, o, acc);
+  else *(f4 *)(ringNew + p) = acc;
 }
 BS_HHD bool ola_quad_ok(const DevGeom &g) { return (g.L % 4 == 0) && (g.H % 4 == 0) && (g.wpStartLen % 4 == 0); }
 
@@ -756,7 +760,7 @@ BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, 
   float *smE = sm;
   int *cpk = (int *)(smE + B);
   float *peaksG = (float *)(cpk + (B / 2 + 2));
-  int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] monotone flag
+  int *misc = (int *)(peaksG + B);   // [0] nPeaks, [1] cpk non-decreasing, [2] cpk strictly increasing, [3] peaks with cpk < 0
   int *wordCnt = misc + 16;          // run starts per 32-bin word, then their exclusive prefix sum
   uint32_t *mask = (uint32_t *)(wordCnt + (nWords + 2));   // bit k&31 of word k>>5: energy[k] > smoothed[k]
   if (mapped) {
@@ -785,7 +789,7 @@ BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, 
       wordCnt[w] = popc_hd(m & ~((m << 1) | carry));
     }
     BS_SYNC();
-    if (tid == 0) { int acc = 0; for (int w = 0; w < nWords; ++w) { int c = wordCnt[w]; wordCnt[w] = acc; acc += c; } misc[0] = acc; misc[1] = 1; }
+    if (tid == 0) { int acc = 0; for (int w = 0; w < nWords; ++w) { int c = wordCnt[w]; wordCnt[w] = acc; acc += c; } misc[0] = acc; misc[1] = 1; misc[2] = 1; misc[3] = 0; }
     BS_SYNC();
     for (int w = tid; w < nWords; w += nt) {
       const uint32_t m = mask[w], carry = w > 0 ? (mask[w - 1] >> 31) : 0u;
@@ -805,10 +809,37 @@ BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, 
       }
     }
     BS_SYNC();
-    {
-      const int nAll = misc[0];
-      for (int i = tid + 1; i < nAll; i += nt) if (cpk[i] < cpk[i - 1]) misc[1] = 0;   // benign race: every writer stores 0
+    // Section lookup for the (usual) strictly increasing cpk: the peaks' bins are marked in a bit array (the run
+    // mask's storage, free by now) and "first p with cpk[p] > k" becomes a prefix count + a popcount.  Equal or
+    // descending neighbours fall back to the searches below.
+    const int nAll = misc[0];
+    for (int w = tid; w <= nWords; w += nt) mask[w] = 0u;
+    for (int i = tid + 1; i < nAll; i += nt) {   // benign races: every writer stores the same value
+      if (cpk[i] < cpk[i - 1]) misc[1] = 0;
+      if (cpk[i] <= cpk[i - 1]) misc[2] = 0;
     }
+    BS_SYNC();
+    const bool marked = misc[2] != 0;
+    if (marked) {
+      for (int i = tid; i < nAll; i += nt) {
+        const int c = cpk[i];
+        if (c < 0) {
+#ifdef BS_HOSTEMU
+          misc[3] += 1;
+#else
+          atomicAdd(&misc[3], 1);
+#endif
+        } else if (c < B) {
+#ifdef BS_HOSTEMU
+          mask[c >> 5] |= 1u << (c & 31);
+#else
+          atomicOr(&mask[c >> 5], 1u << (c & 31));
+#endif
+        }
+      }
+    }
+    BS_SYNC();
+    if (marked && tid == 0) { int acc = misc[3]; for (int w = 0; w < nWords; ++w) { wordCnt[w] = acc; acc += popc_hd(mask[w]); } }
     BS_SYNC();
     // updateOutputMap: every bin finds the LAST section (in the reference's write order) that covers it
     const int nP = misc[0], mono = misc[1];
@@ -820,7 +851,10 @@ BS_HD void map_peaks(const DevGeom &g, const BlockRec rec, const float *energy, 
         int loLast = trunc_i32(lOut); if (loLast < 0) loLast = 0;
         int sec = -2;  // -2: no writer, -1: last section, 0: first section, p>=1: middle section p
         if (k >= loLast) sec = -1;
-        else if (mono) {
+        else if (marked) {
+          const int lo = wordCnt[k >> 5] + popc_hd(mask[k >> 5] & (0xffffffffu >> (31 - (k & 31))));  // peaks with cpk <= k
+          if (lo < nP) sec = lo;
+        } else if (mono) {
           int lo = 0, hi = nP;  // first p with cpk[p] > k
           while (lo < hi) { int mid = (lo + hi) >> 1; if (cpk[mid] > k) hi = mid; else lo = mid + 1; }
           if (lo < nP) sec = lo;  // lo == 0 -> first section (k < ceil(out0)); lo >= 1 -> between lo-1 and lo
