@@ -72,7 +72,6 @@ _BATCH_SIG = {
     "bsb_set_profiling": (None, [C.c_void_p, C.c_int]),
     "bsb_set_overlap": (None, [C.c_void_p, C.c_int]),
     "bsb_set_fast_fft": (None, [C.c_void_p, C.c_int]),
-    "bsb_set_fft_fma": (None, [C.c_void_p, C.c_int]),
     "bsb_fast_fft_active": (C.c_int, [C.c_void_p]),
     "bsb_kernel_count": (C.c_int, [C.c_void_p]),
     "bsb_kernel_launches": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),

@@ -268,11 +268,6 @@ class BatchStretch:
         """STFT kernels specialised for the preset geometries (default on); off = the run-time-geometry kernels."""
         self.lib.bsb_set_fast_fft(self.h, 1 if on else 0)
 
-    def set_fft_fma(self, on=True):
-        """Tolerance mode (default off): the FMA-contracted build of the specialised STFT kernels.  The output is then
-        within BASELINE's tolerance of the reference (max|err| <= 1e-4, SNR >= 90 dB) instead of bit-identical."""
-        self.lib.bsb_set_fft_fma(self.h, 1 if on else 0)
-
     def fast_fft_active(self):
         return bool(self.lib.bsb_fast_fft_active(self.h))
 

@@ -18,12 +18,12 @@
 #include <cuda_runtime.h>
 #include "chain.cuh"
 #include "chain_wide.cuh"
-#include "fft_kernels.cuh"
 #endif
 
 namespace bs {
 
-// the specialised transforms (fft_fast.cuh), by geometry (BS_FAST_GEOMS)
+// the specialised transforms (fft_fast.cuh), by geometry
+#define BS_FAST_GEOMS(X) X(10, 3) X(9, 5) X(10, 5) X(11, 3) X(9, 1)
 #ifdef BS_HOSTEMU
 static bool fast_analyse_any(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, bool rotate) {
   if (!fast_ok(g)) return false;
@@ -101,8 +101,57 @@ __global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T
   analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x, which == 1);
 }
 
-// (the same two kernels for the preset geometries: fft_kernels.cuh)
-static bool fast_set_smem() { return fast_kernels_set_smem<0>() && fast_kernels_set_smem_fma(); }
+// the same two kernels for the preset geometries (fft_fast.cuh): grid (slot, stream, {cur,prev} x channel) -- no index division
+template <int LG, int OUTER>
+__global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) analysis_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
+                                                                  const Window *windows, long long slot0, int nSlots, cf *specIn) {
+  extern __shared__ __align__(16) float sm[];
+  const int slot = blockIdx.x, s = blockIdx.y, which = blockIdx.z & 1, c = blockIdx.z >> 1;
+  const StreamDev sd = streams[s];
+  const long long m = slot0 + slot;
+  if (m >= sd.nBlocks) return;
+  if (!(blocks[sd.blockBase + m].flags & kNew)) return;
+  const Window w = windows[2 * (sd.blockBase + m) + which];
+  cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * guard_pitch(g.B) + kGuard;
+  fast_analyse<LG, OUTER>(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, (cf *)sm, which == 1);
+}
+template <int LG, int OUTER>
+__global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) isynth_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
+                                                                const cf *specOut, StateDev st) {
+  extern __shared__ __align__(16) float sm[];
+  const int slot = blockIdx.x, s = blockIdx.y, c = blockIdx.z;
+  const StreamDev sd = streams[s];
+  if (slot0 + slot >= sd.nBlocks) return;
+  const size_t blk = (size_t)s * nSlots + slot;
+  fast_synth<LG, OUTER>(g, T, specOut + (blk * g.C + c) * g.B, st.frames + (blk * g.C + c) * g.L, (cf *)sm);
+}
+// launchers: false = no specialised kernel for this geometry (or more streams than a grid dimension holds)
+static bool launch_analysis_fast(const DevGeom &g, const DevTables &T, int S, int nSlots, cudaStream_t q, const StreamDev *streams, const BlockRec *blocks,
+                                 const Window *windows, long long slot0, cf *specIn) {
+  if (!fast_ok(g) || S > 65535) return false;
+#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { \
+    analysis_fast_kernel<LG, OUTER><<<dim3((unsigned)nSlots, (unsigned)S, (unsigned)(2 * g.C)), kFastNT, fast_smem_bytes<LG, OUTER>(), q>>>(g, T, streams, blocks, windows, slot0, nSlots, specIn); return true; }
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return false;
+}
+static bool launch_isynth_fast(const DevGeom &g, const DevTables &T, int S, int nSlots, cudaStream_t q, const StreamDev *streams, long long slot0,
+                               const cf *specOut, const StateDev &st) {
+  if (!fast_ok(g) || S > 65535) return false;
+#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { \
+    isynth_fast_kernel<LG, OUTER><<<dim3((unsigned)nSlots, (unsigned)S, (unsigned)g.C), kFastNT, fast_smem_bytes<LG, OUTER>(), q>>>(g, T, streams, slot0, nSlots, specOut, st); return true; }
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return false;
+}
+static bool fast_set_smem() {
+  bool ok = true;
+#define X_(LG, OUTER) ok = ok && raise_smem_limit(analysis_fast_kernel<LG, OUTER>, (size_t)fast_smem_bytes<LG, OUTER>()) == cudaSuccess && \
+                       raise_smem_limit(isynth_fast_kernel<LG, OUTER>, (size_t)fast_smem_bytes<LG, OUTER>()) == cudaSuccess;
+  BS_FAST_GEOMS(X_)
+#undef X_
+  return ok;
+}
 
 // ---- map stage kernels (see kernels.cuh "map stage")
 struct SlotCtx { StreamDev sd; BlockRec rec; BlockRec2 rec2; size_t slot; bool valid; };
@@ -468,7 +517,6 @@ struct bsb_engine {
   struct LaunchRec { int k; double ms; long long units; };
   std::vector<LaunchRec> launchRecs;   // of the last run, in launch order (ms only while profiling)
   bool profiling = false;
-  bool fftFma = false;            // tolerance mode: the FMA-contracted STFT kernels (bsb_set_fft_fma); never on by itself
   bool fastFft = true;             // specialised STFT kernels where the geometry has them (bsb_set_fast_fft; off = the run-time-geometry path)
   bool overlap = true;             // run the chain/synthesis of chunk i beside the analysis/map/terms of chunk i+1 (two CUDA
                                    // streams).  Gains nothing while every stream is live (each kernel fills the GPU alone), but
@@ -724,8 +772,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     const unsigned nCta = (unsigned)((size_t)S * nSlots);
     if (twoStreams && e->backUsed[buf]) cudaStreamWaitEvent(qF, e->evBack[buf], 0);   // the chain that read this record buffer is done
     span("analysis_kernel", nNew * 2 * g.C, [&] {
-      if (!e->fastFft || !(e->fftFma ? launch_analysis_fast_fma(e->dg, e->dt, S, nSlots, q, e->dStreams, e->dBlocks, e->dWindows, slot0, e->specIn)
-                                     : launch_analysis_fast<0>(e->dg, e->dt, S, nSlots, q, e->dStreams, e->dBlocks, e->dWindows, slot0, e->specIn)))
+      if (!e->fastFft || !launch_analysis_fast(e->dg, e->dt, S, nSlots, q, e->dStreams, e->dBlocks, e->dWindows, slot0, e->specIn))
         analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
     span("map_energy_kernel", nBlk * g.C, [&] {
       map_energy_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
@@ -761,8 +808,7 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
   if (stages & 2) {
     if (synthMode & (kSynthAdd | kSynthFrames))
       span("isynth_kernel", nBlk * g.C, [&] {
-        if (!e->fastFft || !(e->fftFma ? launch_isynth_fast_fma(e->dg, e->dt, S, nSlots, q, e->dStreams, slot0, e->specOut, st)
-                                       : launch_isynth_fast<0>(e->dg, e->dt, S, nSlots, q, e->dStreams, slot0, e->specOut, st)))
+        if (!e->fastFft || !launch_isynth_fast(e->dg, e->dt, S, nSlots, q, e->dStreams, slot0, e->specOut, st))
           isynth_kernel<<<(unsigned)((size_t)S * nSlots * g.C), nt, smA, q>>>(e->dg, e->dt, e->dStreams, slot0, nSlots, e->specOut, st); });
     const long long span_n = (long long)std::min<long long>(nSlots, e->maxBlocksOr1(slot0)) * g.H + g.L;
     if (!(synthMode & kSynthFrames)) {
@@ -1346,7 +1392,6 @@ int bsb_run_host(bsb_engine *e, const float *const *hClips, float *const *hOuts,
 
 void bsb_set_overlap(bsb_engine *e, int on) { e->overlap = on != 0; }
 void bsb_set_fast_fft(bsb_engine *e, int on) { e->fastFft = on != 0; }
-void bsb_set_fft_fma(bsb_engine *e, int on) { e->fftFma = on != 0; }
 int bsb_fast_fft_active(const bsb_engine *e) { return (e->fastFft && fast_ok(e->dg) && e->streams.size() <= 65535) ? 1 : 0; }
 
 int bsb_synchronize(bsb_engine *e) {

@@ -450,8 +450,7 @@ BS_HD void fast_synth(const DevGeom &g, const DevTables &T, const cf *X, float *
   })))
 }
 
-// geometries with a specialised path (every other one takes analyse_window / synth_frame): X(log2 inner, outer)
-#define BS_FAST_GEOMS(X) X(10, 3) X(9, 5) X(10, 5) X(11, 3) X(9, 1)
+// geometries with a specialised path (every other one takes analyse_window / synth_frame)
 BS_HHD bool fast_geometry(int inner, int outer) {
   return (inner == 1024 && outer == 3) || (inner == 512 && outer == 5) || (inner == 1024 && outer == 5) || (inner == 2048 && outer == 3) ||
          (inner == 512 && outer == 1);

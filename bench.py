@@ -494,8 +494,6 @@ def main_gpu(args):
         eng = bs.BatchStretch(ch, grp["sr"], **grp["kw"])
         if args.no_fast_fft:
             eng.set_fast_fft(False)
-        if args.fft_fma:
-            eng.set_fft_fma(True)
         eng.plan(clips, [make_drive(bs, s) for s in ss], outputs=outs)
         engines.append((name, eng, ss, clips, outs, clips_all, outs_all))
     plan_s = time.perf_counter() - t0
@@ -693,7 +691,7 @@ def main_gpu(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config == 3 else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, io_bytes),
                 "audio_seconds_out_per_step": out_tot, "audio_seconds_in_per_step": in_tot,
-                "x_realtime_per_gpu": value / world, "plan_seconds": plan_s, "fast_fft": bool(eng0.fast_fft_active()), "fft_fma": bool(args.fft_fma),
+                "x_realtime_per_gpu": value / world, "plan_seconds": plan_s, "fast_fft": bool(eng0.fast_fft_active()),
                 "blocks_per_rank": {"min": -neg_blocks_min, "max": blocks_max},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_tot), "d2h_bytes_per_step": int(d2h_tot), "ms_per_step": ms2 / e2e_steps,
                         "outputs_left_on_device": {"value": out_tot * e2e_steps / (ms3 / 1e3), "ms_per_step": ms3 / e2e_steps,
@@ -719,8 +717,6 @@ def _parser():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--parity-seconds", type=float, default=30.0, help="output seconds per sample stream checked against the CPU engine")
-    ap.add_argument("--fft-fma", action="store_true",
-                    help="tolerance mode: the FMA-contracted STFT kernels (output within 1e-4 / 90 dB of the reference, not bit-identical)")
     ap.add_argument("--no-fast-fft", action="store_true", help="A/B: the run-time-geometry STFT kernels instead of the specialised ones")
     return ap
 

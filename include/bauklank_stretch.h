@@ -157,11 +157,6 @@ void bsb_set_overlap(bsb_engine *e, int on);
  * configuration uses.  Results are identical either way (same butterflies, same order). */
 void bsb_set_fast_fft(bsb_engine *e, int on);
 int bsb_fast_fft_active(const bsb_engine *e);   /* 1 = this engine's runs use the specialised STFT kernels */
-/* Tolerance mode, off by default: run the specialised STFT kernels in their FMA-contracted build (fft_fma.cu, nvcc -fmad=true).
- * The output is then NOT bit-identical to the reference; it is held to BASELINE's tolerance instead (max|err| <= 1e-4 and
- * SNR >= 90 dB against the reference: tests/test_gpu_parity.py, numbers in DESIGN.md).  No effect on geometries without a
- * specialised kernel, on the compat shim, or with bsb_set_fast_fft(e, 0). */
-void bsb_set_fft_fma(bsb_engine *e, int on);
 int bsb_kernel_count(const bsb_engine *e);
 int bsb_kernel_stat(bsb_engine *e, int i, const char **name, double *ms, long long *launches, long long *units);
 /* the launches of kernel i one by one (profiling on): device ms and units of up to `max` launches in launch order; returns
