@@ -8,6 +8,10 @@
 //   - takes the four neighbour values of the chain from the lane of the maximum channel by shuffle and computes the
 //     phase sum and the maximum channel's output redundantly (same operations on the same values in every lane),
 //   - derives its own channel's output from it.
+// SPLIT (few streams: a lone stream's time is blocks x lag x the time of ONE step): S5 at bin q and S6 at bin k of a step
+// both depend only on the step before -- S6(t) reads the S5 value of bin k + longStep = q - 1, written in step t - 1 -- so
+// they run side by side on twice the warps: warps [0, nW) do S6, warps [nW, 2 nW) S5 of the same (block, channel) lanes,
+// exchanging through the shared-memory rings under the barrier every step already has.
 // A warp holds 32 / CPL blocks, a CTA of 8 warps 32 or 64: one or two record groups.  The rows a warp needs in a step
 // (its blocks' rows of one diagonal) are contiguous and arrive by cp.async.bulk into a ring of kWideStages stages; the
 // row pitch is 8 (mod 32) floats so that the lanes' field reads of different blocks fall into different banks.
@@ -16,9 +20,21 @@
 
 namespace bs {
 
-constexpr int kWideStages = 4;
-constexpr int kWideTile = 16;     // bins per relay tile: a CTA follows its predecessor two tiles behind, and a long single stream is
-                                  // a chain of hundreds of such hand-overs (chain_kernel's 64 would cost 130 steps each)
+#ifndef BS_WIDE_STAGES
+#define BS_WIDE_STAGES 4
+#endif
+constexpr int kWideStages = BS_WIDE_STAGES;
+#ifndef BS_WIDE_TILE
+#define BS_WIDE_TILE 8
+#endif
+#ifndef BS_WIDE_AHEAD
+#define BS_WIDE_AHEAD 2
+#endif
+constexpr int kWideTile = BS_WIDE_TILE;    // bins per relay tile.  A long single stream is a chain of hundreds of hand-overs from CTA to
+constexpr int kWideAhead = BS_WIDE_AHEAD;  // CTA, and a follower runs kWideTile + kWideAhead bins behind its predecessor where blocks inside
+                                           // a CTA are lag = longStep + 2 apart: a tile is asked for kWideAhead steps before its first bin is
+                                           // due (time for the poll + the copy), and the predecessor has to have finished it by then
+static_assert(kWideTile >= 4 && (kWideTile & (kWideTile - 1)) == 0 && kWideAhead >= 1 && kWideAhead < kWideTile, "relay tile");
 BS_HHD constexpr int wide_cpl(int C) { return C <= 4 ? 4 : 8; }                  // lanes per block
 BS_HHD constexpr int wide_bpw(int C) { return 32 / wide_cpl(C); }                // blocks per warp
 BS_HHD constexpr int wide_pass_blocks(int C, int warps) { return warps * wide_bpw(C); }   // blocks per CTA
@@ -26,9 +42,10 @@ BS_HHD size_t wide_smem_bytes(int C, int longStep, int warps) {
   const size_t perWarp = (size_t)kWideStages * wide_bpw(C) * nr_pitch(C) * sizeof(float) + (size_t)(chain_ring_n(longStep) + chain_ring_o(longStep)) * 32 * sizeof(cf);
   return warps * perWarp + 2 * (size_t)kWideTile * C * sizeof(cf) + 2 * (size_t)warps * C * sizeof(cf) + (size_t)warps * kWideStages * sizeof(unsigned long long) + 16;
 }
-// Warps per CTA by how many streams there are to fill the GPU with: every warp of a CTA executes every step, so a step of a
-// full CTA costs 8 warps' instructions on one SM, and a lone stream's wavefront is the faster the fewer blocks share an SM.
-BS_HHD int wide_warps_for(int streams) { return streams >= 64 ? 8 : (streams >= 16 ? 4 : 2); }
+// few streams (2 or 4 warps of blocks per CTA): S5 and S6 on separate warps, twice the threads
+BS_HHD constexpr bool wide_split(int warps) { return warps <= 4; }
+BS_HHD constexpr int wide_threads(int warps) { return (wide_split(warps) ? 64 : 32) * warps; }
+// (warps of blocks per CTA: wide_warps_for, kernels.cuh)
 
 // the phase sum of S6 at bin k (chain_bin / chain_fast, kernels.cuh / chain.cuh): no division in here, one form for both
 __device__ __forceinline__ void chain_phase(const float *ra, int k, int B, int ls, cf oPrev, cf oLong, cf n1, cf nL, float &phRe, float &phIm) {
@@ -50,21 +67,23 @@ __device__ __forceinline__ void chain_phase(const float *ra, int k, int B, int l
   }
 }
 
-template <int C>
+template <int C, bool SPLIT>
 __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
                                                                      const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn,
                                                                      cf *specOut, StateDev st, int ctas, int *prog, int *err) {
   extern __shared__ float4 sm4[];
   constexpr int CPL = wide_cpl(C), BPW = wide_bpw(C), NRP = nr_pitch(C), SO = 9 + 5 * C, TL = kWideTile, NSTG = kWideStages;
   constexpr unsigned full = 0xffffffffu;
-  const int nW = blockDim.x >> 5, perPass = nW * BPW, nThreads = blockDim.x;
+  const int nW = SPLIT ? blockDim.x >> 6 : blockDim.x >> 5, perPass = nW * BPW, nThreads = blockDim.x;
   __shared__ int ticket;
   if (ctas > 1) {   // relayed launch: logical CTA index = order of arrival (chain.cuh)
     if (threadIdx.x == 0) ticket = atomicAdd(prog, 1);
     __syncthreads();
   }
   const int bid = ctas > 1 ? ticket : (int)blockIdx.x;
-  const int s = bid / ctas, cta = bid - s * ctas, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+  const int s = bid / ctas, cta = bid - s * ctas, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const bool roleS5 = SPLIT && (int)(threadIdx.x >> 5) >= nW, roleS6 = !roleS5;   // (without SPLIT every warp does both)
+  const int warp = (int)(threadIdx.x >> 5) - (roleS5 ? nW : 0);
   const int bl = lane / CPL, cRaw = lane % CPL, c = cRaw < C ? cRaw : C - 1;   // idle lanes (C < CPL) shadow the last channel, store nothing
   const bool chOK = cRaw < C;
   const int jb = warp * BPW + bl;                            // this lane's block within the CTA's pass
@@ -90,6 +109,9 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
   const size_t CB = (size_t)C * B;
   const cf *specRot = T.specRot;
   const int handSrc = warp > 0 ? warp - 1 : 0;
+  // SPLIT: the S5 lane of (block, channel) reads the previous block's output of that channel out of ITS ring: CPL lanes below, or
+  // the last block of the warp below
+  const cf *ringOPrev = bl > 0 ? ringO - CPL : (warp > 0 ? ringO - (size_t)(RN + RO) * 32 + (32 - CPL) : ringO);
   for (int i = tid; i < nW * (RN + RO) * 32; i += nThreads) { cf z; z.re = z.im = 0.f; rings[i] = z; }
   for (int i = tid; i < 2 * C * TL + 2 * nW * C; i += nThreads) { cf z; z.re = z.im = 0.f; tile[i] = z; }
   if (lane == 0) { for (int i = 0; i < NSTG; ++i) mbar_init(bars + i, 1); mbar_fence_init(); }
@@ -116,7 +138,7 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
     auto has_rows = [&](int t) { const int u = t + OA - uOff; return warpLive && u >= 0 && u < nDiag; };
     auto fetch = [&](int t) {
       if (has_rows(t) && t <= tEnd) {   // (nothing is fetched that no step will wait for)
-        if (lane == 0) {
+        if (lane == 0 && (SPLIT ? roleS5 : true)) {   // (the S5 twin has the slack: issuing a copy costs some 400 cycles)
           const int u = t + OA - uOff;
           unsigned long long *bar = bars + (nIssued % NSTG);
           mbar_expect_tx(bar, BPW * NRP * 4);
@@ -145,7 +167,7 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
       }
       return true;
     };
-    if (!request_tile(0) || !request_tile(1)) { cp_async_commit(); cp_async_wait<0>(); return; }
+    if (!request_tile(0)) { cp_async_commit(); cp_async_wait<0>(); return; }
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
@@ -156,13 +178,14 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
     { const int r = OA - jb * D; if (r >= 1 && r < B) rot = specRot[r]; }
 
     for (int t = 0; t <= tEnd; ++t) {
-      fetch(t + NSTG - 1);                                   // its stage was last read in step t-1 (the __syncwarp below)
+      if (!SPLIT) fetch(t + NSTG - 1);                       // its stage was last read in step t-1 (the __syncwarp below)
       cf rotNxt; rotNxt.re = rotNxt.im = 0.f;
-      { const int r = t + 1 + OA - jb * D; if (r >= 1 && r < B) rotNxt = specRot[r]; }
+      if (!SPLIT || roleS5) { const int r = t + 1 + OA - jb * D; if (r >= 1 && r < B) rotNxt = specRot[r]; }
       const int q0 = t + OA;
-      if (q0 > TL && (q0 % TL) == 1) { const bool ok = request_tile(q0 / TL + 1); cp_async_commit(); if (!ok) return; }
+      if ((q0 % TL) == TL - kWideAhead) { const bool ok = request_tile(q0 / TL + 1); cp_async_commit(); if (!ok) return; }
       if ((q0 % TL) == TL - 1) cp_async_wait<0>();
       __syncthreads();
+      if (SPLIT) fetch(t + NSTG - 1);                        // (both twins have read the stage of step t-1: the barrier)
       const int tau = t - jb * D, q = tau + OA, k = tau - ls;
       const bool validQ = active && q >= 1 && q < B, validK = active && k >= 0 && k < B;
       const float *row = stage + bl * NRP;
@@ -171,24 +194,39 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
         row += (size_t)(nWaited % NSTG) * BPW * NRP;
         ++nWaited;
       }
-      if (__any_sync(full, validQ || validK)) {
-        // ---- S1 + S5 of this lane's channel at bin q: the previous block's output comes from CPL lanes below, the warp below, or the tile
-        const int qc = q & (2 * TL - 1);
-        cf o;
-        o.re = __shfl_up_sync(full, last.re, CPL);
-        o.im = __shfl_up_sync(full, last.im, CPL);
-        const cf oT = tile[((size_t)(qc / TL) * C + c) * TL + (qc % TL)];
-        const cf oH = hand[((size_t)((t & 1) ^ 1) * nW + handSrc) * C + c];
-        if (bl == 0) o = (warp == 0) ? oT : oH;
-        const float tRe = row[SO + 3 * c], tIm = row[SO + 3 * c + 1], dv = row[SO + 3 * c + 2];
-        bool slowQ = false;
-        cf n5 = s5_fast(o, isNew, rot, tRe, tIm, dv, slowQ);
-        if (validQ && slowQ) n5 = s5_bin(o, isNew, rot, tRe, tIm, dv);
+      if (SPLIT && roleS5) {
+        // ---- S1 + S5 of this lane's channel at bin q, on its own warp: the previous block's output is in that block's ring (or the tile)
+        if (__any_sync(full, validQ)) {
+          const int qc = q & (2 * TL - 1);
+          const cf oT = tile[((size_t)(qc / TL) * C + c) * TL + (qc % TL)];
+          cf o = ringOPrev[(size_t)(q & RMO) * 32];
+          if (bl == 0 && warp == 0) o = oT;
+          const float tRe = row[SO + 3 * c], tIm = row[SO + 3 * c + 1], dv = row[SO + 3 * c + 2];
+          bool slowQ = false;
+          cf n5 = s5_fast(o, isNew, rot, tRe, tIm, dv, slowQ);
+          if (validQ && slowQ) n5 = s5_bin(o, isNew, rot, tRe, tIm, dv);
+          if (validQ) ringN[(size_t)(q & RMN) * 32] = n5;
+        }
+      } else if (__any_sync(full, SPLIT ? validK : (validQ || validK))) {
+        if (!SPLIT) {
+          // ---- S1 + S5 of this lane's channel at bin q: the previous block's output comes from CPL lanes below, the warp below, or the tile
+          const int qc = q & (2 * TL - 1);
+          cf o;
+          o.re = __shfl_up_sync(full, last.re, CPL);
+          o.im = __shfl_up_sync(full, last.im, CPL);
+          const cf oT = tile[((size_t)(qc / TL) * C + c) * TL + (qc % TL)];
+          const cf oH = hand[((size_t)((t & 1) ^ 1) * nW + handSrc) * C + c];
+          if (bl == 0) o = (warp == 0) ? oT : oH;
+          const float tRe = row[SO + 3 * c], tIm = row[SO + 3 * c + 1], dv = row[SO + 3 * c + 2];
+          bool slowQ = false;
+          cf n5 = s5_fast(o, isNew, rot, tRe, tIm, dv, slowQ);
+          if (validQ && slowQ) n5 = s5_bin(o, isNew, rot, tRe, tIm, dv);
+          if (validQ) ringN[(size_t)(q & RMN) * 32] = n5;    // (slot q = k + ls + 1: not one of the two read below)
+        }
         // ---- S6 at bin k: the four neighbour values of the maximum channel, from its lane
         const int mc = validK ? __float_as_int(row[8]) : 0;
         const int src = bl * CPL + mc;
         const cf myLong = ringO[(size_t)((k - ls) & RMO) * 32], myN1 = ringN[(size_t)((k + 1) & RMN) * 32], myNL = ringN[(size_t)((k + ls) & RMN) * 32];
-        if (validQ) ringN[(size_t)(q & RMN) * 32] = n5;
         cf oPrev, oLong, n1, nL;
         oPrev.re = __shfl_sync(full, last.re, src); oPrev.im = __shfl_sync(full, last.im, src);
         oLong.re = __shfl_sync(full, myLong.re, src); oLong.im = __shfl_sync(full, myLong.im, src);
@@ -223,7 +261,7 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
           if (chOK) {
             if (k & 1) __stcs(reinterpret_cast<float4 *>(so + k - 1), make_float4(last.re, last.im, out.re, out.im));
             if (isLast) stOut[(size_t)c * B + k] = out;
-            if (bl == BPW - 1) hand[((size_t)(t & 1) * nW + warp) * C + c] = out;
+            if (!SPLIT && bl == BPW - 1) hand[((size_t)(t & 1) * nW + warp) * C + c] = out;
           }
           last = out;
         }

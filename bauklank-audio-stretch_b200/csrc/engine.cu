@@ -355,7 +355,8 @@ template <int C>
 static void launch_chain(int S, int warps, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
                          const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st, int ctas, int *prog, int *err) {
   if constexpr (C <= 2) chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
-  else chain_wide_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+  else if (wide_split(warps)) chain_wide_kernel<C, true><<<S * ctas, wide_threads(warps), smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+  else chain_wide_kernel<C, false><<<S * ctas, wide_threads(warps), smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
 }
 typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &, const DevTables &, const StreamDev *, const BlockRec *, const BlockRec2 *,
                                 long long, int, const cf *, cf *, const StateDev &, int, int *, int *);
@@ -363,13 +364,17 @@ static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>
                                                 launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
 template <int C> static cudaError_t chain_attr(size_t smem) {
   if constexpr (C <= 2) return raise_smem_limit(chain_kernel<C>, (size_t)smem);
-  else return raise_smem_limit(chain_wide_kernel<C>, (size_t)smem);
+  else {
+    const cudaError_t ce = raise_smem_limit(chain_wide_kernel<C, true>, (size_t)smem);
+    return ce != cudaSuccess ? ce : raise_smem_limit(chain_wide_kernel<C, false>, (size_t)smem);
+  }
 }
-template <int C> static int chain_occ(int threads, size_t smem) {
+template <int C> static int chain_occ(int threads, size_t smem, bool wideSplit) {
   int n = 0;
   cudaError_t ce;
   if constexpr (C <= 2) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_kernel<C>, threads, smem);
-  else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C>, threads, smem);
+  else if (wideSplit) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C, true>, threads, smem);
+  else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C, false>, threads, smem);
   if (ce != cudaSuccess) n = 1;
   return n < 1 ? 1 : n;
 }
@@ -379,13 +384,13 @@ static int chain_pass_blocks(int C, int longStep, int nSlots, int wideWarps) { r
 static size_t chain_cta_smem(int C, int longStep, int nSlots, int wideWarps) {
   return C <= 2 ? chain_smem_bytes(C, longStep, chain_warps(C, longStep, nSlots)) : wide_smem_bytes(C, longStep, wideWarps);
 }
-static int chain_resident_ctas(int C, int threads, size_t smem) {   // chain CTAs the whole GPU holds at once
+static int chain_resident_ctas(int C, int threads, size_t smem, bool wideSplit) {   // chain CTAs the whole GPU holds at once
   int dev = 0, sms = 1; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int occ;
   switch (C) {
-    case 1: occ = chain_occ<1>(threads, smem); break; case 2: occ = chain_occ<2>(threads, smem); break; case 3: occ = chain_occ<3>(threads, smem); break;
-    case 4: occ = chain_occ<4>(threads, smem); break; case 5: occ = chain_occ<5>(threads, smem); break; case 6: occ = chain_occ<6>(threads, smem); break;
-    case 7: occ = chain_occ<7>(threads, smem); break; default: occ = chain_occ<8>(threads, smem); break;
+    case 1: occ = chain_occ<1>(threads, smem, wideSplit); break; case 2: occ = chain_occ<2>(threads, smem, wideSplit); break; case 3: occ = chain_occ<3>(threads, smem, wideSplit); break;
+    case 4: occ = chain_occ<4>(threads, smem, wideSplit); break; case 5: occ = chain_occ<5>(threads, smem, wideSplit); break; case 6: occ = chain_occ<6>(threads, smem, wideSplit); break;
+    case 7: occ = chain_occ<7>(threads, smem, wideSplit); break; default: occ = chain_occ<8>(threads, smem, wideSplit); break;
   }
   return sms * occ;
 }
@@ -1082,8 +1087,8 @@ static int chain_capacity(bsb_engine *e) {   // chain CTAs resident at once on t
 #ifdef BS_HOSTEMU
   (void)e; return 296;
 #else
-  const int threads = e->g.C <= 2 ? chain_pass_blocks(e->g.C, e->g.longStep, 1 << 20, e->wideWarps) : 32 * e->wideWarps;   // (a lane per block / a lane per channel)
-  return std::max(1, chain_resident_ctas(e->g.C, threads, chain_cta_smem(e->g.C, e->g.longStep, 1 << 20, e->wideWarps)));
+  const int threads = e->g.C <= 2 ? chain_pass_blocks(e->g.C, e->g.longStep, 1 << 20, e->wideWarps) : wide_threads(e->wideWarps);   // (a lane per block / per channel)
+  return std::max(1, chain_resident_ctas(e->g.C, threads, chain_cta_smem(e->g.C, e->g.longStep, 1 << 20, e->wideWarps), e->g.C > 2 && wide_split(e->wideWarps)));
 #endif
 }
 
@@ -1141,7 +1146,7 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   e->chunk = chunkBlocks;
   // slots allocated in all: S x chunk, or -- a small batch of long streams -- as many as the chain kernel can work on at
   // once when every stream's wavefront is relayed across several CTAs
-  e->wideWarps = e->dg.incremental ? 1 : (S >= 64 ? 8 : (S >= 16 ? 4 : 2));   // (wide_warps_for; the shim walks one block at a time)
+  e->wideWarps = e->dg.incremental ? 1 : wide_warps_for(S);   // (the shim walks one block at a time)
   const int perPass = chain_pass_blocks(g.C, g.longStep, 1 << 20, e->wideWarps);
   const int cap = std::min(chain_capacity(e), 1024);   // (more CTAs in flight than that only lengthen the queue of waiting ones)
   size_t allocSlots = (size_t)S * chunkBlocks;

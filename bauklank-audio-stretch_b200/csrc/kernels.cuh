@@ -998,6 +998,13 @@ BS_HD void unpack2_row(const float *phys, float *logical) {            // 24 phy
   logical[14] = __int_as_float_hd(__float_as_int_hd(phys[13]) & 0x7fffffff);
 }
 BS_HHD int chain_lag(int longStep) { return longStep + 2; }
+// Three and more channels (chain_wide.cuh): warps of blocks per chain CTA, by how many streams there are to fill the GPU with.
+// Every warp of a CTA executes every step, so a step of a full CTA costs 8 warps' instructions on one SM; with few streams the
+// CTAs are smaller, and their S5 / S6 halves run on separate warps (wide_split).
+#ifndef BS_WIDE_WARPS_MIN
+#define BS_WIDE_WARPS_MIN 4
+#endif
+BS_HHD int wide_warps_for(int streams) { return streams >= 64 ? 8 : (streams >= 16 ? 4 : BS_WIDE_WARPS_MIN); }
 BS_HHD size_t rec_group_floats(int B, int longStep, int C) { return (size_t)(rec_rows(B, longStep) + 31 * chain_lag(longStep)) * 32 * nr_pitch(C); }
 BS_HHD size_t rec_row_stride(int C) { return (size_t)32 * nr_pitch(C); }
 // row 0 of chunk slot `slot` of a stream whose chunk records start at `base`; row r is rec_row_stride floats further per row
