@@ -382,3 +382,38 @@ def test_run_host_with_streams_cut_from_one_allocation(bs):
     eng.run(); torch.cuda.synchronize()
     assert torch.equal(got, dev_out.cpu()) and float(got.abs().max()) > 1e-3
     eng.close()
+
+
+@pytest.mark.parametrize("channels,n_streams", [(8, 3), (6, 5), (3, 20), (4, 70)])
+def test_wide_chain_relay_on_ragged_batches(channels, n_streams, bs):
+    """chain_wide_kernel with the wavefront of a stream relayed across CTAs (automatic chunking), for the batch sizes that pick
+    its three shapes -- S5/S6 on separate warps with 4 warps of blocks (< 64 streams), one warp doing both with 8 (>= 64) -- on
+    streams of different lengths: against the same batch run in fixed 40-block chunks (no relay; that path is pinned to the
+    oracle by the tests above), and two of the streams against the CPU oracle directly."""
+    import torch
+    rng = np.random.default_rng(100 * channels + n_streams)
+    sr, blk = 48000, (960, 240, 1)
+    clips, cs = [], []
+    for i in range(n_streams):
+        n_in = int((0.5 + 0.9 * rng.random()) * sr)
+        x = (0.15 * rng.standard_normal((channels, n_in))).astype(np.float32)
+        x[i % channels] *= 3.0                                    # the maximum channel differs from stream to stream
+        rate = float(rng.choice([0.6, 0.9, 1.0, 1.5]))
+        clips.append(x)
+        cs.append(dict(drive="kiosk", sr=sr, n_out=int(0.9 * n_in / rate), block=blk, seed=3 + i,
+                       segments=[cases.seg(rate=rate, semitones=float(rng.integers(-5, 6)), formant_semitones=float(rng.integers(-2, 3)),
+                                           formant_compensation=bool(i % 2), formant_base_hz=0.0 if i % 3 else 200.0)]))
+    runs = []
+    for chunk in (0, 40):
+        eng = bs.BatchStretch(channels, sr, block_samples=blk[0], interval_samples=blk[1], split_computation=True)
+        o = eng.plan([torch.from_numpy(x).cuda() for x in clips], [cases.batch_drive(bs, c, x.shape[1]) for c, x in zip(cs, clips)],
+                     chunk_blocks=chunk)
+        eng.run(); torch.cuda.synchronize()
+        runs.append([t.cpu().numpy() for t in o]); eng.close()
+    for a, b in zip(*runs):
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for i in (0, n_streams - 1):
+        e = refdrive.PortEngine(seed=cs[i]["seed"])
+        ref = cases.run_case(e, cs[i], clip=clips[i]); e.close()
+        same, err, snr = cases.compare(runs[0][i], ref)
+        assert same, (i, err, snr)
