@@ -25,9 +25,9 @@ namespace bs {
 // the specialised transforms (fft_fast.cuh), by geometry
 #define BS_FAST_GEOMS(X) X(10, 3) X(9, 5) X(10, 5) X(11, 3) X(9, 1)
 #ifdef BS_HOSTEMU
-static bool fast_analyse_any(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, bool rotate) {
+static bool fast_analyse_any(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, bool rotate, float *E) {
   if (!fast_ok(g)) return false;
-#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { fast_analyse<LG, OUTER>(g, T, x, w, X, (cf *)sm, rotate); return true; }
+#define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { fast_analyse<LG, OUTER>(g, T, x, w, X, (cf *)sm, rotate, E); return true; }
   BS_FAST_GEOMS(X_)
 #undef X_
   return false;
@@ -86,7 +86,7 @@ static void dzero(void *p, size_t n, stream_t s) { cudaMemsetAsync(p, 0, n, s); 
 static void h2d(void *d, const void *h, size_t n, stream_t s) { cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s); }
 
 __global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                       const Window *windows, long long slot0, int nSlots, cf *specIn) {
+                                                       const Window *windows, long long slot0, int nSlots, cf *specIn, float *inEnergy) {
   extern __shared__ __align__(16) float sm[];
   int idx = blockIdx.x;
   const int c = idx % g.C; idx /= g.C;
@@ -98,13 +98,14 @@ __global__ void __launch_bounds__(256, 3) analysis_kernel(DevGeom g, DevTables T
   if (!(blocks[sd.blockBase + m].flags & kNew)) return;
   const Window w = windows[2 * (sd.blockBase + m) + which];
   cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * guard_pitch(g.B) + kGuard;
-  analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x, which == 1);
+  float *E = which == 0 ? inEnergy + (((size_t)s * nSlots + slot) * g.C + c) * guard_pitch(g.B) + kGuard : nullptr;   // (map_energy's layout)
+  analyse_window(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, sm, threadIdx.x, blockDim.x, which == 1, E);
 }
 
 // the same two kernels for the preset geometries (fft_fast.cuh): grid (slot, stream, {cur,prev} x channel) -- no index division
 template <int LG, int OUTER>
 __global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) analysis_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, const BlockRec *blocks,
-                                                                  const Window *windows, long long slot0, int nSlots, cf *specIn) {
+                                                                  const Window *windows, long long slot0, int nSlots, cf *specIn, float *inEnergy) {
   extern __shared__ __align__(16) float sm[];
   const int slot = blockIdx.x, s = blockIdx.y, which = blockIdx.z & 1, c = blockIdx.z >> 1;
   const StreamDev sd = streams[s];
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) analysis_
   if (!(blocks[sd.blockBase + m].flags & kNew)) return;
   const Window w = windows[2 * (sd.blockBase + m) + which];
   cf *X = specIn + ((((size_t)s * nSlots + slot) * 2 + which) * g.C + c) * guard_pitch(g.B) + kGuard;
-  fast_analyse<LG, OUTER>(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, (cf *)sm, which == 1);
+  float *E = which == 0 ? inEnergy + (((size_t)s * nSlots + slot) * g.C + c) * guard_pitch(g.B) + kGuard : nullptr;
+  fast_analyse<LG, OUTER>(g, T, sd.clip + (size_t)c * sd.clipLen, w, X, (cf *)sm, which == 1, E);
 }
 template <int LG, int OUTER>
 __global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) isynth_fast_kernel(DevGeom g, DevTables T, const StreamDev *streams, long long slot0, int nSlots,
@@ -127,10 +129,10 @@ __global__ void __launch_bounds__(kFastNT, (FastOcc<LG, OUTER>::ctas)) isynth_fa
 }
 // launchers: false = no specialised kernel for this geometry (or more streams than a grid dimension holds)
 static bool launch_analysis_fast(const DevGeom &g, const DevTables &T, int S, int nSlots, cudaStream_t q, const StreamDev *streams, const BlockRec *blocks,
-                                 const Window *windows, long long slot0, cf *specIn) {
+                                 const Window *windows, long long slot0, cf *specIn, float *inEnergy) {
   if (!fast_ok(g) || S > 65535) return false;
 #define X_(LG, OUTER) if (g.inner == (1 << LG) && g.outer == OUTER) { \
-    analysis_fast_kernel<LG, OUTER><<<dim3((unsigned)nSlots, (unsigned)S, (unsigned)(2 * g.C)), kFastNT, fast_smem_bytes<LG, OUTER>(), q>>>(g, T, streams, blocks, windows, slot0, nSlots, specIn); return true; }
+    analysis_fast_kernel<LG, OUTER><<<dim3((unsigned)nSlots, (unsigned)S, (unsigned)(2 * g.C)), kFastNT, fast_smem_bytes<LG, OUTER>(), q>>>(g, T, streams, blocks, windows, slot0, nSlots, specIn, inEnergy); return true; }
   BS_FAST_GEOMS(X_)
 #undef X_
   return false;
@@ -654,7 +656,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
           for (int c = 0; c < g.C; ++c) {
             cf *X = e->specIn + ((((size_t)s * nSlots + t) * 2 + which) * g.C + c) * guard_pitch(g.B) + kGuard;
             const float *x = sd.clip + (size_t)c * sd.clipLen; const Window w = e->dWindows[2 * (sd.blockBase + m) + which];
-            if (!e->fastFft || !fast_analyse_any(e->dg, e->dt, x, w, X, sm, which == 1)) analyse_window(e->dg, e->dt, x, w, X, sm, 0, 1, which == 1);
+            float *E = which == 0 ? st.inEnergy + (((size_t)s * nSlots + t) * g.C + c) * guard_pitch(g.B) + kGuard : nullptr;
+            if (!e->fastFft || !fast_analyse_any(e->dg, e->dt, x, w, X, sm, which == 1, E)) analyse_window(e->dg, e->dt, x, w, X, sm, 0, 1, which == 1, E);
           }
       }
     }
@@ -777,8 +780,8 @@ static int launch_chunk(bsb_engine *e, long long slot0, int nSlots, int nLive, i
     const unsigned nCta = (unsigned)((size_t)S * nSlots);
     if (twoStreams && e->backUsed[buf]) cudaStreamWaitEvent(qF, e->evBack[buf], 0);   // the chain that read this record buffer is done
     span("analysis_kernel", nNew * 2 * g.C, [&] {
-      if (!e->fastFft || !launch_analysis_fast(e->dg, e->dt, S, nSlots, q, e->dStreams, e->dBlocks, e->dWindows, slot0, e->specIn))
-        analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn); });
+      if (!e->fastFft || !launch_analysis_fast(e->dg, e->dt, S, nSlots, q, e->dStreams, e->dBlocks, e->dWindows, slot0, e->specIn, st.inEnergy))
+        analysis_kernel<<<nCta * 2 * g.C, nt, smA, q>>>(e->dg, e->dt, e->dStreams, e->dBlocks, e->dWindows, slot0, nSlots, e->specIn, st.inEnergy); });
     span("map_energy_kernel", nBlk * g.C, [&] {
       map_energy_kernel<<<nCta, nt, 0, q>>>(e->dg, e->dStreams, e->dBlocks, e->dBlocks2, slot0, nSlots, e->specIn, st); });
     // the smoothers: one launch over the whole chunk, one lane per (stream, block) (slicing the chunk so that the arrays stay

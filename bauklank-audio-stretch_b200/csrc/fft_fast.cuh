@@ -300,7 +300,7 @@ BS_HD void fast_fwd_pack(const DevGeom &g, const DevTables &T, const float *x, W
 
 // untangle of the forward transform: bins i and M-1-i from the complex transform's outputs (analyse_window's last loop)
 template <int LG, int OUTER>
-BS_HD void fast_fwd_untangle(const DevTables &T, const cf *Y /* natural order */, cf *X, bool rotate, int tid) {
+BS_HD void fast_fwd_untangle(const DevTables &T, const cf *Y /* natural order */, cf *X, bool rotate, float *E /* |X|^2 too, or nullptr */, int tid) {
   constexpr int M = FastGeom<LG, OUTER>::M, half = M >> 1, U = 3;
   constexpr bool whole = (half % (kFastNT * U)) == 0;   // every trip is full: nothing between the loads
   for (int p0 = tid; p0 < half; p0 += kFastNT * U) {
@@ -326,6 +326,7 @@ BS_HD void fast_fwd_untangle(const DevTables &T, const cf *Y /* natural order */
         xi_.im = pp + dI; xi_.re = qq + sR; xj_.im = pp - dI; xj_.re = sR - qq;
         if (rotate) { xi_ = rot_prev(xi_, ri[k]); xj_ = rot_prev(xj_, rj[k]); }
         X[i] = xi_; X[j] = xj_;
+        if (E) { E[i] = (xi_.im * xi_.im) + (xi_.re * xi_.re); E[j] = (xj_.im * xj_.im) + (xj_.re * xj_.re); }
       }
     }
   }
@@ -411,7 +412,7 @@ BS_HD void fast_mid_stages(const cf *tw, cf *buf0, cf *buf1) {
 
 // whole forward transform of one window of one channel; sm = 2 * fast_buf_elems cf (16-byte aligned)
 template <int LG, int OUTER>
-BS_HD void fast_analyse(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, cf *sm, bool rotate) {
+BS_HD void fast_analyse(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, cf *sm, bool rotate, float *E = nullptr) {
   using F = FastGeom<LG, OUTER>;
   constexpr int NB = FastBuf<LG, OUTER>::elems;
   cf *buf0 = sm, *buf1 = sm + NB;
@@ -422,7 +423,7 @@ BS_HD void fast_analyse(const DevGeom &g, const DevTables &T, const float *x, Wi
   using LL = typename StageOf<LG, OUTER, KL>::In;
   cf *src = (KL & 1) ? buf1 : buf0, *Y = (KL & 1) ? buf0 : buf1;
   BS_FAST_FORALL((fast_last<LG, OUTER, false, LL>(T.tw, T.otw, src, tid, [&](int k, float re, float im) { cf v; v.re = re; v.im = im; Y[k] = v; })))
-  BS_FAST_FORALL((fast_fwd_untangle<LG, OUTER>(T, Y, X, rotate, tid)))
+  BS_FAST_FORALL((fast_fwd_untangle<LG, OUTER>(T, Y, X, rotate, E, tid)))
 }
 
 // whole inverse transform of one channel's output spectrum, synthesis window applied (synth_frame)

@@ -328,7 +328,8 @@ BS_HD cf rot_prev(cf v, cf r) { cf o; o.re = (v.re * r.re) - (v.im * r.im); o.im
 // analysis of one window of one channel (W#35): window, zero-phase rotate, zero-pad, modified real FFT.
 // smem: 4*fft_pitch(M) floats.  `x` = channel base of the clip.
 BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, Window w, cf *X, float *sm, int tid, int nt,
-                          bool rotate = false /* store X[k] * specRot[k]: the S1 rotation of a "previous" spectrum, applied once here */) {
+                          bool rotate = false /* store X[k] * specRot[k]: the S1 rotation of a "previous" spectrum, applied once here */,
+                          float *E = nullptr /* [B]: also store |X[k]|^2, the block's input energies (map_energy then only sums them) */) {
   const int M = g.M, N = g.N, L = g.L, off = g.off, MP = fft_pitch(M);
   float *ar = sm, *ai = sm + MP, *br = sm + 2 * MP, *bi = sm + 3 * MP;
   // window * sample for the packed pair (2j, 2j+1): second half of the window first (zero-phase rotation), the first
@@ -404,6 +405,7 @@ BS_HD void analyse_window(const DevGeom &g, const DevTables &T, const float *x, 
       xi_.im = p + dI; xi_.re = q + sR; xj_.im = p - dI; xj_.re = sR - q;
       if (rotate) { xi_ = rot_prev(xi_, T.specRot[i]); xj_ = rot_prev(xj_, T.specRot[j]); }
       X[i] = xi_; X[j] = xj_;
+      if (E) { E[i] = (xi_.im * xi_.im) + (xi_.re * xi_.re); E[j] = (xj_.im * xj_.im) + (xj_.re * xj_.re); }
     }
   }
   BS_SYNC();
@@ -675,12 +677,17 @@ BS_HD void map_energy(const DevGeom &g, const BlockRec rec, const cf *inp, float
                       float *mapv, int tid, int nt) {
   const int C = CT > 0 ? CT : g.C, B = g.B;
   const bool mapped = rec.flags & kMapped, formants = rec.flags & kFormants;
+  const bool have = rec.flags & kNew;   // the block was analysed in this chunk: its input energies are in place already
   for (int k = tid; k < B; k += nt) {
     float e = 0.f;
     for (int c = 0; c < C; ++c) {
-      const cf v = inp[(size_t)c * guard_pitch(B) + k];
-      const float en = (v.im * v.im) + (v.re * v.re);
-      inEnergy[(size_t)c * guard_pitch(B) + k] = en;
+      float en;
+      if (have) en = inEnergy[(size_t)c * guard_pitch(B) + k];   // stored by the analysis of this block, same expression
+      else {
+        const cf v = inp[(size_t)c * guard_pitch(B) + k];
+        en = (v.im * v.im) + (v.re * v.re);
+        inEnergy[(size_t)c * guard_pitch(B) + k] = en;
+      }
       e = e + en;
     }
     if (mapped || formants) energy[k] = e;

@@ -361,10 +361,11 @@ class ClockSampler:
 def own_bytes(name, g):
     """HBM bytes per unit as THIS implementation moves them.  The term records written by
     preterms_kernel and read back by chain_kernel are an artefact of the design, not algorithmic traffic: see stage_model."""
-    L, H, B = g["L"], g["H"], g["B"]
+    L, H, B, C = g["L"], g["H"], g["B"], g.get("C", 2)
     table = {
-        "analysis_kernel": 4 * L + 8 * B,             # per (window, channel): L samples in, B complex bins out
-        "map_energy_kernel": 8 * B + 4 * B + 4 * B,   # per channel-block: spectrum in, input energy out, band energy + smoother input
+        "analysis_kernel": 4 * L + 8 * B + 2 * B,     # per (window, channel): L samples in, B complex bins out; the current window (one of
+                                                      # the two) also stores its B input energies
+        "map_energy_kernel": 4 * B + 8 * B // C,      # per channel-block: input energy in; per block: band energy + smoother input out
         "map_smooth_kernel": 4 * B * 8,               # per block: 4 sweeps over the smoothed array, read + write each
         "map_peaks_kernel": 8 * B + 8 * B,            # per block: energy + smoothed in, map out
         "map_fmapply_kernel": 4 * B + 8 * B,          # per channel-block: envelope in, input energy read + write
@@ -633,7 +634,7 @@ def main_gpu(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         eng0 = big[1]
-        geom = dict(L=eng0.blockSamples(), H=eng0.intervalSamples(), B=eng0.bands())
+        geom = dict(L=eng0.blockSamples(), H=eng0.intervalSamples(), B=eng0.bands(), C=GROUPS[engines[0][0]]["channels"])
         single_geom = len(engines) == 1
         sm = stage_model(geom)
 
