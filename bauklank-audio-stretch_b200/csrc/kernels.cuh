@@ -1,10 +1,13 @@
-// Device code of the stretch engine: five kernels per time-chunk of blocks
+// Device code of the stretch engine: the kernels of one time-chunk of blocks
 //
-//   analysis_kernel   (stream, block, {cur,prev}, channel)  window -> half-bin-shifted real FFT -> spectrum in HBM
+//   analysis_kernel   (stream, block, {cur,prev}, channel)  window -> half-bin-shifted real FFT -> spectrum in HBM (+ the current
+//                     window's input energies); analysis_fast_kernel<LG,OUTER> (fft_fast.cuh) for the preset geometries
 //   map stage         energy / smooth / peaks (/ freqest / fmsmooth / fmapply) kernels, see "map stage" below
 //   preterms_kernel   (stream, block)  per-bin coefficient records of the phase prediction (everything state-free)
-//   chain_kernel      one warp per stream: the bin-to-bin / block-to-block phase recurrence as a 32-block wavefront
-//   isynth_kernel     (stream, block, channel)  inverse FFT -> synthesis window -> frame in HBM
+//   chain_kernel<1,2> (chain.cuh)  the bin-to-bin / block-to-block phase recurrence as a wavefront over consecutive blocks of a
+//                     stream: a lane per block, 8 warps per CTA, relayed from CTA to CTA for long streams;
+//   chain_wide_kernel<3..8> (chain_wide.cuh)  the same with the channels of a block spread over lanes
+//   isynth_kernel     (stream, block, channel)  inverse FFT -> synthesis window -> frame in HBM; isynth_fast_kernel<LG,OUTER>
 //   ola_kernel        (stream, channel, output sample)  overlap-add of the frames in block order -> normalised output
 //
 // All arithmetic is f32 in the reference's operation order (compile with -fmad=false; IEEE div/sqrt), see the
