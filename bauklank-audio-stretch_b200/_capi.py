@@ -106,7 +106,7 @@ _cache = {}
 
 def load_library(path=None):
     """dlopen the engine and attach prototypes.  Raises if the shared object is missing (no fallback)."""
-    path = os.path.abspath(path or DEFAULT_LIB)
+    path = os.path.abspath(path or os.environ.get("BAUKLANK_STRETCH_LIB") or DEFAULT_LIB)   # (the variable: A/B builds, scripts/probe_wide.py)
     if path in _cache:
         return _cache[path]
     if not os.path.exists(path):
