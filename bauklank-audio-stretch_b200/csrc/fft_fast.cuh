@@ -81,10 +81,25 @@ template <int LG, int OUTER, int K = 0> struct FastSmem {
 };
 template <int LG, int OUTER> struct FastSmem<LG, OUTER, 8> { static constexpr int value = (1 << LG) * OUTER; };
 template <int LG, int OUTER> struct FastBuf { static constexpr int elems = (FastSmem<LG, OUTER>::value + 1) & ~1; };
-template <int LG, int OUTER> constexpr size_t fast_smem_bytes() { return 2 * (size_t)FastBuf<LG, OUTER>::elems * sizeof(cf); }
+// The second radix-4 pass of a radix-16 stage at sub-transform size 2^LGS takes 12 twiddles per work item that depend only on
+// the item's position iA in [0, 2^LGS): with 16 or 32 positions, a warp's lanes gather them from 8 or 16 places of the table --
+// one sector each, 12 loads per item -- although the whole stage uses 12 * 2^LGS values.  That stage keeps them in shared
+// memory ([jA][m][iA]: the positions of a row side by side, conflict-free, lanes of equal iA broadcast).
+template <int LG, int OUTER, int K = 0> struct TwCacheStage {   // the radix-16 stage (0-based, after the pack) that has the cache, or -1
+  using F = FastGeom<LG, OUTER>;
+  static constexpr bool here = K < F::nR16 && (F::lg0 + 4 * K) >= 4;
+  static constexpr int value = here ? K : TwCacheStage<LG, OUTER, K + 1>::value;
+};
+template <int LG, int OUTER> struct TwCacheStage<LG, OUTER, 4> { static constexpr int value = -1; };
+template <int LG, int OUTER> struct TwCache {
+  static constexpr int stage = TwCacheStage<LG, OUTER>::value;
+  static constexpr int lgs = stage < 0 ? 0 : FastGeom<LG, OUTER>::lg0 + 4 * stage, sets = 1 << lgs;
+  static constexpr int elems = stage < 0 ? 0 : 12 * sets;          // cf
+};
+template <int LG, int OUTER> constexpr size_t fast_smem_bytes() { return (2 * (size_t)FastBuf<LG, OUTER>::elems + TwCache<LG, OUTER>::elems) * sizeof(cf); }
 // CTAs per SM the kernels are compiled for: three where shared memory allows (80 registers), else what fits of 227 KB
 template <int LG, int OUTER> struct FastOcc {
-  static constexpr int bySmem = (int)(232448 / (2 * (size_t)FastBuf<LG, OUTER>::elems * sizeof(cf) + 1024));
+  static constexpr int bySmem = (int)(232448 / ((2 * (size_t)FastBuf<LG, OUTER>::elems + TwCache<LG, OUTER>::elems) * sizeof(cf) + 1024));
   static constexpr int ctas = bySmem >= 4 ? 4 : (bySmem < 1 ? 1 : bySmem);
 };
 
@@ -132,8 +147,8 @@ BS_HD void outer_point(float *xr, float *xi, const cf *w /* [OUTER-1] */) {
 }
 
 // ---- radix-16 stage: radix-4 passes at sub-transform sizes 2^LGS and 2^(LGS+2), fused in registers (pow2_ffts_t)
-template <int LG, int OUTER, bool INV, int LGS, class LIn, class LOut>
-BS_HD void fast_r16(const cf *tw, const cf *src, cf *dst, int tid) {
+template <int LG, int OUTER, bool INV, int LGS, class LIn, class LOut, bool CACHED = false>
+BS_HD void fast_r16(const cf *tw, const cf *src, cf *dst, int tid, const cf *twc = nullptr /* CACHED: TwCache, filled by fast_fill_twcache */) {
   constexpr int lgStrideA = LG - LGS - 2, lgStrideB = lgStrideA - 2, lgPer = LG - 4, nItems = OUTER << lgPer, strideB = 1 << lgStrideB;
   static_assert(lgStrideB >= 0, "radix-16 stage does not fit");
   for (int idx = tid; idx < nItems; idx += kFastNT) {
@@ -157,7 +172,9 @@ BS_HD void fast_r16(const cf *tw, const cf *src, cf *dst, int tid) {
     for (int jA = 0; jA < 4; ++jA) {
       // iB = iA + (jA << LGS): tw[iB << lgStrideB], tw[2 iB << lgStrideB], tw[3 iB << lgStrideB] = constant offsets from tw[k iA << lgStrideB]
       constexpr int one = 1 << (LGS + lgStrideB);
-      const cf tB = pt[jA * one], tC = pt[(iA << lgStrideB) + 2 * jA * one], tD = pt[((2 * iA) << lgStrideB) + 3 * jA * one];
+      cf tB, tC, tD;
+      if constexpr (CACHED) { const cf *pc = twc + (jA * 3 << LGS) + iA; tB = pc[0]; tC = pc[1 << LGS]; tD = pc[2 << LGS]; }
+      else { tB = pt[jA * one]; tC = pt[(iA << lgStrideB) + 2 * jA * one]; tD = pt[((2 * iA) << lgStrideB) + 3 * jA * one]; }
       bfly4<INV>(vr[0][jA], vi[0][jA], vr[1][jA], vi[1][jA], vr[2][jA], vi[2][jA], vr[3][jA], vi[3][jA], tB, tC, tD);
 #pragma unroll
       for (int jB = 0; jB < 4; ++jB) {
@@ -204,8 +221,16 @@ BS_HD void fast_last(const cf *tw, const cf *otw, const cf *src, int tid, Emit &
       const int k = i + m * quarter;
       float xr[OUTER], xi[OUTER];
       cf w[OUTER > 1 ? OUTER - 1 : 1];
+      if constexpr (OUTER > 1 && ((OUTER - 1) & 1) == 0) {   // the bin's outer twiddles lie side by side: 16 bytes at a time
 #pragma unroll
-      for (int s = 1; s < OUTER; ++s) w[s - 1] = otw[(size_t)k * (OUTER - 1) + (s - 1)];
+        for (int h = 0; h < (OUTER - 1) / 2; ++h) {
+          const f4 v = ((const f4 *)otw)[(size_t)k * ((OUTER - 1) / 2) + h];
+          w[2 * h].re = v.x; w[2 * h].im = v.y; w[2 * h + 1].re = v.z; w[2 * h + 1].im = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int s = 1; s < OUTER; ++s) w[s - 1] = otw[(size_t)k * (OUTER - 1) + (s - 1)];
+      }
 #pragma unroll
       for (int s = 0; s < OUTER; ++s) { xr[s] = vr[s][m]; xi[s] = vi[s][m]; }
       outer_point<INV, OUTER>(xr, xi, w);
@@ -384,13 +409,28 @@ BS_HD void fast_inv_untangle(const DevTables &T, const cf *X, cf *dst, int tid) 
   (void)put;
 }
 
+// the twiddle cache of TwCache's stage: entry (jA, m, iA) = tw[(m + 1) * ((iA << lgStrideB) + (jA << (LG - 4)))], the value fast_r16 reads
+template <int LG, int OUTER>
+BS_HD void fast_fill_twcache(const cf *tw, cf *twc, int tid) {
+  using C = TwCache<LG, OUTER>;
+  if constexpr (C::stage >= 0) {
+    constexpr int lgStrideB = LG - C::lgs - 4;
+    for (int idx = tid; idx < C::elems; idx += kFastNT) {
+      const int iA = idx & (C::sets - 1), jm = idx >> C::lgs, jA = jm / 3, m = jm - 3 * jA;
+      twc[idx] = tw[(m + 1) * ((iA << lgStrideB) + (jA << (LG - 4)))];
+    }
+  }
+}
+
 // ---- stage sequencing: stage K reads buffer (K & 1), writes the other one
 template <int LG, int OUTER, bool INV, int K>
 BS_HD void fast_mid_stage(const cf *tw, cf *buf0, cf *buf1, int tid) {
   using S = StageOf<LG, OUTER, K>;
   using Nx = StageOf<LG, OUTER, K + 1>;
   const cf *src = (K & 1) ? buf1 : buf0; cf *dst = (K & 1) ? buf0 : buf1;
-  if constexpr (S::isR16) fast_r16<LG, OUTER, INV, S::lgSize, typename S::In, typename Nx::In>(tw, src, dst, tid);
+  if constexpr (S::isR16 && TwCache<LG, OUTER>::stage == K)
+    fast_r16<LG, OUTER, INV, S::lgSize, typename S::In, typename Nx::In, true>(tw, src, dst, tid, buf0 + 2 * FastBuf<LG, OUTER>::elems);   // (buf1 = buf0 + elems)
+  else if constexpr (S::isR16) fast_r16<LG, OUTER, INV, S::lgSize, typename S::In, typename Nx::In>(tw, src, dst, tid);
   else fast_r4<LG, OUTER, INV, S::lgSize, typename S::In, typename Nx::In>(tw, src, dst, tid);
 }
 
@@ -417,7 +457,7 @@ BS_HD void fast_analyse(const DevGeom &g, const DevTables &T, const float *x, Wi
   constexpr int NB = FastBuf<LG, OUTER>::elems;
   cf *buf0 = sm, *buf1 = sm + NB;
   using L0 = typename StageOf<LG, OUTER, 0>::In;
-  BS_FAST_FORALL((fast_fwd_pack<LG, OUTER, L0>(g, T, x, w, buf0, tid)))
+  BS_FAST_FORALL((fast_fill_twcache<LG, OUTER>(T.tw, buf0 + 2 * NB, tid), fast_fwd_pack<LG, OUTER, L0>(g, T, x, w, buf0, tid)))
   fast_mid_stages<LG, OUTER, false>(T.tw, buf0, buf1);
   constexpr int KL = F::nStages - 1;
   using LL = typename StageOf<LG, OUTER, KL>::In;
@@ -433,7 +473,7 @@ BS_HD void fast_synth(const DevGeom &g, const DevTables &T, const cf *X, float *
   constexpr int NB = FastBuf<LG, OUTER>::elems;
   cf *buf0 = sm, *buf1 = sm + NB;
   using L0 = typename StageOf<LG, OUTER, 0>::In;
-  BS_FAST_FORALL((fast_inv_untangle<LG, OUTER, L0>(T, X, buf0, tid)))
+  BS_FAST_FORALL((fast_fill_twcache<LG, OUTER>(T.tw, buf0 + 2 * NB, tid), fast_inv_untangle<LG, OUTER, L0>(T, X, buf0, tid)))
   fast_mid_stages<LG, OUTER, true>(T.tw, buf0, buf1);
   constexpr int KL = F::nStages - 1;
   using LL = typename StageOf<LG, OUTER, KL>::In;
