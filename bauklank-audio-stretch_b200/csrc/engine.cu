@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) carry_kernel(DevGeom g, const StreamDev *
 
 // warps per chain CTA: as many as the chunk can use, the kernel was compiled for, and shared memory holds
 static int chain_warps(int C, int longStep, int nSlots) {
-  int w = std::max(1, std::min(kChainWarps, (nSlots + 31) / 32));
+  int w = std::max(1, std::min(kChainWarpsUsed, (nSlots + 31) / 32));
   while (w > 1 && chain_smem_bytes(C, longStep, w) > (size_t)200 * 1024) --w;
   return w;
 }
@@ -1151,7 +1151,10 @@ int bsb_commit(bsb_engine *e, int chunkBlocks) {
   // once when every stream's wavefront is relayed across several CTAs
   e->wideWarps = e->dg.incremental ? 1 : wide_warps_for(S);   // (the shim walks one block at a time)
   const int perPass = chain_pass_blocks(g.C, g.longStep, 1 << 20, e->wideWarps);
-  const int cap = std::min(chain_capacity(e), 1024);   // (more CTAs in flight than that only lengthen the queue of waiting ones)
+#ifndef BS_CHAIN_CTA_CAP
+#define BS_CHAIN_CTA_CAP 1024
+#endif
+  const int cap = std::min(chain_capacity(e), BS_CHAIN_CTA_CAP);   // (more CTAs in flight than that only lengthen the queue of waiting ones)
   size_t allocSlots = (size_t)S * chunkBlocks;
   const bool relayOk = autoChunk && chunkBlocks >= perPass && !e->dg.incremental;
   if (relayOk) {
