@@ -1138,11 +1138,16 @@ BS_HD void preterms_block(const DevGeom &g, const DevTables &T, const BlockRec r
     // whole sectors / lines, one 16-byte piece per thread.  The threads walk the staging area piece by piece INCLUDING the
     // padding piece(s) of every row (which they skip): consecutive threads then read consecutive pieces -- conflict-free --
     // where a walk over the stored pieces only (6 of every 7) had two threads of every eight on one bank group.
-    for (int i = tid; i < nOut * (NR / 4); i += nt) {
-      const int r = i / (NR / 4), f = i - r * (NR / 4);
-      if (f < NRP / 4) {
-        const f4 v = ((const f4 *)sm)[i];   // staged in stored form: a plain copy
-        ((f4 *)(recRows + (size_t)(k0 + r) * rowStride))[f] = v;
+    {
+      const int P = NR / 4, dr = nt / P, df = nt - dr * P;   // (row, piece) of a thread's next element: no division per piece
+      int r = tid / P, f = tid - r * P;
+      for (int i = tid; i < nOut * P; i += nt) {
+        if (f < NRP / 4) {
+          const f4 v = ((const f4 *)sm)[i];   // staged in stored form: a plain copy
+          ((f4 *)(recRows + (size_t)(k0 + r) * rowStride))[f] = v;
+        }
+        r += dr; f += df;
+        if (f >= P) { f -= P; ++r; }
       }
     }
     BS_SYNC();
