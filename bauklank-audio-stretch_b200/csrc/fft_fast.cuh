@@ -246,6 +246,14 @@ BS_HD void fast_last(const cf *tw, const cf *otw, const cf *src, int tid, Emit &
 // window -- read as zero.  PAIR: both samples of a pair are valid together and 8-byte aligned (one 64-bit load).
 // Loads of U pairs are issued before the first one is used.
 struct PackCtx { const float *xs; const f4 *tab; int lo, span, jA, jC, off, cStart; bool none; };
+// the clip pointer comes out of a structure in global memory: say that the samples are in global memory too (LDG, not a generic LD)
+#ifdef BS_HOSTEMU
+BS_HD float pack_ld(const float *p) { return *p; }
+BS_HD f2 pack_ld2(const float *p) { return *(const f2 *)p; }
+#else
+BS_HD float pack_ld(const float *p) { return __ldg(p); }
+BS_HD f2 pack_ld2(const float *p) { const float2 v = __ldg((const float2 *)p); f2 r; r.x = v.x; r.y = v.y; return r; }
+#endif
 template <bool PAIR>
 BS_HD void fast_pack_load(const PackCtx &c, int j, float &x0, float &x1, f4 &t, bool &live) {
   const bool inA = j < c.jA;
@@ -256,10 +264,10 @@ BS_HD void fast_pack_load(const PackCtx &c, int j, float &x0, float &x1, f4 &t, 
   // no branch around the loads (the U pairs of a trip must be in flight together): a sample that is not there is read from
   // the nearest position that is (the caller has made sure there is one: span > 0) and replaced by zero
   const int hiM = c.lo + c.span - (PAIR ? 2 : 1);
-  if (PAIR) { const int ic = min(max(i, c.lo), hiM); const f2 v = *(const f2 *)(c.xs + ic); x0 = v0 ? v.x : 0.f; x1 = v0 ? v.y : 0.f; }
+  if (PAIR) { const int ic = min(max(i, c.lo), hiM); const f2 v = pack_ld2(c.xs + ic); x0 = v0 ? v.x : 0.f; x1 = v0 ? v.y : 0.f; }
   else {
     const bool v1 = live && !c.none && (unsigned)(i + 1 - c.lo) < (unsigned)c.span;
-    const float a = c.xs[min(max(i, c.lo), hiM)], b = c.xs[min(max(i + 1, c.lo), hiM)];
+    const float a = pack_ld(c.xs + min(max(i, c.lo), hiM)), b = pack_ld(c.xs + min(max(i + 1, c.lo), hiM));
     x0 = v0 ? a : 0.f; x1 = v1 ? b : 0.f;
   }
 }
