@@ -356,7 +356,10 @@ static int chain_warps(int C, int longStep, int nSlots) {
 template <int C>
 static void launch_chain(int S, int warps, size_t smem, cudaStream_t q, const DevGeom &g, const DevTables &T, const StreamDev *streams, const BlockRec *blocks,
                          const BlockRec2 *blocks2, long long slot0, int nSlots, const cf *specIn, cf *specOut, const StateDev &st, int ctas, int *prog, int *err) {
-  if constexpr (C <= 2) chain_kernel<C><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+  if constexpr (C <= 2) {
+    if (g.incremental) chain_kernel<C, true><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+    else chain_kernel<C, false><<<S * ctas, 32 * warps, smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
+  }
   else if (wide_split(warps)) chain_wide_kernel<C, true><<<S * ctas, wide_threads(warps), smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
   else chain_wide_kernel<C, false><<<S * ctas, wide_threads(warps), smem, q>>>(g, T, streams, blocks, blocks2, slot0, nSlots, specIn, specOut, st, ctas, prog, err);
 }
@@ -365,7 +368,10 @@ typedef void (*chain_launch_fn)(int, int, size_t, cudaStream_t, const DevGeom &,
 static const chain_launch_fn kChainLaunch[8] = {launch_chain<1>, launch_chain<2>, launch_chain<3>, launch_chain<4>,
                                                 launch_chain<5>, launch_chain<6>, launch_chain<7>, launch_chain<8>};
 template <int C> static cudaError_t chain_attr(size_t smem) {
-  if constexpr (C <= 2) return raise_smem_limit(chain_kernel<C>, (size_t)smem);
+  if constexpr (C <= 2) {
+    const cudaError_t ce = raise_smem_limit(chain_kernel<C, false>, (size_t)smem);
+    return ce != cudaSuccess ? ce : raise_smem_limit(chain_kernel<C, true>, (size_t)smem);
+  }
   else {
     const cudaError_t ce = raise_smem_limit(chain_wide_kernel<C, true>, (size_t)smem);
     return ce != cudaSuccess ? ce : raise_smem_limit(chain_wide_kernel<C, false>, (size_t)smem);
@@ -374,7 +380,7 @@ template <int C> static cudaError_t chain_attr(size_t smem) {
 template <int C> static int chain_occ(int threads, size_t smem, bool wideSplit) {
   int n = 0;
   cudaError_t ce;
-  if constexpr (C <= 2) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_kernel<C>, threads, smem);
+  if constexpr (C <= 2) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_kernel<C, false>, threads, smem);
   else if (wideSplit) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C, true>, threads, smem);
   else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, chain_wide_kernel<C, false>, threads, smem);
   if (ce != cudaSuccess) n = 1;
