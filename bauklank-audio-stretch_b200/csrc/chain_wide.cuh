@@ -12,6 +12,13 @@
 // both depend only on the step before -- S6(t) reads the S5 value of bin k + longStep = q - 1, written in step t - 1 -- so
 // they run side by side on twice the warps: warps [0, nW) do S6, warps [nW, 2 nW) S5 of the same (block, channel) lanes,
 // exchanging through the shared-memory rings under the barrier every step already has.
+// Why the twins never touch the same ring slot in the same step (the barrier at the top of a step is the only ordering between
+// them):  in step t a block is at S6 bin k and S5 bin q = k + longStep + 1.
+//   ringO (outputs, written by S6 at slot k): the S5 twin of the NEXT block reads its predecessor's slot q' = k - 1 of that
+//     column -- last step's write; this step's write goes to slot k, and slot k - 1 is not rewritten before step t + RO - 1.
+//   ringN (S5 values, written by S5 at slot q): S6 reads slots k + 1 = q - longStep and k + longStep = q - 1 -- older writes, the
+//     younger of them from step t - 1; RN > longStep keeps q, q - 1 and q - longStep apart.
+//   record stage of step t - 1: read by both twins before the barrier of step t, refilled by the copy issued after it.
 // A warp holds 32 / CPL blocks, a CTA of 8 warps 32 or 64: one or two record groups.  The rows a warp needs in a step
 // (its blocks' rows of one diagonal) are contiguous and arrive by cp.async.bulk into a ring of kWideStages stages; the
 // row pitch is 8 (mod 32) floats so that the lanes' field reads of different blocks fall into different banks.
