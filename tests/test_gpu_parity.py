@@ -292,7 +292,8 @@ def test_edge_cases_empty_tiny_and_ragged_on_gpu(bs):
 @pytest.mark.parametrize("channels,block,interval,split,sr", [
     (1, 1000, 250, 0, 32000), (3, 1536, 384, 1, 48000), (4, 2500, 700, 0, 44100), (5, 960, 240, 1, 96000),
     (6, 3000, 1000, 0, 48000), (7, 514, 130, 1, 22050), (8, 4800, 1920, 1, 48000), (2, 5762, 1441, 0, 48000),
-    (2, 1111, 277, 1, 48000), (2, 14000, 3500, 0, 96000)])
+    (2, 1111, 277, 1, 48000), (2, 14000, 3500, 0, 96000),
+    (8, 960, 720, 0, 48000), (3, 1024, 1000, 1, 48000), (2, 960, 720, 1, 48000)])   # interval > block / 2: longStep 1, the smallest rings
 def test_other_channel_counts_and_geometries_against_live_oracle(channels, block, interval, split, sr, bs):
     """Every chain_kernel<C> instantiation and the run-time FFT geometries (outer factors 1..8, odd block sizes that
     take the generic pack / overlap-add paths), each with transpose + formant shift, against the CPU oracle."""
