@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
       }
       return true;
     };
+    // a CTA may not leave while bulk copies into its shared memory are in flight (the relay's time-out path)
+    auto drain = [&]() { while (nWaited < nIssued) { mbar_wait(bars + (nWaited % NSTG), (nWaited / NSTG) & 1); ++nWaited; } };
     if (!request_tile(0)) { cp_async_commit(); cp_async_wait<0>(); return; }
     cp_async_commit();
     cp_async_wait<0>();
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(32 * kChainWarps, 2) chain_wide_kernel(DevGeom
       cf rotNxt; rotNxt.re = rotNxt.im = 0.f;
       if (!SPLIT || roleS5) { const int r = t + 1 + OA - jb * D; if (r >= 1 && r < B) rotNxt = specRot[r]; }
       const int q0 = t + OA;
-      if ((q0 % TL) == TL - kWideAhead) { const bool ok = request_tile(q0 / TL + 1); cp_async_commit(); if (!ok) return; }
+      if ((q0 % TL) == TL - kWideAhead) { const bool ok = request_tile(q0 / TL + 1); cp_async_commit(); if (!ok) { drain(); return; } }
       if ((q0 % TL) == TL - 1) cp_async_wait<0>();
       __syncthreads();
       if (SPLIT) fetch(t + NSTG - 1);                        // (both twins have read the stage of step t-1: the barrier)
